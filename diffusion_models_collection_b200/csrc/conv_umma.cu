@@ -1,0 +1,453 @@
+// Convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA.  Replaces nn.Conv2d 3x3 / 1x1 of /root/reference/models/unet.py:37,54,58,81,82,106,116,240
+// (and the nn.Linear GEMMs of models/dit.py:94-109) with bias + conditioning + residual (+ fused 1x1 shortcut as
+// extra K columns) in the epilogue.
+//
+// GEMM view:  D[M = B*Hout*Wout pixels, N = Cout] = A[M, K] * W[N, K]^T,  K = sum_src taps * C_src.
+//   * A is never materialised (no im2col buffer): for K-block (source s, tap (dh,dw), 64-channel chunk c) the
+//     128 x 64 bf16 A tile is ONE tiled 4-D TMA box {64 ch, BW, BH, BNIMG} over the NHWC tensor, shifted by the tap
+//     offset; TMA zero-fills the out-of-image halo (= conv padding) and strided (stride-2) convs use the tensor
+//     map's element strides.  The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle,
+//     i.e. exactly the K-major SWIZZLE_128B operand layout tcgen05.mma consumes.
+//   * W is a bf16 [Cout_pad, Ktot] matrix (K ordered like the K-blocks), loaded as {64, BN} boxes.
+//   * One CTA per SM, persistent over output tiles (128 pixels x BN channels), warp-specialised:
+//       warp 0 lane 0 : TMA producer          (smem ring of NST stages, full/empty mbarriers)
+//       warp 1 lane 0 : tcgen05.mma issuer    (UMMA 128 x BN x 16, fp32 accumulate, 2 TMEM accumulators)
+//       warp 2        : TMEM allocator
+//       warps 4..7    : epilogue: tcgen05.ld -> +bias +cond +residual -> GroupNorm partial sums -> bf16 NHWC
+//                       (or fp32 NCHW for the model head), overlapped with the next tile's MMAs.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <new>
+
+namespace dmc {
+
+constexpr int TILE_M = 128;
+constexpr int KB = 64;  // K elements per block = 128 bytes of bf16 = one swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * KB * 2;
+
+struct ConvKParams {
+  int nseg;
+  int seg_taps[3];
+  int seg_chunks[3];
+  int seg_kb_end[3];  // cumulative K-block count
+  signed char dh[3][9];
+  signed char dw[3][9];
+  int stride;
+  int BW, BH, BNIMG;
+  int tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles, num_kb;
+  int B, Hout, Wout;     // iteration space (output pixels per image = Hout*Wout)
+  int out_H, out_W;      // stored output tensor spatial dims
+  int oscale, ooff_h, ooff_w;
+  int Cout;
+  const float* bias;
+  const float* cond;
+  int cond_stride;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  float* out_nchw;
+  float* stats;
+};
+
+struct ConvPrepared {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB;
+  ConvKParams kp;
+  int BN;
+  int grid;
+  size_t smem;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int B_STAGE_BYTES = BN * KB * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int NST = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr size_t SMEM = static_cast<size_t>(NST) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int NST = Cfg::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NST;
+  uint64_t* tfull_bar = empty_bar + NST;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.nseg > 1) tma_prefetch_desc(&tmA1);
+    if (p.nseg > 2) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int ti = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW * p.stride, h0 = th * p.BH * p.stride, n0 = ti * p.BNIMG;
+        int seg = 0, kb_in_seg = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int stage = it % NST;
+          const uint32_t phase = (it / NST) & 1u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          const int chunks = p.seg_chunks[seg];
+          const int tap = kb_in_seg / chunks, chunk = kb_in_seg % chunks;
+          const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+          tma_load_4d(sa, tm, &full_bar[stage], chunk * KB, w0 + p.dw[seg][tap], h0 + p.dh[seg][tap], n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+          if (++kb_in_seg == p.seg_taps[seg] * chunks) {
+            ++seg;
+            kb_in_seg = 0;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1u;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int stage = it % NST;
+          const uint32_t phase = (it / NST) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;             // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;      // tile row == TMEM lane
+    const int ppi = p.BW * p.BH;        // pixels per image inside one tile
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1u;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int ti = m_tile / (p.tiles_w * p.tiles_h);
+      const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / ppi;
+      const int n = ti * p.BNIMG + ni;
+      const int oh = (th * p.BH + hi) * p.oscale + p.ooff_h;
+      const int ow = (tw * p.BW + wi) * p.oscale + p.ooff_w;
+      const bool valid = n < p.B;
+      const size_t pix = (static_cast<size_t>(n) * p.out_H + oh) * p.out_W + ow;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_wait();
+        const int cg = n_tile * BN + c0;  // first global output channel of this chunk
+        if (cg >= p.Cout) continue;       // padded weight rows (warp-uniform)
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.out_nchw != nullptr) {
+          // model head: few real channels, fp32 NCHW, coalesced along W across the warp
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = cg + j;
+              if (c < p.Cout) {
+                float o = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
+                p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+              }
+            }
+          }
+          continue;
+        }
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.cond != nullptr && valid) {
+          const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(c4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u = __ldg(r4 + j);
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 f = unpack_bf16x2(w[k]);
+              v[8 * j + 2 * k] += f.x;
+              v[8 * j + 2 * k + 1] += f.y;
+            }
+          }
+        }
+        if (p.stats != nullptr) {
+          // GroupNorm partial sums of the OUTPUT per (image, 8-channel block): reduce over the rows of this warp
+          // that belong to the same image (32 when ppi >= 32, else 16-lane halves), one atomic pair per block.
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            float s = 0.f, ss = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s += v[8 * b + j];
+                ss = fmaf(v[8 * b + j], v[8 * b + j], ss);
+              }
+            }
+#pragma unroll
+            for (int o = 8; o; o >>= 1) {
+              s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+              ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+            }
+            if (ppi >= 32) {
+              s += __shfl_xor_sync(0xFFFFFFFFu, s, 16);
+              ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 16);
+            }
+            const bool writer = (ppi >= 32) ? (lane == 0) : ((lane & 15) == 0);
+            if (writer && valid) {
+              float* dst = p.stats + (static_cast<size_t>(n) * (p.Cout >> 3) + ((cg >> 3) + b)) * 2;
+              atomicAdd(dst, s);
+              atomicAdd(dst + 1, ss);
+            }
+          }
+        }
+        if (valid && p.out != nullptr) {
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* estr) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  DMC_REQUIRE(fn != nullptr, "conv: cuTensorMapEncodeTiled unavailable -- call dmc_init() on a CUDA 12+ driver");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMC_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+static int pick_bn(int cout_pad, int m_tiles) {
+  const int sms = num_sms();
+  const int cands[3] = {256, 128, 64};
+  for (int bn : cands)
+    if (cout_pad % bn == 0 && static_cast<long long>(m_tiles) * (cout_pad / bn) >= sms) return bn;
+  for (int i = 2; i >= 0; --i)
+    if (cout_pad % cands[i] == 0) return cands[i];
+  return 32;
+}
+
+int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
+  DMC_REQUIRE(d.nsrc >= 1 && d.nsrc <= 3, "conv: nsrc=%d", d.nsrc);
+  DMC_REQUIRE(d.stride == 1 || d.stride == 2, "conv: stride=%d", d.stride);
+  DMC_REQUIRE(d.up_phase >= -1 && d.up_phase <= 3, "conv: up_phase=%d", d.up_phase);
+  DMC_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0, "conv: empty input");
+  DMC_REQUIRE(d.Hin % d.stride == 0 && d.Win % d.stride == 0, "conv: odd spatial size with stride 2");
+  DMC_REQUIRE(d.weight && (d.out_bf16 || d.out_f32_nchw), "conv: null weight/output");
+  DMC_REQUIRE(d.Cout_pad % 32 == 0 && d.Cout <= d.Cout_pad, "conv: Cout_pad=%d must be a multiple of 32", d.Cout_pad);
+  if (d.out_bf16) DMC_REQUIRE(d.Cout % 32 == 0, "conv: bf16 NHWC output needs Cout %% 32 == 0 (got %d)", d.Cout);
+  if (d.stats) DMC_REQUIRE(d.out_bf16 != nullptr, "conv: stats need a bf16 output");
+
+  ConvPrepared* P = new (std::nothrow) ConvPrepared();
+  DMC_REQUIRE(P != nullptr, "conv: out of host memory");
+  ConvKParams& kp = P->kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.nseg = d.nsrc;
+  kp.stride = d.stride;
+  const int Hout = d.Hin / d.stride, Wout = d.Win / d.stride;
+  kp.B = d.B; kp.Hout = Hout; kp.Wout = Wout;
+  if (d.up_phase >= 0) {
+    DMC_REQUIRE(d.stride == 1, "conv: upsample phases need stride 1");
+    kp.oscale = 2; kp.ooff_h = d.up_phase >> 1; kp.ooff_w = d.up_phase & 1;
+    kp.out_H = 2 * Hout; kp.out_W = 2 * Wout;
+  } else {
+    kp.oscale = 1; kp.ooff_h = kp.ooff_w = 0; kp.out_H = Hout; kp.out_W = Wout;
+  }
+  // tile box over output pixels: 128 = BW * BH * BNIMG
+  int BW = std::min(Wout, TILE_M);
+  DMC_REQUIRE(TILE_M % BW == 0 && Wout % BW == 0, "conv: Wout=%d unsupported", Wout);
+  int BH = std::min(Hout, TILE_M / BW);
+  DMC_REQUIRE((TILE_M / BW) % BH == 0 && Hout % BH == 0, "conv: Hout=%d unsupported", Hout);
+  int BNIMG = TILE_M / (BW * BH);
+  kp.BW = BW; kp.BH = BH; kp.BNIMG = BNIMG;
+  kp.tiles_w = Wout / BW; kp.tiles_h = Hout / BH;
+  const int img_tiles = (d.B + BNIMG - 1) / BNIMG;
+  kp.num_m_tiles = img_tiles * kp.tiles_w * kp.tiles_h;
+
+  int kb = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    const int taps = d.src_taps[s], C = d.src_c[s];
+    DMC_REQUIRE(d.src[s] != nullptr, "conv: source %d is null", s);
+    DMC_REQUIRE(C > 0 && C % KB == 0, "conv: source %d has %d channels (need a multiple of 64)", s, C);
+    DMC_REQUIRE(taps == 9 || taps == 1 || (taps == 4 && d.up_phase >= 0), "conv: source %d taps=%d", s, taps);
+    kp.seg_taps[s] = taps;
+    kp.seg_chunks[s] = C / KB;
+    for (int t = 0; t < taps; ++t) {
+      int dh = 0, dw = 0;
+      if (taps == 9) { dh = t / 3 - 1; dw = t % 3 - 1; }
+      else if (taps == 4) { dh = (d.up_phase >> 1) - 1 + t / 2; dw = (d.up_phase & 1) - 1 + t % 2; }
+      kp.dh[s][t] = static_cast<signed char>(dh);
+      kp.dw[s][t] = static_cast<signed char>(dw);
+    }
+    kb += taps * (C / KB);
+    kp.seg_kb_end[s] = kb;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(d.Win), static_cast<cuuint64_t>(d.Hin),
+                          static_cast<cuuint64_t>(d.B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(d.Win) * C * 2,
+                             static_cast<cuuint64_t>(d.Hin) * d.Win * C * 2};
+    cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(BW * d.stride), static_cast<cuuint32_t>(BH * d.stride),
+                         static_cast<cuuint32_t>(BNIMG)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
+    if (encode_map(&P->tmA[s], d.src[s], 4, dims, strides, box, estr) != 0) { delete P; return -1; }
+  }
+  for (int s = d.nsrc; s < 3; ++s) P->tmA[s] = P->tmA[0];
+  kp.num_kb = kb;
+  if (kb * KB != d.Ktot) {
+    delete P;
+    DMC_REQUIRE(false, "conv: Ktot=%d does not match the sources (%d)", d.Ktot, kb * KB);
+  }
+
+  const int BN = pick_bn(d.Cout_pad, kp.num_m_tiles);
+  P->BN = BN;
+  kp.num_n_tiles = d.Cout_pad / BN;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Ktot), static_cast<cuuint64_t>(d.Cout_pad)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.Ktot) * 2};
+    cuuint32_t box[2] = {KB, static_cast<cuuint32_t>(BN)};
+    cuuint32_t estr[2] = {1, 1};
+    if (encode_map(&P->tmB, d.weight, 2, dims, strides, box, estr) != 0) { delete P; return -1; }
+  }
+  kp.Cout = d.Cout;
+  kp.bias = d.bias; kp.cond = d.cond; kp.cond_stride = d.cond_stride;
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
+  kp.out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
+  kp.out_nchw = d.out_f32_nchw;
+  kp.stats = d.stats;
+  P->grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
+  P->smem = BN == 256 ? ConvCfg<256>::SMEM : BN == 128 ? ConvCfg<128>::SMEM : BN == 64 ? ConvCfg<64>::SMEM : ConvCfg<32>::SMEM;
+  *out = P;
+  return 0;
+}
+
+void conv_release(ConvPrepared* p) { delete p; }
+
+template <int BN>
+static int launch_bn(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(ConvCfg<BN>::SMEM)));
+    attr_set = true;
+  }
+  conv_umma_kernel<BN><<<P->grid, 256, ConvCfg<BN>::SMEM, st>>>(P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv(const dmc_conv_desc& d, const ConvPrepared* P, cudaStream_t st) {
+  ConvKParams kp = P->kp;
+  kp.out_nchw = d.out_f32_nchw;  // the only re-bindable pointer (dmc_plan_rebind which=2)
+  switch (P->BN) {
+    case 256: return launch_bn<256>(P, kp, st);
+    case 128: return launch_bn<128>(P, kp, st);
+    case 64: return launch_bn<64>(P, kp, st);
+    default: return launch_bn<32>(P, kp, st);
+  }
+}
+
+}  // namespace dmc

@@ -1,0 +1,355 @@
+// Memory-bound kernels of the UNet forward: conditioning table, input convolution (fp32 NCHW -> bf16 NHWC),
+// GroupNorm statistics / apply(+SiLU, + channel concat), nearest 2x upsample.  All 128-bit vectorised.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dmc {
+
+// =============================================================================================
+// Conditioning: sinusoid -> Linear -> SiLU -> Linear -> SiLU -> all time_mlp projections (+ label table)
+// /root/reference/models/unet.py:18-25, 167-172, 40-48, 65-68, 256-260
+// =============================================================================================
+__global__ void __launch_bounds__(256) cond_hidden_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          float* __restrict__ h1, int half, int temb) {
+  extern __shared__ float emb[];  // 2*half
+  const int r = blockIdx.x;
+  const float tf = static_cast<float>(t[r]);  // int64 * fp32 promotes to fp32 (unet.py:23)
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float arg = __fmul_rn(tf, freqs[i]);
+    emb[i] = sinf(arg);
+    emb[half + i] = cosf(arg);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int K = 2 * half;
+  for (int j = blockIdx.y * nw + warp; j < temb; j += gridDim.y * nw) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(w1[static_cast<size_t>(j) * K + k], emb[k], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) {
+      float v = acc + b1[j];
+      h1[static_cast<size_t>(r) * temb + j] = v / (1.0f + expf(-v));  // SiLU feeding time_embed.3
+    }
+  }
+}
+
+// out[r, j] = act(b[j] + sum_k w[j, k] * in[r, k]);  act = SiLU when silu_out (the shared SiLU(t_emb) of :40-42)
+__global__ void __launch_bounds__(256) cond_linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out, int K,
+                                                          int N, int silu_out) {
+  const int r = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* row_in = in + static_cast<size_t>(r) * K;
+  for (int j = blockIdx.y * nw + warp; j < N; j += gridDim.y * nw) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(w[static_cast<size_t>(j) * K + k], row_in[k], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) {
+      float v = acc + b[j];
+      out[static_cast<size_t>(r) * N + j] = silu_out ? v / (1.0f + expf(-v)) : v;
+    }
+  }
+}
+
+// One warp per output column j keeps its weight row in registers and walks all R rows of SiLU(t_emb).
+template <int KPL>  // K / 32
+__global__ void __launch_bounds__(256) cond_project_kernel(const float* __restrict__ st, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* __restrict__ out, int R,
+                                                           int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (j >= N) return;
+  constexpr int K = KPL * 32;
+  float wr[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) wr[i] = w[static_cast<size_t>(j) * K + lane + 32 * i];
+  const float bj = b[j];
+  for (int r = 0; r < R; ++r) {
+    const float* s = st + static_cast<size_t>(r) * K;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) acc = fmaf(wr[i], s[lane + 32 * i], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) out[static_cast<size_t>(r) * N + j] = acc + bj;
+  }
+}
+
+__global__ void __launch_bounds__(256) cond_expand_kernel(const float* __restrict__ cond_t, const float* __restrict__ ytab,
+                                                          const int64_t* __restrict__ y, float* __restrict__ cond, int B,
+                                                          int ncols, int uniform_t, int num_classes) {
+  const int n4 = ncols >> 2;
+  const size_t total = static_cast<size_t>(B) * n4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / n4), c = static_cast<int>(i % n4);
+    float4 v = reinterpret_cast<const float4*>(cond_t + static_cast<size_t>(uniform_t ? 0 : n) * ncols)[c];
+    if (ytab != nullptr && y != nullptr) {
+      long long lab = y[n];
+      lab = lab < 0 ? 0 : (lab > num_classes ? num_classes : lab);  // torch.clamp(y, 0, num_classes), unet.py:257
+      float4 u = reinterpret_cast<const float4*>(ytab + static_cast<size_t>(lab) * ncols)[c];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    reinterpret_cast<float4*>(cond + static_cast<size_t>(n) * ncols)[c] = v;
+  }
+}
+
+int cond_num_launches(const dmc_cond_desc&) { return 4; }
+
+int launch_cond(const dmc_cond_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.t && d.freqs && d.w1 && d.b1 && d.w2 && d.b2 && d.wt_all && d.bt_all && d.scratch && d.cond,
+              "cond: null pointer argument");
+  DMC_REQUIRE(d.B > 0 && d.ncols % 4 == 0 && d.temb == 512, "cond: unsupported shape (B=%d ncols=%d temb=%d)", d.B,
+              d.ncols, d.temb);
+  const int R = d.uniform_t ? 1 : d.B;
+  float* h1 = d.scratch;
+  float* sil = d.scratch + static_cast<size_t>(R) * d.temb;
+  float* cond_t = d.scratch + 2 * static_cast<size_t>(R) * d.temb;
+  cond_hidden_kernel<<<dim3(R, 8), 256, 2 * d.half * sizeof(float), st>>>(d.t, d.freqs, d.w1, d.b1, h1, d.half, d.temb);
+  cond_linear_kernel<<<dim3(R, 8), 256, 0, st>>>(h1, d.w2, d.b2, sil, d.temb, d.temb, 1);
+  cond_project_kernel<16><<<(d.ncols + 7) / 8, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols);
+  size_t total = static_cast<size_t>(d.B) * (d.ncols / 4);
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  cond_expand_kernel<<<blocks, 256, 0, st>>>(cond_t, d.ytab, d.y, d.cond, d.B, d.ncols, d.uniform_t, d.num_classes);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// Stem: 3x3 conv with Cin <= 4 from fp32 NCHW straight to bf16 NHWC (models/unet.py:188, 263)
+// =============================================================================================
+constexpr int STEM_MAX_K = 36;
+
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                   int x_batch, int B, int Cin, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [K][Cout] transposed weights, then bias[Cout]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    int k = i / Cout, c = i % Cout;
+    sw[i] = w[static_cast<size_t>(c) * K + k];
+  }
+  float* sb = sw + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int vec_per_pix = Cout >> 3;
+  const size_t total = static_cast<size_t>(B) * H * W * vec_per_pix;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cb = static_cast<int>(i % vec_per_pix);
+    size_t pix = i / vec_per_pix;
+    const int ww = static_cast<int>(pix % W);
+    const int hh = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    const float* xin = x + static_cast<size_t>(n % x_batch) * Cin * H * W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[cb * 8 + j];
+    for (int ci = 0; ci < Cin; ++ci) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = hh + r - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = ww + s - 1;
+          if (iw < 0 || iw >= W) continue;
+          const float v = __ldg(xin + (static_cast<size_t>(ci) * H + ih) * W + iw);
+          const float* wk = sw + ((ci * 3 + r) * 3 + s) * Cout + cb * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wk[j], acc[j]);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+int launch_stem(const dmc_stem_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.x && d.weight && d.bias && d.out, "stem: null pointer argument");
+  DMC_REQUIRE(d.Cin * 9 <= STEM_MAX_K && d.Cout % 8 == 0 && d.x_batch > 0 && d.B > 0, "stem: unsupported shape");
+  size_t total = static_cast<size_t>(d.B) * d.H * d.W * (d.Cout / 8);
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  size_t smem = (static_cast<size_t>(d.Cin) * 9 * d.Cout + d.Cout) * sizeof(float);
+  stem_kernel<<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, reinterpret_cast<__nv_bfloat16*>(d.out), d.x_batch, d.B,
+                                         d.Cin, d.H, d.W, d.Cout);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// GroupNorm statistics: (sum, sumsq) per image per 8-channel block (fp32 atomics into a pre-zeroed buffer)
+// =============================================================================================
+constexpr int GN_SLAB = 128;  // pixels per CTA
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ src, float* __restrict__ stats, int HW,
+                                                       int C8 /* C/8 */, int rows /* blockDim / C8 */) {
+  extern __shared__ float red[];  // [rows][C8][2]
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * GN_SLAB;
+  const int p1 = min(p0 + GN_SLAB, HW);
+  const int cb = threadIdx.x % C8, r = threadIdx.x / C8;
+  float s = 0.f, ss = 0.f;
+  if (r < rows) {
+    for (int p = p0 + r; p < p1; p += rows) {
+      uint4 v = src[(static_cast<size_t>(n) * HW + p) * C8 + cb];
+      uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(u[j]);
+        s += f.x + f.y;
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+    red[(r * C8 + cb) * 2] = s;
+    red[(r * C8 + cb) * 2 + 1] = ss;
+  }
+  __syncthreads();
+  if (r == 0) {
+    for (int k = 1; k < rows; ++k) {
+      s += red[(k * C8 + cb) * 2];
+      ss += red[(k * C8 + cb) * 2 + 1];
+    }
+    float* dst = stats + (static_cast<size_t>(n) * C8 + cb) * 2;
+    atomicAdd(dst, s);
+    atomicAdd(dst + 1, ss);
+  }
+}
+
+int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.src && d.stats && d.B > 0 && d.HW > 0, "gn_stats: bad arguments");
+  DMC_REQUIRE(d.C % 8 == 0 && d.C / 8 <= 256, "gn_stats: C=%d unsupported", d.C);
+  const int C8 = d.C / 8;
+  const int rows = std::max(1, 256 / C8);
+  const int threads = rows * C8;
+  dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
+  gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads) * 2 * sizeof(float), st>>>(
+      reinterpret_cast<const uint4*>(d.src), d.stats, d.HW, C8, rows);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// GroupNorm apply (+SiLU) over the concatenation of up to two sources -> one bf16 NHWC tensor
+// =============================================================================================
+struct GnApplyArgs {
+  const uint4* src0;
+  const uint4* src1;
+  const float* stats0;
+  const float* stats1;
+  const float* gamma;
+  const float* beta;
+  uint4* out;
+  int HW, C0_8, C1_8, groups;
+  float eps;
+  int silu;
+};
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
+  extern __shared__ float sc[];  // scale[C], shift[C]
+  const int C8 = a.C0_8 + a.C1_8;
+  const int C = C8 * 8;
+  float* scale = sc;
+  float* shift = sc + C;
+  const int n = blockIdx.y;
+  const int gs8 = C8 / a.groups;  // 8-channel blocks per group
+  const float inv_cnt = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.HW));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = (c >> 3) / gs8;
+    float s = 0.f, ss = 0.f;
+    for (int b = g * gs8; b < (g + 1) * gs8; ++b) {
+      const float* p = (b < a.C0_8) ? a.stats0 + (static_cast<size_t>(n) * a.C0_8 + b) * 2
+                                    : a.stats1 + (static_cast<size_t>(n) * a.C1_8 + (b - a.C0_8)) * 2;
+      s += p[0];
+      ss += p[1];
+    }
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + a.eps);
+    const float gsc = rstd * a.gamma[c];
+    scale[c] = gsc;
+    shift[c] = a.beta[c] - mean * gsc;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * GN_SLAB;
+  const int p1 = min(p0 + GN_SLAB, a.HW);
+  const int nvec = (p1 - p0) * C8;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int p = p0 + v / C8, cb = v % C8;
+    uint4 in = (cb < a.C0_8) ? a.src0[(static_cast<size_t>(n) * a.HW + p) * a.C0_8 + cb]
+                             : a.src1[(static_cast<size_t>(n) * a.HW + p) * a.C1_8 + (cb - a.C0_8)];
+    uint32_t u[4] = {in.x, in.y, in.z, in.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(u[j]);
+      const int c = cb * 8 + 2 * j;
+      float y0 = fmaf(f.x, scale[c], shift[c]);
+      float y1 = fmaf(f.y, scale[c + 1], shift[c + 1]);
+      if (a.silu) {
+        y0 = silu_f(y0);
+        y1 = silu_f(y1);
+      }
+      o[j] = pack_bf16x2(y0, y1);
+    }
+    a.out[(static_cast<size_t>(n) * a.HW + p) * C8 + cb] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.nsrc == 1 || d.nsrc == 2, "gn_apply: nsrc=%d", d.nsrc);
+  DMC_REQUIRE(d.src[0] && d.stats[0] && d.gamma && d.beta && d.out, "gn_apply: null pointer argument");
+  const int C0 = d.src_c[0], C1 = d.nsrc == 2 ? d.src_c[1] : 0;
+  const int C = C0 + C1;
+  DMC_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && d.groups > 0 && (C / 8) % d.groups == 0,
+              "gn_apply: channels (%d + %d) must split into %d groups of a multiple of 8", C0, C1, d.groups);
+  if (d.nsrc == 2) DMC_REQUIRE(d.src[1] && d.stats[1], "gn_apply: second source missing");
+  GnApplyArgs a;
+  a.src0 = reinterpret_cast<const uint4*>(d.src[0]);
+  a.src1 = reinterpret_cast<const uint4*>(d.nsrc == 2 ? d.src[1] : d.src[0]);
+  a.stats0 = d.stats[0];
+  a.stats1 = d.nsrc == 2 ? d.stats[1] : d.stats[0];
+  a.gamma = d.gamma; a.beta = d.beta; a.out = reinterpret_cast<uint4*>(d.out);
+  a.HW = d.HW; a.C0_8 = C0 / 8; a.C1_8 = C1 / 8; a.groups = d.groups; a.eps = d.eps; a.silu = d.silu;
+  dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
+  gn_apply_kernel<<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(a);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// nearest 2x upsample, bf16 NHWC (models/unet.py:119)
+// =============================================================================================
+__global__ void __launch_bounds__(256) upsample_kernel(const uint4* __restrict__ src, uint4* __restrict__ out, int B, int H,
+                                                       int W, int C8) {
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cb = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int ow = static_cast<int>(pix % (2 * W));
+    const int oh = static_cast<int>((pix / (2 * W)) % (2 * H));
+    const size_t n = pix / (static_cast<size_t>(4) * W * H);
+    out[i] = src[((n * H + (oh >> 1)) * W + (ow >> 1)) * C8 + cb];
+  }
+}
+
+int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.src && d.out && d.C % 8 == 0 && d.B > 0, "upsample: bad arguments");
+  size_t total = static_cast<size_t>(d.B) * 4 * d.H * d.W * (d.C / 8);
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  upsample_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(d.src), reinterpret_cast<uint4*>(d.out), d.B, d.H,
+                                          d.W, d.C / 8);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dmc

@@ -1,0 +1,43 @@
+// Internal launch interface between the plan interpreter (plan.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "../../include/dmc.h"
+
+namespace dmc {
+
+// sched.cu
+int launch_step(bool ddpm, const dmc_step_desc& d, cudaStream_t st);
+int launch_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sa, const float* s1, float* out,
+                    int B, int n, cudaStream_t st);
+
+// elementwise.cu
+int launch_cond(const dmc_cond_desc& d, cudaStream_t st);
+int cond_num_launches(const dmc_cond_desc& d);
+int launch_stem(const dmc_stem_desc& d, cudaStream_t st);
+int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st);
+int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st);
+int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
+
+// attention.cu
+int launch_attention(const dmc_attn_desc& d, cudaStream_t st);
+
+// conv_umma.cu : the tcgen05 implicit-GEMM convolution.  `prepared` holds the TMA descriptors and tile geometry
+struct ConvPrepared;
+int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out);
+void conv_release(ConvPrepared* p);
+int launch_conv(const dmc_conv_desc& d, const ConvPrepared* p, cudaStream_t st);
+// conv_ref.cu : CUDA-core debug implementation of the same contract (tests only)
+int launch_conv_ref(const dmc_conv_desc& d, cudaStream_t st);
+
+// driver entry point for TMA descriptors, resolved by dmc_init()
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+
+}  // namespace dmc

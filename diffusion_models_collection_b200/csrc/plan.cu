@@ -1,0 +1,316 @@
+// C ABI (include/dmc.h): error plumbing, dmc_init, stateless scheduler entry points, and the "plan" interpreter that
+// replays one denoiser forward (or a forward + scheduler-step chain) as a fixed list of kernel launches.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dmc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_num_sms = 0;
+static EncodeTiledFn g_encode = nullptr;
+
+int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+EncodeTiledFn encode_tiled_fn() { return g_encode; }
+
+enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM };
+
+struct Op {
+  int kind;
+  union {
+    struct { void* ptr; size_t bytes; } memset_;
+    dmc_cond_desc cond;
+    dmc_stem_desc stem;
+    dmc_gn_stats_desc gn_stats;
+    dmc_gn_apply_desc gn_apply;
+    dmc_conv_desc conv;
+    dmc_attn_desc attn;
+    dmc_upsample_desc up;
+    dmc_step_desc step;
+  };
+  ConvPrepared* conv_prep;
+  double flops;  // algorithmic tensor FLOPs (GEMM-shaped ops)
+  double bytes;  // algorithmic HBM bytes (read inputs once + write outputs once)
+  Op() {
+    memset(static_cast<void*>(this), 0, sizeof(*this));
+    kind = -1;
+  }
+};
+
+}  // namespace dmc
+
+struct dmc_plan {
+  std::vector<dmc::Op> ops;
+};
+
+namespace dmc {
+
+static int run_op(const Op& op, cudaStream_t st) {
+  switch (op.kind) {
+    case OP_MEMSET: DMC_CUDA_OK(cudaMemsetAsync(op.memset_.ptr, 0, op.memset_.bytes, st)); return 0;
+    case OP_COND: return launch_cond(op.cond, st);
+    case OP_STEM: return launch_stem(op.stem, st);
+    case OP_GN_STATS: return launch_gn_stats(op.gn_stats, st);
+    case OP_GN_APPLY: return launch_gn_apply(op.gn_apply, st);
+    case OP_CONV: return op.conv.impl == 1 ? launch_conv_ref(op.conv, st) : launch_conv(op.conv, op.conv_prep, st);
+    case OP_ATTN: return launch_attention(op.attn, st);
+    case OP_UPSAMPLE: return launch_upsample(op.up, st);
+    case OP_DDIM: return launch_step(false, op.step, st);
+    case OP_DDPM: return launch_step(true, op.step, st);
+  }
+  set_error("plan: unknown op kind %d", op.kind);
+  return -1;
+}
+
+}  // namespace dmc
+
+using namespace dmc;
+
+extern "C" {
+
+const char* dmc_last_error(void) { return g_err; }
+int dmc_abi_version(void) { return DMC_ABI_VERSION; }
+
+int dmc_init(void) {
+  int dev = 0;
+  DMC_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DMC_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  DMC_REQUIRE(prop.major == 10, "dmc_init: device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major,
+              prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DMC_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DMC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "dmc_init: cuTensorMapEncodeTiled not found in the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return g_num_sms;
+}
+
+int dmc_ddim_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
+                  int32_t n_per_sample, const dmc_ddim_coef* coef_dev, const dmc_guidance* g, void* stream) {
+  DMC_REQUIRE(g != nullptr, "dmc_ddim_step: guidance is null");
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g};
+  return launch_step(false, d, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_ddpm_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
+                  int32_t n_per_sample, const dmc_ddpm_coef* coef_dev, const dmc_guidance* g, void* stream) {
+  DMC_REQUIRE(g != nullptr, "dmc_ddpm_step: guidance is null");
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g};
+  return launch_step(true, d, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp, const float* sqrt_1m_acp,
+                 float* x_t, int32_t B, int32_t n_per_sample, void* stream) {
+  return launch_q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, x_t, B, n_per_sample, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_plan_create(dmc_plan** out) {
+  DMC_REQUIRE(out != nullptr, "dmc_plan_create: null out");
+  *out = new (std::nothrow) dmc_plan();
+  DMC_REQUIRE(*out != nullptr, "dmc_plan_create: out of memory");
+  return 0;
+}
+
+int dmc_plan_destroy(dmc_plan* p) {
+  if (p == nullptr) return 0;
+  for (auto& op : p->ops)
+    if (op.conv_prep) conv_release(op.conv_prep);
+  delete p;
+  return 0;
+}
+
+int dmc_plan_run(dmc_plan* p, void* stream) {
+  DMC_REQUIRE(p != nullptr, "dmc_plan_run: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    int r = run_op(p->ops[i], st);
+    if (r != 0) return r;
+  }
+  return 0;
+}
+
+int dmc_plan_num_ops(const dmc_plan* p) { return p ? static_cast<int>(p->ops.size()) : -1; }
+int dmc_plan_op_kind(const dmc_plan* p, int32_t i) {
+  DMC_REQUIRE(p && i >= 0 && i < static_cast<int>(p->ops.size()), "dmc_plan_op_kind: bad index");
+  return p->ops[i].kind;
+}
+double dmc_plan_op_flops(const dmc_plan* p, int32_t i) {
+  return (p && i >= 0 && i < static_cast<int>(p->ops.size())) ? p->ops[i].flops : 0.0;
+}
+double dmc_plan_op_bytes(const dmc_plan* p, int32_t i) {
+  return (p && i >= 0 && i < static_cast<int>(p->ops.size())) ? p->ops[i].bytes : 0.0;
+}
+
+int dmc_plan_num_launches(const dmc_plan* p) {
+  if (!p) return -1;
+  int n = 0;
+  for (const auto& op : p->ops) n += (op.kind == OP_COND) ? cond_num_launches(op.cond) : 1;
+  return n;
+}
+
+double dmc_plan_gemm_flops(const dmc_plan* p) {
+  double f = 0;
+  if (p)
+    for (const auto& op : p->ops) f += op.flops;
+  return f;
+}
+
+int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr) {
+  DMC_REQUIRE(p && op_index >= 0 && op_index < static_cast<int>(p->ops.size()), "dmc_plan_rebind: bad op index");
+  Op& op = p->ops[op_index];
+  if (op.kind == OP_STEM && which == 0) { op.stem.x = static_cast<const float*>(ptr); return 0; }
+  if (op.kind == OP_COND && which == 0) { op.cond.t = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_COND && which == 1) { op.cond.y = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_CONV && which == 2 && op.conv.out_f32_nchw != nullptr && ptr != nullptr) {
+    op.conv.out_f32_nchw = static_cast<float*>(const_cast<void*>(ptr));
+    return 0;
+  }
+  set_error("dmc_plan_rebind: op %d (kind %d) has no binding %d", op_index, op.kind, which);
+  return -1;
+}
+
+int dmc_plan_time_ops(dmc_plan* p, void* stream, int32_t iters, float* ms_out, int32_t n_out) {
+  DMC_REQUIRE(p && ms_out && iters > 0 && n_out >= static_cast<int>(p->ops.size()), "dmc_plan_time_ops: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  DMC_CUDA_OK(cudaEventCreate(&e0));
+  DMC_CUDA_OK(cudaEventCreate(&e1));
+  int rc = 0;
+  for (size_t i = 0; i < p->ops.size() && rc == 0; ++i) {
+    rc = run_op(p->ops[i], st);  // warm
+    if (rc) break;
+    cudaEventRecord(e0, st);
+    for (int k = 0; k < iters && rc == 0; ++k) rc = run_op(p->ops[i], st);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("dmc_plan_time_ops: op %zu failed: %s", i, cudaGetErrorString(cudaGetLastError())); rc = -2; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms_out[i] = ms / iters;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+static int push(dmc_plan* p, const Op& op) {
+  p->ops.push_back(op);
+  return static_cast<int>(p->ops.size()) - 1;
+}
+
+int dmc_plan_add_memset(dmc_plan* p, void* ptr, size_t bytes) {
+  DMC_REQUIRE(p && ptr && bytes > 0, "dmc_plan_add_memset: bad arguments");
+  Op op;
+  op.kind = OP_MEMSET;
+  op.memset_.ptr = ptr;
+  op.memset_.bytes = bytes;
+  op.bytes = static_cast<double>(bytes);
+  return push(p, op);
+}
+
+int dmc_plan_add_cond(dmc_plan* p, const dmc_cond_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_cond: null argument");
+  Op op;
+  op.kind = OP_COND;
+  op.cond = *d;
+  op.bytes = 4.0 * (static_cast<double>(d->ncols) * d->temb + 2.0 * d->B * d->ncols);
+  return push(p, op);
+}
+
+int dmc_plan_add_stem(dmc_plan* p, const dmc_stem_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_stem: null argument");
+  Op op;
+  op.kind = OP_STEM;
+  op.stem = *d;
+  const double pix = static_cast<double>(d->B) * d->H * d->W;
+  op.bytes = pix * (4.0 * d->Cin + 2.0 * d->Cout);
+  op.flops = 2.0 * pix * d->Cout * d->Cin * 9;
+  return push(p, op);
+}
+
+int dmc_plan_add_gn_stats(dmc_plan* p, const dmc_gn_stats_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_gn_stats: null argument");
+  Op op;
+  op.kind = OP_GN_STATS;
+  op.gn_stats = *d;
+  op.bytes = 2.0 * d->B * d->HW * d->C;
+  return push(p, op);
+}
+
+int dmc_plan_add_gn_apply(dmc_plan* p, const dmc_gn_apply_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_gn_apply: null argument");
+  Op op;
+  op.kind = OP_GN_APPLY;
+  op.gn_apply = *d;
+  const int C = d->src_c[0] + (d->nsrc == 2 ? d->src_c[1] : 0);
+  op.bytes = 2.0 * 2.0 * d->B * d->HW * C;
+  return push(p, op);
+}
+
+int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_conv: null argument");
+  Op op;
+  op.kind = OP_CONV;
+  op.conv = *d;
+  if (d->impl == 0) {
+    int r = conv_prepare(*d, &op.conv_prep);
+    if (r != 0) return r;
+  } else {
+    DMC_REQUIRE(d->impl == 1, "dmc_plan_add_conv: impl=%d", d->impl);
+  }
+  const double opix = static_cast<double>(d->B) * (d->Hin / d->stride) * (d->Win / d->stride);
+  op.flops = 2.0 * opix * d->Cout * d->Ktot;
+  double in_bytes = 0;
+  for (int s = 0; s < d->nsrc; ++s) in_bytes += 2.0 * d->B * d->Hin * d->Win * d->src_c[s];
+  op.bytes = in_bytes + 2.0 * static_cast<double>(d->Cout_pad) * d->Ktot + opix * d->Cout * (d->out_bf16 ? 2.0 : 4.0) +
+             (d->residual ? 2.0 * opix * d->Cout : 0.0);
+  return push(p, op);
+}
+
+int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_attention: null argument");
+  Op op;
+  op.kind = OP_ATTN;
+  op.attn = *d;
+  op.flops = 4.0 * d->B * static_cast<double>(d->L) * d->L * d->C;  // QK^T and PV
+  op.bytes = 2.0 * d->B * d->L * 4.0 * d->C;
+  return push(p, op);
+}
+
+int dmc_plan_add_upsample(dmc_plan* p, const dmc_upsample_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_upsample: null argument");
+  Op op;
+  op.kind = OP_UPSAMPLE;
+  op.up = *d;
+  op.bytes = 2.0 * 5.0 * d->B * d->H * d->W * d->C;
+  return push(p, op);
+}
+
+static int add_step(dmc_plan* p, const dmc_step_desc* d, int kind) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_*_step: null argument");
+  Op op;
+  op.kind = kind;
+  op.step = *d;
+  const double n = static_cast<double>(d->B) * d->n_per_sample;
+  op.bytes = 4.0 * n * (3.0 + (d->eps_u ? 1.0 : 0.0) + (d->noise ? 1.0 : 0.0));
+  return push(p, op);
+}
+int dmc_plan_add_ddim_step(dmc_plan* p, const dmc_step_desc* d) { return add_step(p, d, OP_DDIM); }
+int dmc_plan_add_ddpm_step(dmc_plan* p, const dmc_step_desc* d) { return add_step(p, d, OP_DDPM); }
+
+}  // extern "C"

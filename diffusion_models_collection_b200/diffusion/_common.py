@@ -1,0 +1,120 @@
+"""Shared host logic of the DDPM / DDIM drop-ins: schedule tables (built with the reference's torch expressions on
+``device`` so that they are bit-equal to the reference's on the same device), the training-side helpers
+(q_sample / p_losses / _extract) and the glue that hands a sampling step to the fused CUDA kernels."""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+def make_betas(num_timesteps, beta_start, beta_end, beta_schedule, device):
+    # /root/reference/diffusion/ddpm.py:38-46, :73-82 (same expressions, same op order)
+    if beta_schedule == "linear":
+        return torch.linspace(beta_start, beta_end, num_timesteps, device=device)
+    if beta_schedule == "cosine":
+        s = 0.008
+        x = torch.linspace(0, num_timesteps, num_timesteps + 1, device=device)
+        acp = torch.cos(((x / num_timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+        acp = acp / acp[0]
+        return torch.clip(1 - (acp[1:] / acp[:-1]), 0.0001, 0.9999)
+    if beta_schedule == "quadratic":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_timesteps, device=device) ** 2
+    raise ValueError(f"Unknown beta schedule: {beta_schedule}")
+
+
+def quantile_rank(n, q):
+    """(lower rank, upper rank, lerp weight) of torch.quantile for an fp32 row of length n (fp32 rank arithmetic)."""
+    rank = (torch.tensor(float(q), dtype=torch.float32) * (n - 1)).item()
+    lo = int(math.floor(rank))
+    hi = int(math.ceil(rank))
+    w = float(torch.tensor(rank, dtype=torch.float32) - torch.tensor(float(lo), dtype=torch.float32))
+    return lo, hi, w
+
+
+def guidance(cfg_scale, clip_mode, n_per_sample=0, p_threshold=None):
+    g = _lib.Guidance()
+    g.cfg_scale = float(cfg_scale)
+    g.clip_mode = int(clip_mode)
+    if clip_mode == 2:
+        g.q_lo, g.q_hi, g.q_weight = quantile_rank(n_per_sample, p_threshold)
+    return g
+
+
+class DiffusionBase:
+    """Attributes and training-side methods shared by DDPM and DDIM (reference: diffusion/ddpm.py:27-149,
+    diffusion/ddim.py:27-152)."""
+
+    progress = True  # show the reference's tqdm bars
+
+    def _init_common(self, num_timesteps, beta_start, beta_end, beta_schedule, device):
+        self.num_timesteps = num_timesteps
+        self.device = device
+        self.betas = make_betas(num_timesteps, beta_start, beta_end, beta_schedule, device)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod)
+
+    # ---- training side -------------------------------------------------------------------------
+    def _extract(self, a, t, x_shape):
+        out = a.to(t.device)[t]
+        return out.reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
+
+    def q_sample(self, x_start, t, noise=None):
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        if x_start.is_cuda and x_start.dtype == torch.float32:
+            lib = _lib.load()
+            x0 = x_start.contiguous()
+            nz = noise.contiguous()
+            tt = t.to(device=x0.device, dtype=torch.long).contiguous()
+            sa = self.sqrt_alphas_cumprod.to(x0.device)
+            s1 = self.sqrt_one_minus_alphas_cumprod.to(x0.device)
+            out = torch.empty_like(x0)
+            B = x0.shape[0]
+            _lib.check(lib.dmc_q_sample(x0.data_ptr(), nz.data_ptr(), tt.data_ptr(), sa.data_ptr(), s1.data_ptr(),
+                                        out.data_ptr(), B, x0.numel() // B, _lib.stream_ptr()), "dmc_q_sample")
+            return out
+        raise _lib.DmcError("q_sample needs fp32 CUDA tensors: the B200 hot path has no CPU fallback")
+
+    def p_losses(self, model, x_start, t, y=None, noise=None, loss_type="l2"):
+        if loss_type not in ("l1", "l2", "huber"):
+            raise ValueError(f"Unknown loss type: {loss_type}")
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        x_noisy = self.q_sample(x_start, t, noise)
+        predicted = model(x_noisy, t, y)
+        if loss_type == "l1":
+            return F.l1_loss(noise, predicted)
+        if loss_type == "l2":
+            return F.mse_loss(noise, predicted)
+        return F.smooth_l1_loss(noise, predicted)
+
+    # ---- sampling glue ---------------------------------------------------------------------------
+    def _bar(self, it, desc, total=None):
+        if not self.progress:
+            return it
+        from tqdm import tqdm
+
+        return tqdm(it, desc=desc, total=total)
+
+    @staticmethod
+    def _require_cuda(t, what):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise _lib.DmcError(f"{what}: the sampler runs on a CUDA device only (no CPU fallback); got device "
+                                f"{getattr(t, 'device', None)}")
+
+    @staticmethod
+    def _eps_pair(model, img, t_batch, y, y_uncond):
+        """(eps_cond, eps_uncond): ONE 2B-image forward when the model is the native denoiser (identical weights, only
+        the label differs, nothing in the model mixes samples); otherwise two calls in the reference's order."""
+        fwd = getattr(model, "forward_cfg", None)
+        if fwd is not None:
+            return fwd(img, t_batch, y)
+        return model(img, t_batch, y), model(img, t_batch, y_uncond)

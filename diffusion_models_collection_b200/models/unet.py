@@ -1,0 +1,607 @@
+"""UNet denoiser drop-in: same constructor, attributes, parameter names/shapes (state_dict keys) and
+``forward(x, t, y=None)`` contract as /root/reference/models/unet.py:126-292 -- but the forward is a *plan* of
+hand-written sm_100a kernels replayed through the C ABI (include/dmc.h):
+
+  conditioning table (1 fused group of launches for time_embed + all 22 time_mlp/label_proj projections)
+  stem conv (fp32 NCHW -> bf16 NHWC), GroupNorm statistics / apply(+SiLU, + skip concat as one tensor),
+  every 3x3 / 1x1 convolution as a tcgen05 implicit GEMM fed by TMA with bias + conditioning + residual
+  + the 1x1 shortcut (extra K columns) fused, flash-style attention, head conv writing fp32 NCHW eps.
+
+There is no PyTorch / CPU fallback: the forward raises when the CUDA library or device is missing.
+Parameters stay ordinary ``nn.Parameter``s (optimizer, EMA, DDP and checkpoints see the reference layout); the
+bf16 K-major packed copies the kernels read are rebuilt whenever a parameter version changes.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..synth import unet_block_structure
+
+_ALIGN = 1024
+
+
+def _round_up(v, a=_ALIGN):
+    return (v + a - 1) // a * a
+
+
+class _Node(nn.Module):
+    """Anonymous container: gives parameters the reference's dotted names."""
+
+
+def _register(root: nn.Module, name: str, tensor: torch.Tensor):
+    parts = name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], nn.Parameter(tensor))
+
+
+class _Arena:
+    """First-fit offset allocator with coalescing; activations are reused as soon as their last reader has been
+    enqueued (stream order makes that safe)."""
+
+    def __init__(self):
+        self.free = [(0, 1 << 62)]
+        self.peak = 0
+
+    def alloc(self, nbytes):
+        nbytes = _round_up(nbytes)
+        for i, (off, size) in enumerate(self.free):
+            if size >= nbytes:
+                if size == nbytes:
+                    self.free.pop(i)
+                else:
+                    self.free[i] = (off + nbytes, size - nbytes)
+                self.peak = max(self.peak, off + nbytes)
+                return off, nbytes
+        raise MemoryError
+
+    def release(self, blk):
+        off, size = blk
+        self.free.append((off, size))
+        self.free.sort()
+        merged = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        self.free = merged
+
+
+class _Act:
+    """A bf16 NHWC activation [B, H, W, C] living in the plan workspace."""
+
+    __slots__ = ("blk", "C", "H", "W", "stats")
+
+    def __init__(self, blk, Cc, H, W):
+        self.blk, self.C, self.H, self.W, self.stats = blk, Cc, H, W, None
+
+
+class _PlanBuilder:
+    """Walks the UNet topology once (dry run -> workspace size, then for real) and records the op list."""
+
+    def __init__(self, net: "UNet", nimg, x_batch, has_y, uniform_t, conv_impl):
+        self.net, self.B, self.x_batch = net, nimg, x_batch
+        self.has_y, self.uniform_t, self.conv_impl = has_y, uniform_t, conv_impl
+        self.arena = _Arena()
+        self.stats_bytes = 0
+        self.ops = []  # (kind, dict)
+
+    # -- workspace ---------------------------------------------------------------------------------
+    def act(self, Cc, H, W):
+        return _Act(self.arena.alloc(self.B * H * W * Cc * 2), Cc, H, W)
+
+    def free(self, a: _Act):
+        self.arena.release(a.blk)
+
+    def stats_of(self, a: _Act):
+        """(offset into the stats arena) of the per-(image, 8-channel block) sums of `a`; emitted once per tensor."""
+        if a.stats is None:
+            a.stats = self.stats_bytes
+            self.stats_bytes += _round_up(self.B * (a.C // 8) * 2 * 4, 256)
+            self.ops.append(("gn_stats", dict(src=a, stats=a.stats)))
+        return a.stats
+
+    # -- layers --------------------------------------------------------------------------------------
+    def gn_apply(self, srcs, prefix, silu):
+        H, W = srcs[0].H, srcs[0].W
+        out = self.act(sum(s.C for s in srcs), H, W)
+        self.ops.append(("gn_apply", dict(srcs=list(srcs), stats=[self.stats_of(s) for s in srcs], prefix=prefix,
+                                          silu=silu, out=out)))
+        return out
+
+    def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
+             up_phase=-1):
+        Ho, Wo = H // stride, W // stride
+        if up_phase >= 0:
+            Ho, Wo = 2 * H, 2 * W
+        out = None if out_nchw else self.act(Cout, Ho, Wo)
+        self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), wname=wname, Cout=Cout, H=H, W=W, stride=stride,
+                                      bias=bias, cond_col=cond_col, residual=residual, out=out, out_nchw=out_nchw,
+                                      up_phase=up_phase)))
+        return out
+
+    def resblock(self, srcs, prefix, cout, cond_col):
+        cin = sum(s.C for s in srcs)
+        H, W = srcs[0].H, srcs[0].W
+        a1 = self.gn_apply(srcs, prefix + ".conv1.0", 1)
+        h1 = self.conv([a1], [9], prefix + ".conv1", cout, H, W, cond_col=cond_col)  # bias folded into cond table
+        self.free(a1)
+        a2 = self.gn_apply([h1], prefix + ".conv2.0", 1)
+        self.free(h1)
+        if cin != cout:  # 1x1 shortcut fused as extra K columns over the raw (un-normalised) inputs
+            out = self.conv([a2] + list(srcs), [9] + [1] * len(srcs), prefix + ".conv2+sc", cout, H, W,
+                            bias=prefix + ".conv2+sc")
+        else:
+            assert len(srcs) == 1
+            out = self.conv([a2], [9], prefix + ".conv2", cout, H, W, bias=prefix + ".conv2", residual=srcs[0])
+        self.free(a2)
+        return out
+
+    def attnblock(self, x, prefix):
+        an = self.gn_apply([x], prefix + ".norm", 0)
+        qkv = self.conv([an], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv")
+        self.free(an)
+        ao = self.act(x.C, x.H, x.W)
+        self.ops.append(("attention", dict(qkv=qkv, out=ao, L=x.H * x.W, C=x.C)))
+        self.free(qkv)
+        out = self.conv([ao], [1], prefix + ".proj", x.C, x.H, x.W, bias=prefix + ".proj", residual=x)
+        self.free(ao)
+        return out
+
+    def build(self):
+        net = self.net
+        H, W = net._hw
+        mc = net.model_channels
+        down, middle, up, out_ch = unet_block_structure(net._cfg())
+        self.ops.append(("cond", {}))
+        h = self.act(mc, H, W)
+        self.ops.append(("stem", dict(out=h)))
+        hs = [h]
+        col = 0
+
+        def run_entry(prefix, layers, h, srcs_first):
+            nonlocal col
+            cur = h
+            for j, l in enumerate(layers):
+                p = f"{prefix}.{j}"
+                if l[0] == "res":
+                    srcs = srcs_first if j == 0 else [cur]
+                    new = self.resblock(srcs, p, l[2], col)
+                    col += l[2]
+                elif l[0] == "attn":
+                    new = self.attnblock(cur, p)
+                elif l[0] == "down":
+                    new = self.conv([cur], [9], p + ".conv", l[1], cur.H, cur.W, stride=2, bias=p + ".conv")
+                elif l[0] == "up":
+                    upb = self.act(cur.C, 2 * cur.H, 2 * cur.W)
+                    self.ops.append(("upsample", dict(src=cur, out=upb)))
+                    new = self.conv([upb], [9], p + ".conv", l[1], 2 * cur.H, 2 * cur.W, bias=p + ".conv")
+                    self.free(upb)
+                else:
+                    continue
+                if j > 0:  # an intermediate of this entry (not a skip): dead once consumed
+                    self.free(cur)
+                cur = new
+            return cur
+
+        for i, layers in enumerate(down):
+            h = run_entry(f"down_blocks.{i}", layers, h, [h])
+            hs.append(h)
+        h = run_entry("middle_block", [l for l in middle], h, [h])  # its input is the last skip: stays alive
+        for i, layers in enumerate(up):
+            skip = hs.pop()
+            new = run_entry(f"up_blocks.{i}", layers, h, [h, skip])
+            self.free(h)     # previous up / middle output: only this block's concat read it
+            self.free(skip)  # popped skip: dead after the concat
+            h = new
+        assert not hs
+        a = self.gn_apply([h], "output.0", 1)
+        self.free(h)
+        self.conv([a], [9], "output.2", net.out_channels, H, W, bias="output.2", out_nchw=True)
+        self.free(a)
+        self.ncols = col
+        return self
+
+
+class UNet(nn.Module):
+    """UNet model for diffusion (reference: models/unet.py:126-292); see the module docstring."""
+
+    max_images_per_launch = 2048  # activations of larger batches are processed in chunks of this many images
+
+    def __init__(self, image_size: Tuple[int, int] = (32, 32), in_channels=3, model_channels=128, out_channels=3,
+                 num_res_blocks=2, attention_resolutions=(16, 8), dropout=0.1, channel_mult=(1, 2, 2, 2),
+                 num_classes=None, use_attention=True):
+        super().__init__()
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.num_classes = num_classes
+        self.use_attention = use_attention
+        self._hw = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
+        self._uniform_t = False
+        self._plans = {}
+        self._packed = None
+        self._packed_version = None
+        self._init_parameters()
+
+    # ------------------------------------------------------------------------------------------------
+    def _cfg(self):
+        return dict(image_size=self._hw, in_channels=self.in_channels, model_channels=self.model_channels,
+                    out_channels=self.out_channels, num_res_blocks=self.num_res_blocks,
+                    attention_resolutions=tuple(self.attention_resolutions), channel_mult=tuple(self.channel_mult),
+                    use_attention=self.use_attention)
+
+    def _init_parameters(self):
+        """Registers every tensor of the reference's state_dict with PyTorch's default init laws
+        (Kaiming-uniform a=sqrt(5) conv/linear, GroupNorm 1/0, Embedding N(0,1) with the padding row zeroed)."""
+        mc, temb = self.model_channels, self.model_channels * 4
+
+        def conv(name, cout, cin, k):
+            bound = 1.0 / math.sqrt(cin * k * k)
+            _register(self, name + ".weight", torch.empty(cout, cin, k, k).uniform_(-bound, bound))
+            _register(self, name + ".bias", torch.empty(cout).uniform_(-bound, bound))
+
+        def linear(name, cout, cin, bias=True):
+            bound = 1.0 / math.sqrt(cin)
+            _register(self, name + ".weight", torch.empty(cout, cin).uniform_(-bound, bound))
+            if bias:
+                _register(self, name + ".bias", torch.empty(cout).uniform_(-bound, bound))
+
+        def gn(name, c):
+            _register(self, name + ".weight", torch.ones(c))
+            _register(self, name + ".bias", torch.zeros(c))
+
+        linear("time_embed.1", temb, mc)
+        linear("time_embed.3", temb, temb)
+        if self.num_classes is not None:
+            w = torch.randn(self.num_classes + 1, temb)
+            w[0].zero_()
+            _register(self, "label_embed.weight", w)
+        conv("input_conv", mc, self.in_channels, 3)
+
+        def entry(prefix, layers):
+            for j, l in enumerate(layers):
+                p = f"{prefix}.{j}"
+                if l[0] == "res":
+                    gn(p + ".conv1.0", l[1])
+                    conv(p + ".conv1.2", l[2], l[1], 3)
+                    linear(p + ".time_mlp.1", l[2], temb)
+                    if self.num_classes is not None:
+                        linear(p + ".label_proj.1", l[2], temb, bias=False)
+                    gn(p + ".conv2.0", l[2])
+                    conv(p + ".conv2.3", l[2], l[2], 3)
+                    if l[1] != l[2]:
+                        conv(p + ".shortcut", l[2], l[1], 1)
+                elif l[0] == "attn":
+                    gn(p + ".norm", l[1])
+                    conv(p + ".qkv", 3 * l[1], l[1], 1)
+                    conv(p + ".proj", l[1], l[1], 1)
+                elif l[0] in ("down", "up"):
+                    conv(p + ".conv", l[1], l[1], 3)
+
+        down, middle, up, out_ch = unet_block_structure(self._cfg())
+        for i, layers in enumerate(down):
+            entry(f"down_blocks.{i}", layers)
+        entry("middle_block", middle)
+        for i, layers in enumerate(up):
+            entry(f"up_blocks.{i}", layers)
+        gn("output.0", out_ch)
+        conv("output.2", self.out_channels, out_ch, 3)
+
+    # ------------------------------------------------------------------------------------------------
+    # weight packing (one-time / on parameter change; plain torch ops -- not on the hot path)
+    # ------------------------------------------------------------------------------------------------
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device):
+        ver = (str(device), self._param_version())
+        if self._packed is not None and self._packed_version == ver:
+            return self._packed
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()}
+        down, middle, up, out_ch = unet_block_structure(self._cfg())
+        temb = self.model_channels * 4
+        W, Bv = {}, {}  # packed bf16 [Cout_pad, K] matrices and fp32 bias vectors by logical name
+
+        def pack3(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin], tap-major (r, s), channel-minor
+            return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+        wt, bt, wy = [], [], []
+
+        def entry(prefix, layers):
+            for j, l in enumerate(layers):
+                p = f"{prefix}.{j}"
+                if l[0] == "res":
+                    W[p + ".conv1"] = pack3(sd[p + ".conv1.2.weight"])
+                    wt.append(sd[p + ".time_mlp.1.weight"])
+                    bt.append(sd[p + ".time_mlp.1.bias"] + sd[p + ".conv1.2.bias"])
+                    if self.num_classes is not None:
+                        wy.append(sd[p + ".label_proj.1.weight"])
+                    if l[1] != l[2]:
+                        W[p + ".conv2+sc"] = torch.cat([pack3(sd[p + ".conv2.3.weight"]),
+                                                        sd[p + ".shortcut.weight"].reshape(l[2], l[1])], dim=1)
+                        Bv[p + ".conv2+sc"] = sd[p + ".conv2.3.bias"] + sd[p + ".shortcut.bias"]
+                    else:
+                        W[p + ".conv2"] = pack3(sd[p + ".conv2.3.weight"])
+                        Bv[p + ".conv2"] = sd[p + ".conv2.3.bias"]
+                elif l[0] == "attn":
+                    W[p + ".qkv"] = sd[p + ".qkv.weight"].reshape(3 * l[1], l[1])
+                    Bv[p + ".qkv"] = sd[p + ".qkv.bias"]
+                    W[p + ".proj"] = sd[p + ".proj.weight"].reshape(l[1], l[1])
+                    Bv[p + ".proj"] = sd[p + ".proj.bias"]
+                elif l[0] in ("down", "up"):
+                    W[p + ".conv"] = pack3(sd[p + ".conv.weight"])
+                    Bv[p + ".conv"] = sd[p + ".conv.bias"]
+
+        for i, layers in enumerate(down):
+            entry(f"down_blocks.{i}", layers)
+        entry("middle_block", middle)
+        for i, layers in enumerate(up):
+            entry(f"up_blocks.{i}", layers)
+        head = pack3(sd["output.2.weight"])
+        W["output.2"] = torch.cat([head, head.new_zeros(32 - head.shape[0], head.shape[1])], dim=0)
+        Bv["output.2"] = sd["output.2.bias"]
+
+        # one bf16 blob for all GEMM weights (1 KiB aligned slices: TMA needs 16 B), one fp32 blob for the rest
+        offs, total = {}, 0
+        for k, v in W.items():
+            offs[k] = total
+            total += _round_up(v.numel() * 2)
+        wblob = torch.zeros(total // 2, dtype=torch.bfloat16, device=device)
+        for k, v in W.items():
+            wblob[offs[k] // 2: offs[k] // 2 + v.numel()] = v.reshape(-1).to(torch.bfloat16)
+        wt_all = torch.cat(wt, dim=0).contiguous()
+        bt_all = torch.cat(bt, dim=0).contiguous()
+        ytab = None
+        if self.num_classes is not None:
+            wy_all = torch.cat(wy, dim=0)
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                ytab = (torch.nn.functional.silu(sd["label_embed.weight"]) @ wy_all.t()).contiguous()
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        half = self.model_channels // 2
+        # models/unet.py:20-22 -- exponent divisor (half - 1); computed with the reference's own expression
+        freqs = torch.exp(torch.arange(half, device=device) * -(math.log(10000) / (half - 1))).float().contiguous()
+        self._packed = dict(
+            sd=sd, wblob=wblob, woffs=offs, wshape={k: tuple(v.shape) for k, v in W.items()},
+            bias={k: v.contiguous() for k, v in Bv.items()}, wt_all=wt_all, bt_all=bt_all, ytab=ytab, freqs=freqs,
+            ncols=wt_all.shape[0], temb=temb,
+        )
+        self._packed_version = ver
+        for pl in self._plans.values():
+            pl.destroy()
+        self._plans = {}
+        return self._packed
+
+    # ------------------------------------------------------------------------------------------------
+    # plans
+    # ------------------------------------------------------------------------------------------------
+    def _get_plan(self, device, nimg, x_batch, has_y, uniform_t):
+        key = (str(device), nimg, x_batch, has_y, uniform_t)
+        pl = self._plans.get(key)
+        if pl is None:
+            pk = self._ensure_packed(device)
+            pl = _UNetPlan(self, pk, device, nimg, x_batch, has_y, uniform_t)
+            self._plans[key] = pl
+        return pl
+
+    def _run(self, x, t, y, cfg):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise _lib.DmcError("UNet.forward: CUDA tensors only -- the B200 hot path has no CPU / PyTorch fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError("the native UNet implements the inference forward only (sampling); "
+                                      "wrap calls in torch.no_grad() / model.eval()")
+        _lib.load()
+        device = x.device
+        self._ensure_packed(device)
+        Hh, Ww = self._hw
+        if x.dim() != 4 or x.shape[1] != self.in_channels or tuple(x.shape[2:]) != (Hh, Ww):
+            raise ValueError(f"UNet.forward: expected x of shape [B, {self.in_channels}, {Hh}, {Ww}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        if t.shape[0] != B or (y is not None and y.shape[0] != B):
+            raise ValueError("UNet.forward: t / y batch size mismatch")
+        x = x.contiguous().float()
+        t = t.to(device=device, dtype=torch.long).contiguous()
+        has_y = self.num_classes is not None and y is not None
+        if cfg and not has_y:
+            raise ValueError("forward_cfg needs a conditional model and labels")
+        if has_y:
+            y = y.to(device=device, dtype=torch.long).contiguous()
+        mult = 2 if cfg else 1
+        out = torch.empty((mult * B, self.out_channels, Hh, Ww), device=device, dtype=torch.float32)
+        cb = max(1, min(B, self.max_images_per_launch // mult))
+        with torch.cuda.device(device):
+            for s in range(0, B, cb):
+                n = min(cb, B - s)
+                pl = self._get_plan(device, mult * n, n, has_y, bool(self._uniform_t))
+                pl.run(x[s:s + n], t[s:s + n], y[s:s + n] if has_y else None, cfg,
+                       out[s:s + n], out[B + s:B + s + n] if cfg else None)
+        return out
+
+    def forward(self, x, t, y=None):
+        """eps = UNet(x, t, y): x fp32 [B, C, H, W], t int64 [B], y int64 [B] in [0, num_classes] (0 = null) or None."""
+        return self._run(x, t, y, cfg=False)
+
+    def forward_cfg(self, x, t, y):
+        """(eps(x, t, y), eps(x, t, 0)) computed as ONE batch of 2B images (the reference runs two full forwards,
+        diffusion/ddim.py:300-301; samples never interact inside the model, so this is the same arithmetic)."""
+        B = x.shape[0]
+        out = self._run(x, t, y, cfg=True)
+        return out[:B], out[B:]
+
+    def plan_info(self, batch, cfg=False, device=None):
+        """(plan, ops) for introspection / profiling: builds (or reuses) the plan for a batch of `batch` images."""
+        device = device or next(self.parameters()).device
+        _lib.load()
+        mult = 2 if cfg else 1
+        self._ensure_packed(torch.device(device))
+        return self._get_plan(torch.device(device), mult * batch, batch, self.num_classes is not None,
+                              bool(self._uniform_t))
+
+
+class _UNetPlan:
+    """Owns one dmc_plan (C side), its workspace and the small staging tensors of one (batch, mode) signature."""
+
+    def __init__(self, net: UNet, pk, device, nimg, x_batch, has_y, uniform_t):
+        lib = _lib.load()
+        self.lib = lib
+        self.nimg, self.x_batch, self.has_y = nimg, x_batch, has_y
+        conv_impl = int(os.environ.get("DMC_DEBUG_CONV_IMPL", "0"))
+        b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl).build()
+        self.workspace_bytes = b.arena.peak
+        self.stats_bytes = b.stats_bytes
+        Hh, Ww = net._hw
+        R = 1 if uniform_t else nimg
+        temb, ncols = pk["temb"], pk["ncols"]
+        assert ncols == b.ncols
+        self.ws = torch.empty(max(b.arena.peak, 16), dtype=torch.uint8, device=device)
+        self.stats = torch.empty(max(b.stats_bytes, 16), dtype=torch.uint8, device=device)
+        self.cond = torch.empty((nimg, ncols), dtype=torch.float32, device=device)
+        self.cond_scratch = torch.empty((2 * R * temb + R * ncols,), dtype=torch.float32, device=device)
+        self.t_stage = torch.zeros((nimg,), dtype=torch.long, device=device)
+        self.y_stage = torch.zeros((nimg,), dtype=torch.long, device=device) if has_y else None
+        self.eps = torch.empty((nimg, net.out_channels, Hh, Ww), dtype=torch.float32, device=device)
+        self.x_keepalive = None
+        handle = C.c_void_p()
+        _lib.check(lib.dmc_plan_create(C.byref(handle)), "dmc_plan_create")
+        self.handle = handle
+        self.op_names = []
+        wsp, stp = self.ws.data_ptr(), self.stats.data_ptr()
+        sd = pk["sd"]
+
+        def ap(a):
+            return wsp + a.blk[0]
+
+        def add(fn, desc, name):
+            idx = _lib.check(fn(handle, C.byref(desc)), name)
+            self.op_names.append(name)
+            return idx
+
+        if b.stats_bytes:
+            _lib.check(lib.dmc_plan_add_memset(handle, stp, b.stats_bytes), "memset")
+            self.op_names.append("memset.stats")
+        self.stem_idx = self.cond_idx = self.head_idx = -1
+        for kind, o in b.ops:
+            if kind == "cond":
+                d = _lib.CondDesc()
+                d.t, d.y = self.t_stage.data_ptr(), (self.y_stage.data_ptr() if has_y else None)
+                d.B, d.uniform_t = nimg, 1 if uniform_t else 0
+                d.num_classes = net.num_classes if net.num_classes is not None else 0
+                d.half, d.temb, d.ncols = net.model_channels // 2, temb, ncols
+                d.freqs = pk["freqs"].data_ptr()
+                d.w1, d.b1 = sd["time_embed.1.weight"].data_ptr(), sd["time_embed.1.bias"].data_ptr()
+                d.w2, d.b2 = sd["time_embed.3.weight"].data_ptr(), sd["time_embed.3.bias"].data_ptr()
+                d.wt_all, d.bt_all = pk["wt_all"].data_ptr(), pk["bt_all"].data_ptr()
+                d.ytab = pk["ytab"].data_ptr() if (has_y and pk["ytab"] is not None) else None
+                d.scratch, d.cond = self.cond_scratch.data_ptr(), self.cond.data_ptr()
+                self.cond_idx = add(lib.dmc_plan_add_cond, d, "cond")
+            elif kind == "stem":
+                d = _lib.StemDesc()
+                d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
+                d.Cin, d.H, d.W, d.Cout = net.in_channels, Hh, Ww, net.model_channels
+                d.weight, d.bias = sd["input_conv.weight"].data_ptr(), sd["input_conv.bias"].data_ptr()
+                d.out, d.stats = ap(o["out"]), None
+                self.stem_idx = add(lib.dmc_plan_add_stem, d, "input_conv")
+            elif kind == "gn_stats":
+                a = o["src"]
+                d = _lib.GnStatsDesc()
+                d.src, d.B, d.HW, d.C, d.stats = ap(a), nimg, a.H * a.W, a.C, stp + o["stats"]
+                add(lib.dmc_plan_add_gn_stats, d, "gn_stats")
+            elif kind == "gn_apply":
+                d = _lib.GnApplyDesc()
+                d.nsrc = len(o["srcs"])
+                for i, s in enumerate(o["srcs"]):
+                    d.src[i], d.src_c[i], d.stats[i] = ap(s), s.C, stp + o["stats"][i]
+                d.B, d.HW, d.groups = nimg, o["srcs"][0].H * o["srcs"][0].W, 8
+                d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
+                d.eps, d.silu, d.out = 1e-5, o["silu"], ap(o["out"])
+                add(lib.dmc_plan_add_gn_apply, d, o["prefix"])
+            elif kind == "conv":
+                d = _lib.ConvDesc()
+                d.nsrc = len(o["srcs"])
+                for i, s in enumerate(o["srcs"]):
+                    d.src[i], d.src_c[i], d.src_taps[i] = ap(s), s.C, o["taps"][i]
+                d.B, d.Hin, d.Win, d.stride, d.up_phase = nimg, o["H"], o["W"], o["stride"], o["up_phase"]
+                rows, K = pk["wshape"][o["wname"]]
+                d.weight = pk["wblob"].data_ptr() + pk["woffs"][o["wname"]]
+                d.Cout, d.Cout_pad, d.Ktot = o["Cout"], rows, K
+                d.bias = pk["bias"][o["bias"]].data_ptr() if o["bias"] is not None else None
+                if o["cond_col"] is not None:
+                    d.cond, d.cond_stride = self.cond.data_ptr() + 4 * o["cond_col"], ncols
+                d.residual = ap(o["residual"]) if o["residual"] is not None else None
+                if o["out_nchw"]:
+                    d.out_f32_nchw = self.eps.data_ptr()
+                else:
+                    d.out_bf16 = ap(o["out"])
+                d.stats, d.impl = None, conv_impl
+                idx = add(lib.dmc_plan_add_conv, d, o["wname"])
+                if o["out_nchw"]:
+                    self.head_idx = idx
+            elif kind == "attention":
+                d = _lib.AttnDesc()
+                d.qkv, d.out, d.B, d.L, d.heads, d.C = ap(o["qkv"]), ap(o["out"]), nimg, o["L"], 4, o["C"]
+                add(lib.dmc_plan_add_attention, d, "attention")
+            elif kind == "upsample":
+                d = _lib.UpsampleDesc()
+                d.src, d.out, d.B, d.H, d.W, d.C = ap(o["src"]), ap(o["out"]), nimg, o["src"].H, o["src"].W, o["src"].C
+                add(lib.dmc_plan_add_upsample, d, "upsample")
+        self.num_launches = lib.dmc_plan_num_launches(handle)
+        self.gemm_flops = lib.dmc_plan_gemm_flops(handle)
+
+    def run(self, x, t, y, cfg, out_a, out_b):
+        """x: [x_batch, C, H, W] fp32 (a contiguous slice), t/y: [x_batch]; out_a/out_b: destination slices."""
+        lib, n = self.lib, self.x_batch
+        if cfg:
+            self.t_stage[:n].copy_(t)
+            self.t_stage[n:].copy_(t)
+            self.y_stage[:n].copy_(y)  # second half stays 0 = null label (ddim.py:283 y_uncond)
+        else:
+            self.t_stage.copy_(t)
+            if self.has_y:
+                self.y_stage.copy_(y)
+        _lib.check(lib.dmc_plan_rebind(self.handle, self.stem_idx, 0, x.data_ptr()), "rebind x")
+        _lib.check(lib.dmc_plan_run(self.handle, _lib.stream_ptr()), "dmc_plan_run")
+        if cfg:
+            out_a.copy_(self.eps[:n])
+            out_b.copy_(self.eps[n:])
+        else:
+            out_a.copy_(self.eps)
+
+    def time_ops(self, iters=5):
+        n = self.lib.dmc_plan_num_ops(self.handle)
+        buf = (C.c_float * n)()
+        _lib.check(self.lib.dmc_plan_time_ops(self.handle, _lib.stream_ptr(), iters, buf, n), "dmc_plan_time_ops")
+        kinds = [_lib.OP_KINDS[self.lib.dmc_plan_op_kind(self.handle, i)] for i in range(n)]
+        flops = [self.lib.dmc_plan_op_flops(self.handle, i) for i in range(n)]
+        nbytes = [self.lib.dmc_plan_op_bytes(self.handle, i) for i in range(n)]
+        return [dict(name=self.op_names[i], kind=kinds[i], ms=buf[i], flops=flops[i], bytes=nbytes[i]) for i in range(n)]
+
+    def destroy(self):
+        if getattr(self, "handle", None) is not None:
+            self.lib.dmc_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.destroy()
+        except Exception:
+            pass

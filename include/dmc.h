@@ -1,0 +1,251 @@
+/*
+ * dmc.h -- C ABI of libdmc_b200.so: the B200 (sm_100a) denoising hot path of
+ * sunyzhi55/Diffusion_Models_Collection.
+ *
+ * The reference has no FFI / plugin interface of its own (it is pure PyTorch); this
+ * header is the drop-in boundary a maintainer binds with ctypes.  Each entry
+ * names the reference code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.  Every function returns 0 on success
+ *     (or a non-negative index where stated) and a negative value on error; dmc_last_error() returns
+ *     a thread-local message.  No C++ exception crosses the boundary.
+ *   - All data pointers are DEVICE pointers owned by the caller (torch tensors); the library never
+ *     allocates device memory.  `stream` is a cudaStream_t passed as void*; hot calls are
+ *     allocation-free, sync-free and CUDA-graph-capturable.
+ *   - Activations inside the model are bf16 NHWC; the model boundary (x, eps) is fp32 NCHW exactly
+ *     like the reference's `model(x, t, y)`.
+ */
+#ifndef DMC_H_
+#define DMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DMC_API __attribute__((visibility("default")))
+#else
+#define DMC_API
+#endif
+
+DMC_API const char* dmc_last_error(void);
+DMC_API int dmc_abi_version(void);
+/* Resolves the driver entry points (cuTensorMapEncodeTiled) and caches device properties.  Returns the
+ * SM count of the current device, or <0 when no sm_100 device is usable (the product path then
+ * fails loudly -- there is no CPU fallback). */
+DMC_API int dmc_init(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused scheduler steps  (stateless; replace ~80-190 ATen calls + 1 host sync per step)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-step scalar coefficients, computed by the host with the reference's own fp32 expressions. */
+typedef struct {
+  float sqrt_one_minus_a; /* sqrt(1 - a_t)                       diffusion/ddim.py:186,315 */
+  float sqrt_a;           /* sqrt(a_t)                            (true division, not rsqrt) */
+  float sqrt_a_next;      /* sqrt(a_next), a_next = 1 if t_next<0 diffusion/ddim.py:176-179,203 */
+  float dir_coef;         /* sqrt(clamp(1 - a_next - sigma^2, 0)) diffusion/ddim.py:201 */
+  float sigma;            /* eta * sqrt(clamp(..., 0))            diffusion/ddim.py:193-199 */
+} dmc_ddim_coef;
+
+typedef struct {
+  float sqrt_recip_a;   /* sqrt(1/a_t)          diffusion/ddpm.py:170-172 */
+  float sqrt_recipm1_a; /* sqrt(1/a_t - 1)      diffusion/ddpm.py:173-175 */
+  float coef1;          /* posterior_mean_coef1 diffusion/ddpm.py:184 */
+  float coef2;          /* posterior_mean_coef2 diffusion/ddpm.py:185 */
+  float noise_scale;    /* (t != 0) * exp(0.5 * posterior_log_variance_clipped[t])  diffusion/ddpm.py:218-220 */
+} dmc_ddpm_coef;
+
+/* Guidance / x0 post-processing shared by both samplers. */
+typedef struct {
+  float cfg_scale;   /* eps = eps_u + cfg_scale * (eps_c - eps_u) when eps_u != NULL   ddim.py:302 ddpm.py:292 */
+  int32_t clip_mode; /* 0 none, 1 clamp(x0,-1,1) (ddim.py:189-190), 2 dynamic threshold (ddim.py:320-325) */
+  int32_t q_lo;      /* dynamic threshold: indices into the ascending sort of |x0| ...                       */
+  int32_t q_hi;      /* ... and the lerp weight, exactly as torch.quantile derives them (fp32 rank)          */
+  float q_weight;
+} dmc_guidance;
+
+/* x_out = DDIM update of x.  Replaces DDIM.p_sample (diffusion/ddim.py:154-208) and the CFG / dynamic
+ * threshold block of DDIM.sample_with_cfg (:300-339).  x, eps_c, eps_u, noise, x_out: fp32 [B, n_per_sample]
+ * (eps_u and noise may be NULL; noise is required iff coef->sigma != 0).  coef is a DEVICE pointer
+ * (one table row per step, so a captured graph can walk it). */
+DMC_API int dmc_ddim_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out,
+                  int32_t B, int32_t n_per_sample, const dmc_ddim_coef* coef_dev, const dmc_guidance* g,
+                  void* stream);
+
+/* x_out = DDPM posterior sample.  Replaces DDPM.p_mean_variance + p_sample (diffusion/ddpm.py:151-220)
+ * and the CFG block of DDPM.sample_with_cfg (:289-324).  noise is always read (the reference draws it
+ * at every step, including t == 0 where noise_scale is 0). */
+DMC_API int dmc_ddpm_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out,
+                  int32_t B, int32_t n_per_sample, const dmc_ddpm_coef* coef_dev, const dmc_guidance* g,
+                  void* stream);
+
+/* x_t = sqrt_acp[t_n] * x0 + sqrt_1m_acp[t_n] * noise with per-sample t (training).  Replaces q_sample
+ * (diffusion/ddpm.py:84-104, ddim.py:87-107). */
+DMC_API int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
+                 const float* sqrt_1m_acp, float* x_t, int32_t B, int32_t n_per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Denoiser forward as a "plan": an ordered list of kernel launches with all pointers, shapes and TMA
+ * descriptors resolved once per (model, batch size, workspace).  One dmc_plan_run() == one
+ * model(x, t, y) call of the reference (models/unet.py:243-292, models/dit.py:263-295).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dmc_plan dmc_plan;
+
+DMC_API int dmc_plan_create(dmc_plan** out);
+DMC_API int dmc_plan_destroy(dmc_plan* p);
+DMC_API int dmc_plan_run(dmc_plan* p, void* stream);
+/* number of kernel launches (and memsets) one dmc_plan_run() performs */
+DMC_API int dmc_plan_num_launches(const dmc_plan* p);
+/* algorithmic tensor-core FLOPs (2*M*N*K summed over GEMM-shaped ops, real channels only) per run */
+DMC_API double dmc_plan_gemm_flops(const dmc_plan* p);
+/* Re-point one external binding of op `op_index` (returned by dmc_plan_add_*):
+ *   which = 0: primary input  (stem: x, cond: t)     which = 1: secondary input (cond: y, may be NULL)
+ *   which = 2: primary output (conv: out_f32_nchw)                                                     */
+DMC_API int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr);
+/* Per-op device timing: runs every op `iters` times between CUDA events on `stream`, writes the average
+ * milliseconds per op into ms_out[num ops].  Debug / profiling aid used by bench.py's roofline leg. */
+DMC_API int dmc_plan_time_ops(dmc_plan* p, void* stream, int32_t iters, float* ms_out, int32_t n_out);
+DMC_API int dmc_plan_num_ops(const dmc_plan* p);
+/* kind of op i: 0 memset, 1 cond, 2 stem, 3 gn_stats, 4 gn_apply, 5 conv, 6 attention, 7 upsample, 8 ddim, 9 ddpm */
+DMC_API int dmc_plan_op_kind(const dmc_plan* p, int32_t i);
+DMC_API double dmc_plan_op_flops(const dmc_plan* p, int32_t i);
+DMC_API double dmc_plan_op_bytes(const dmc_plan* p, int32_t i);
+
+DMC_API int dmc_plan_add_memset(dmc_plan* p, void* ptr, size_t bytes);
+
+/* Conditioning table.  Replaces TimeEmbedding + time_embed (models/unet.py:18-25,167-172), the label
+ * lookup (:256-260) and the 22 time_mlp / label_proj projections (:40-48,65-68):
+ *   cond[n, :] = bt_all + Wt_all . SiLU(time_embed(t_n))  +  ytab[clamp(y_n, 0, num_classes), :]
+ * freqs: the [half] sinusoid frequencies computed on the host with the reference's expression. */
+typedef struct {
+  const int64_t* t;     /* [B] */
+  const int64_t* y;     /* [B] or NULL */
+  int32_t B;
+  int32_t uniform_t;    /* 1: all t_n equal (sampling) -> the time part is computed once */
+  int32_t num_classes;  /* label clamp upper bound; ignored when ytab == NULL */
+  int32_t half;         /* model_channels / 2 */
+  int32_t temb;         /* model_channels * 4 */
+  int32_t ncols;        /* sum of Cout over all residual blocks */
+  const float* freqs;   /* [half] */
+  const float* w1;      /* [temb, 2*half]  time_embed.1.weight */
+  const float* b1;      /* [temb] */
+  const float* w2;      /* [temb, temb]    time_embed.3.weight */
+  const float* b2;      /* [temb] */
+  const float* wt_all;  /* [ncols, temb]   all time_mlp.1.weight stacked */
+  const float* bt_all;  /* [ncols]         time_mlp.1.bias + conv1 bias */
+  const float* ytab;    /* [num_classes+1, ncols] label_proj(SiLU(label_embed)) per class, or NULL */
+  float* scratch;       /* [2 * R * temb + R * ncols], R = uniform_t ? 1 : B */
+  float* cond;          /* [B, ncols] */
+} dmc_cond_desc;
+DMC_API int dmc_plan_add_cond(dmc_plan* p, const dmc_cond_desc* d);
+
+/* Input convolution 3x3, Cin <= 4, straight from the fp32 NCHW model input to bf16 NHWC
+ * (models/unet.py:188,263).  x has x_batch images; image n reads x[n % x_batch] (CFG runs the cond and
+ * uncond halves of one 2B batch over the same x). */
+typedef struct {
+  const float* x;      /* [x_batch, Cin, H, W] fp32 */
+  int32_t x_batch, B, Cin, H, W, Cout;
+  const float* weight; /* [Cout, Cin, 3, 3] fp32 */
+  const float* bias;   /* [Cout] */
+  void* out;           /* bf16 [B, H, W, Cout] */
+  float* stats;        /* optional [B, Cout/8, 2] partial (sum, sumsq) accumulators, pre-zeroed */
+} dmc_stem_desc;
+DMC_API int dmc_plan_add_stem(dmc_plan* p, const dmc_stem_desc* d);
+
+/* GroupNorm statistics: accumulates (sum, sumsq) per image per 8-channel block into stats (pre-zeroed). */
+typedef struct {
+  const void* src; /* bf16 [B, HW, C] */
+  int32_t B, HW, C;
+  float* stats;    /* [B, C/8, 2] */
+} dmc_gn_stats_desc;
+DMC_API int dmc_plan_add_gn_stats(dmc_plan* p, const dmc_gn_stats_desc* d);
+
+/* GroupNorm(groups, C) (+ SiLU) over the channel concatenation of up to two sources, written as ONE
+ * bf16 NHWC tensor (models/unet.py:35-36,51-52,80,238-239 and the torch.cat of :284). */
+typedef struct {
+  int32_t nsrc;
+  const void* src[2];     /* bf16 [B, HW, c_i] */
+  int32_t src_c[2];
+  const float* stats[2];  /* [B, c_i/8, 2] */
+  int32_t B, HW, groups;
+  const float* gamma;     /* [C] */
+  const float* beta;      /* [C] */
+  float eps;
+  int32_t silu;
+  void* out;              /* bf16 [B, HW, C] */
+} dmc_gn_apply_desc;
+DMC_API int dmc_plan_add_gn_apply(dmc_plan* p, const dmc_gn_apply_desc* d);
+
+/* Convolution as an implicit GEMM on tcgen05 tensor cores: M = B*Hout*Wout pixels, N = Cout,
+ * K = sum_i taps_i * c_i.  Replaces nn.Conv2d 3x3 / 1x1 (models/unet.py:37,54,58,81,82,106,116,240) with
+ * bias, conditioning add (:65-68), residual add (:72,:99) and the 1x1 shortcut (:58, as extra K columns)
+ * fused.  Every source is bf16 NHWC [B, Hin, Win, c_i] with c_i % 64 == 0.
+ *   taps_i = 9: 3x3 window, padding 1 (TMA zero fill), stride `stride`
+ *   taps_i = 1: centre tap only (1x1 conv / fused shortcut), sampled at stride `stride`
+ *   taps_i = 4: one phase (up_phase = 2*ph+pw) of "nearest 2x upsample then 3x3" (:118-120) computed on the
+ *               low-res tensor as a 2x2 window; the output pixel (i, j) is scattered to (2i+ph, 2j+pw).
+ * weight: bf16 [Cout_pad, Ktot] row-major, K ordered source by source, tap-major, channel-minor. */
+typedef struct {
+  int32_t nsrc;
+  const void* src[3];
+  int32_t src_c[3];
+  int32_t src_taps[3];
+  int32_t B, Hin, Win;
+  int32_t stride;   /* 1 or 2 */
+  int32_t up_phase; /* -1, or 0..3 */
+  const void* weight;
+  int32_t Cout, Cout_pad, Ktot;
+  const float* bias;      /* [Cout] or NULL */
+  const float* cond;      /* per-image addend row pointer base (already offset to this layer's column) or NULL */
+  int32_t cond_stride;    /* floats between images */
+  const void* residual;   /* bf16, same shape as out_bf16, or NULL */
+  void* out_bf16;         /* bf16 NHWC [B, Hout*, Wout*, Cout] or NULL */
+  float* out_f32_nchw;    /* fp32 [B, Cout, Hout, Wout] or NULL (model output head) */
+  float* stats;           /* optional [B, Cout/8, 2] accumulators of the OUTPUT (pre-zeroed) */
+  int32_t impl;           /* 0: tcgen05/TMA kernel (product path)   1: CUDA-core debug kernel (tests only) */
+} dmc_conv_desc;
+DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
+
+/* Multi-head self-attention core softmax(Q K^T / sqrt(hd)) V over L tokens (models/unet.py:88-96;
+ * models/dit.py:94,123).  qkv: bf16 [B, L, 3*C], channel order [q|k|v][head][hd]; out: bf16 [B, L, C]. */
+typedef struct {
+  const void* qkv;
+  void* out;
+  int32_t B, L, heads, C;
+} dmc_attn_desc;
+DMC_API int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d);
+
+/* nearest-neighbour 2x upsample of a bf16 NHWC tensor (models/unet.py:119) */
+typedef struct {
+  const void* src; /* [B, H, W, C] */
+  void* out;       /* [B, 2H, 2W, C] */
+  int32_t B, H, W, C;
+} dmc_upsample_desc;
+DMC_API int dmc_plan_add_upsample(dmc_plan* p, const dmc_upsample_desc* d);
+
+/* Scheduler steps as plan ops, so that "model forward + update" chains (and whole sampling loops) can be
+ * replayed with a single call / captured in one CUDA graph. */
+typedef struct {
+  const float* x;
+  const float* eps_c;
+  const float* eps_u;
+  const float* noise;
+  float* x_out;
+  int32_t B, n_per_sample;
+  const void* coef_dev; /* dmc_ddim_coef* or dmc_ddpm_coef* (device) */
+  dmc_guidance g;
+} dmc_step_desc;
+DMC_API int dmc_plan_add_ddim_step(dmc_plan* p, const dmc_step_desc* d);
+DMC_API int dmc_plan_add_ddpm_step(dmc_plan* p, const dmc_step_desc* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMC_H_ */
