@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- DDIM-50 UNet CIFAR-10 sampling throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[2]: class-conditional UNet (10 classes + null label), DDIM 50 steps, classifier-free
+guidance 3.0 with the reference's default dynamic thresholding (p = 0.995), global batch 4096 images sharded over the
+N ranks (contiguous slices, no data-path collective; one NCCL all-gather of the final images).  One "step" = one complete
+DDIM-50 sampling of the global batch.  `value` is images/s with x_T and the labels already resident in HBM; `e2e` is the
+same call fed from pinned HOST buffers (labels + x_T) with the images read back to the host inside the timed region.
+
+`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port: /root/reference is Python
+and does not exist on the GPU box) on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "ddim50_unet_cifar10_images_per_sec"
+UNIT = "images/s"
+FLOPS_PER_IMAGE_FORWARD = 12.638e9  # cond UNet, SURVEY.md 8(d) (hooks on the reference modules)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm (oracle port, fp32, all host threads) on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_images_per_sec(batch=8, sub_steps=4, cfg_scale=3.0, repeats=1):
+    """images/s of DDIM-50 + CFG on the host: runs `sub_steps` of the 50 DDIM steps (2 forwards each) on `batch` images
+    and scales the time by 50 / sub_steps (every step costs the same)."""
+    from diffusion_models_collection_b200 import synth
+    from oracle import model_oracle, sched_oracle as so
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = synth.CIFAR_UNET
+    sd = synth.make_unet_state_dict(cfg, 10, seed=42)
+    tb = so.make_tables()
+    ts = so.ddim_timesteps(1000, 50)[:sub_steps + 1]
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (batch,), generator=g) + 1
+
+    def model(xx, t, yy):
+        return model_oracle.unet_forward(sd, cfg, xx, t, yy, num_classes=10)
+
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        img = x
+        for i in range(sub_steps):
+            t_, tn_ = torch.full((batch,), int(ts[i])), torch.full((batch,), int(ts[i + 1]))
+            eps = so.cfg_combine(model(img, t_, y), model(img, t_, torch.zeros_like(y)), cfg_scale)
+            x0 = so.dynamic_threshold(so.ddim_x0(tb, img, eps, t_), 0.995)
+            img = so.ddim_step(tb, img, eps, t_, tn_, clip_denoised=False, x0_pred=x0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    full = best * 50.0 / sub_steps
+    return batch / full, {"value": batch / full, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                          "sample": f"{batch} images x {sub_steps} of 50 DDIM steps (2 UNet forwards each, CFG 3.0, "
+                                    f"dynamic threshold), fp32 oracle port on the host, time scaled by 50/{sub_steps}"}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_reference_images_per_sec(batch=2, sub_steps=1)
+    vals, cb = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 0),
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_rank):
+    return {"workload": "UNet cond (10+1 null) CIFAR-10 32x32, DDIM-50, CFG 3.0, dynamic threshold 0.995 "
+                        "(BASELINE.json configs[2])", "global_batch": args.batch, "per_gpu_batch": per_rank,
+            "sampler": "ddim50", "cfg_scale": 3.0, "parallelism": f"sample-sharded x{args.gpus}",
+            "l2": "inputs larger than L2 (activations of one forward are >10x the 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="global batch (images per step)")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--ref-sub-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--ops-out", default=None, help="write the per-op timing table (JSON) here")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch ourselves under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+                   os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    import torch.distributed as dist
+
+    from diffusion_models_collection_b200 import synth
+    from diffusion_models_collection_b200.diffusion import DDIM
+    from diffusion_models_collection_b200.models import UNet
+    from diffusion_models_collection_b200.sharding import sharded_sample_with_cfg, shard_bounds
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    net = UNet(**synth.CIFAR_UNET, num_classes=10)
+    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    net = net.to(dev).eval()
+    ddim = DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device=dev)
+    ddim.progress = False
+
+    B = args.batch
+    lo, hi = shard_bounds(B, rank, world)
+    nb = hi - lo
+    g = torch.Generator().manual_seed(42)
+    y_host = (torch.randint(0, 10, (B,), generator=g) + 1).pin_memory()
+    xT_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    y_dev, xT_dev = y_host.to(dev), xT_host.to(dev)
+    shape = (B, 3, 32, 32)
+
+    def step_resident():
+        return sharded_sample_with_cfg(ddim, net, shape, y_dev, cfg_scale=3.0, noise=xT_dev, rank=rank, world=world)
+
+    def step_e2e():
+        # host -> device of this rank's slice of the inputs, device -> host of the gathered images
+        yl = y_host[lo:hi].to(dev, non_blocking=True)
+        xl = xT_host[lo:hi].to(dev, non_blocking=True)
+        out = sharded_sample_with_cfg(ddim, net, shape, yl, cfg_scale=3.0, noise=xl, rank=rank, world=world, sliced=True)
+        return out.cpu() if rank == 0 else out[:1].cpu()
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    with ClockSampler(local_rank) as cs:
+        ms = timed(step_resident, args.steps)
+    clocks = cs.summary()
+    value = B * args.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 2)))
+    e2e_value = B * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
+
+    # launches of OUR kernels in the timed region: per DDIM step, per chunk: one plan run + one fused scheduler kernel
+    launches = net.launches_per_forward(nb, cfg=True) * 50 * args.steps
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, nb), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)),
+                    "d2h_bytes_per_step": int(B * 3 * 32 * 32 * 4)},
+            "gpu_launches": int(launches)}
+    pk = peaks()
+    flops_step = 2 * 50 * FLOPS_PER_IMAGE_FORWARD * B  # 2 forwards per DDIM step (cond + uncond)
+    line["model_flops_utilization"] = {"achieved_tflops": flops_step * args.steps / (ms / 1e3) / 1e12 / world,
+                                       "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
+
+    if rank == 0 and not args.no_roofline:
+        line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
+        line["cpu_baseline"] = cb
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_leg(net, dev, nb, pk, ops_out):
+    """Per-op device times of ONE forward (CUDA events on the launching stream, each op timed alone -> burst peak),
+    aggregated per kernel family.  Dominant kernel: the tcgen05 implicit-GEMM convolution."""
+    nimg = min(2 * nb, net.max_images_per_launch)
+    plan = net.plan_info(nimg // 2, cfg=True, device=dev)
+    ops = plan.time_ops(iters=3)
+    fam = {}
+    for o in ops:
+        f = fam.setdefault(o["kind"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        f["ms"] += o["ms"]
+        f["flops"] += o["flops"]
+        f["bytes"] += o["bytes"]
+        f["launches"] += 1
+    total_ms = sum(f["ms"] for f in fam.values())
+    conv = fam.get("conv", {"ms": 1e-9, "flops": 0.0, "launches": 1})
+    achieved = conv["flops"] / (conv["ms"] / 1e3) / 1e12
+    peak = pk["bf16_tflops"]
+    per_family = {}
+    for k, f in fam.items():
+        e = {"ms": round(f["ms"], 4), "share": round(f["ms"] / total_ms, 4), "launches": f["launches"]}
+        if f["flops"] > 0 and k in ("conv", "attention", "gemm"):
+            e["tflops"] = round(f["flops"] / (f["ms"] / 1e3) / 1e12, 2)
+            e["frac_tensor"] = round(e["tflops"] / peak, 4)
+        else:
+            e["gbs"] = round(f["bytes"] / (f["ms"] / 1e3) / 1e9, 1)
+            e["frac_hbm"] = round(e["gbs"] / pk["hbm_gbs"], 4)
+        per_family[k] = e
+    if ops_out:
+        with open(ops_out, "w") as fh:
+            json.dump({"images": nimg, "ops": ops, "families": per_family}, fh, indent=1)
+    return {"bound": "tensor", "kernel": "conv_umma_kernel (all conv launches of one forward, FLOP-weighted)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": pk["_source"] + " burst (ops timed alone)", "images_per_launch": nimg,
+            "forward_ms": total_ms, "per_family": per_family}
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,7 @@ def pack3(w):
 
 
 def run_conv(srcs, taps, wmat, Cout, *, stride=1, bias=None, cond=None, residual=None, out_nchw=False, stats=False,
-             impl=0, up_phase=-1):
+             impl=0, up_phase=-1, out_tensor=None):
     """srcs: list of bf16 NHWC tensors; wmat: fp32 [Cout_pad, K]; returns (out, stats or None)."""
     dev = srcs[0].device
     B, H, W, _ = srcs[0].shape
@@ -72,7 +72,8 @@ def run_conv(srcs, taps, wmat, Cout, *, stride=1, bias=None, cond=None, residual
         out = torch.full((B, Cout, Ho, Wo), float("nan"), device=dev)
         d.out_f32_nchw = out.data_ptr()
     else:
-        out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+        out = out_tensor if out_tensor is not None else torch.full((B, Ho, Wo, Cout), float("nan"), device=dev,
+                                                                   dtype=torch.bfloat16)
         d.out_bf16 = out.data_ptr()
     if stats:
         st = torch.zeros((B, Cout // 8, 2), device=dev)

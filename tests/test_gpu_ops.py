@@ -1,0 +1,273 @@
+"""GPU: every kernel of the UNet forward through the C ABI (one-op plans) vs a plain PyTorch fp32 reference of the
+same op on the same bf16-rounded operands.  Tolerances: outputs are bf16 (rel. rounding 2^-9 = 2e-3), accumulation
+is fp32 -> per-op relative L2 < 4e-3 (fp32 outputs < 1e-4); the tcgen05 kernel must also agree with the CUDA-core
+debug implementation of the same contract (impl=1)."""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import Plan, nchw_f32, nhwc_bf16, pack3, rel_l2, run_conv
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 4e-3
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def _q(x):  # bf16 rounding, back in fp32
+    return x.to(torch.bfloat16).float()
+
+
+# (Cin list, Cout, H, stride, B)  -- SURVEY.md A.2 shape classes (3x3)
+CONV3 = [
+    ([128], 128, 32, 1, 2), ([128], 128, 32, 2, 3), ([128], 256, 16, 1, 2), ([256], 256, 16, 1, 1),
+    ([256], 256, 16, 2, 5), ([256], 256, 8, 1, 3), ([256], 256, 8, 2, 9), ([256], 256, 4, 1, 5), ([256], 256, 4, 1, 16),
+    ([256, 256], 256, 4, 1, 3), ([256, 256], 256, 8, 1, 2), ([256, 256], 256, 16, 1, 1), ([256, 128], 256, 16, 1, 2),
+    ([256, 128], 128, 32, 1, 1), ([128, 128], 128, 32, 1, 2), ([256], 256, 32, 1, 1), ([64], 64, 32, 1, 2),
+    ([64], 128, 16, 1, 1), ([128, 64], 64, 32, 1, 1),
+]
+
+
+@pytest.mark.parametrize("cins,cout,H,stride,B", CONV3)
+def test_conv3x3_classes(cins, cout, H, stride, B):
+    cin = sum(cins)
+    x = _q(_rand((B, cin, H, H), 1))
+    w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
+    bias = _rand((cout,), 3, 0.1)
+    cond = _rand((B, cout + 8), 4, 0.2)
+    ref = F.conv2d(x, w, bias, stride=stride, padding=1) + cond[:, :cout, None, None]
+    # the GEMM K order is source by source: split the channel range like the concat does
+    srcs, wparts, c0 = [], [], 0
+    for c in cins:
+        srcs.append(nhwc_bf16(x[:, c0:c0 + c]))
+        wparts.append(pack3(w[:, c0:c0 + c]))
+        c0 += c
+    wmat = torch.cat(wparts, dim=1)
+    out, st = run_conv(srcs, [9] * len(cins), wmat, cout, stride=stride, bias=bias, cond=cond, stats=True)
+    got = nchw_f32(out)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < TOL_BF16
+    dbg, st_dbg = run_conv(srcs, [9] * len(cins), wmat, cout, stride=stride, bias=bias, cond=cond, stats=True, impl=1)
+    assert rel_l2(got, nchw_f32(dbg)) < 2.5e-3
+    # GroupNorm partial sums of the fp32 (pre-rounding) output per (image, 8-channel block)
+    want_s = ref.reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
+    want_ss = (ref * ref).reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
+    assert rel_l2(st[..., 1], want_ss) < 1e-3
+    assert float((st[..., 0] - want_s).abs().max()) < 2e-2 * float(want_ss.sqrt().max())
+
+
+@pytest.mark.parametrize("cin,cout,H,B", [(256, 768, 16, 2), (256, 768, 8, 3), (256, 768, 4, 5), (256, 256, 16, 1),
+                                          (256, 256, 4, 9), (128, 256, 16, 2), (64, 192, 16, 3)])
+def test_conv1x1_with_residual(cin, cout, H, B):
+    x = _q(_rand((B, cin, H, H), 5))
+    w = _q(_rand((cout, cin, 1, 1), 6, cin ** -0.5))
+    bias = _rand((cout,), 7, 0.1)
+    res = _q(_rand((B, cout, H, H), 8))
+    ref = F.conv2d(x, w, bias) + res
+    out, _ = run_conv([nhwc_bf16(x)], [1], w.reshape(cout, cin), cout, bias=bias, residual=nhwc_bf16(res))
+    assert rel_l2(nchw_f32(out), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("cins,cout,H,B", [([128], 256, 16, 2), ([256, 256], 256, 4, 3), ([256, 128], 128, 32, 1),
+                                           ([256, 128], 256, 16, 2)])
+def test_conv2_with_fused_shortcut(cins, cout, H, B):
+    """conv2(3x3 over a2) + shortcut(1x1 over the raw concat inputs) as one GEMM with extra K columns"""
+    a2 = _q(_rand((B, cout, H, H), 9))
+    xs = [_q(_rand((B, c, H, H), 10 + i)) for i, c in enumerate(cins)]
+    w2 = _q(_rand((cout, cout, 3, 3), 20, (cout * 9) ** -0.5))
+    wsc = _q(_rand((cout, sum(cins), 1, 1), 21, sum(cins) ** -0.5))
+    bias = _rand((cout,), 22, 0.1)
+    ref = F.conv2d(a2, w2, None, padding=1) + F.conv2d(torch.cat(xs, 1), wsc) + bias[None, :, None, None]
+    wmat = torch.cat([pack3(w2), wsc.reshape(cout, -1)], dim=1)
+    out, _ = run_conv([nhwc_bf16(a2)] + [nhwc_bf16(v) for v in xs], [9] + [1] * len(xs), wmat, cout, bias=bias)
+    assert rel_l2(nchw_f32(out), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_head_conv_fp32_nchw(B):
+    x = _q(_rand((B, 128, 32, 32), 30))
+    w = _q(_rand((3, 128, 3, 3), 31, (128 * 9) ** -0.5))
+    bias = _rand((3,), 32, 0.1)
+    ref = F.conv2d(x, w, bias, padding=1)
+    wmat = torch.cat([pack3(w), torch.zeros(29, 128 * 9, device="cuda")], dim=0)
+    out, _ = run_conv([nhwc_bf16(x)], [9], wmat, 3, bias=bias, out_nchw=True)
+    assert rel_l2(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("C,H,B", [(256, 4, 3), (256, 8, 2), (128, 16, 2)])
+def test_upsample_phase_convs(C, H, B):
+    """nearest-2x + conv3x3 (models/unet.py:118-120) == four 2x2 phase convolutions on the low-res tensor"""
+    x = _q(_rand((B, C, H, H), 40))
+    w = _rand((C, C, 3, 3), 41, (C * 9) ** -0.5)
+    bias = _rand((C,), 42, 0.1)
+    from diffusion_models_collection_b200.models.unet import phase_weights
+
+    out = torch.full((B, 2 * H, 2 * H, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wq = []
+    for ph in range(4):
+        wm = phase_weights(w, ph)  # [C, 4*C] fp32, rounded to bf16 by the packer
+        wq.append(wm.to(torch.bfloat16).float())
+        o, _ = run_conv([nhwc_bf16(x)], [4], wm, C, bias=bias, up_phase=ph, out_tensor=out)
+    got = nchw_f32(out)
+    assert torch.isfinite(got).all()
+    # reference with the same (phase-summed, then bf16-rounded) weights: rebuild per-phase dense conv in fp32
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    ref_exact = F.conv2d(up, w, bias, padding=1)
+    assert rel_l2(got, ref_exact) < 6e-3  # bf16 rounding of the summed taps instead of each tap
+
+
+def test_stem_conv():
+    B = 5
+    x = _rand((3, 3, 32, 32), 50)  # x_batch = 3 < B: images n read x[n % 3] (CFG halves share x)
+    w = _rand((128, 3, 3, 3), 51, 27 ** -0.5)
+    bias = _rand((128,), 52, 0.1)
+    from diffusion_models_collection_b200 import _lib
+
+    out = torch.full((B, 32, 32, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = _lib.StemDesc()
+    d.x, d.x_batch, d.B, d.Cin, d.H, d.W, d.Cout = x.data_ptr(), 3, B, 3, 32, 32, 128
+    d.weight, d.bias, d.out = w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    p = Plan()
+    p.add("stem", d)
+    p.run()
+    ref = F.conv2d(x[torch.arange(B) % 3], w, bias, padding=1)
+    assert rel_l2(nchw_f32(out), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("cs,H,B,silu", [([128], 32, 2, 1), ([256], 16, 3, 0), ([256, 256], 4, 5, 1), ([256, 128], 16, 2, 1),
+                                         ([256, 128], 32, 1, 1), ([256], 8, 2, 1), ([128, 64], 32, 2, 1)])
+def test_groupnorm_stats_apply_concat(cs, H, B, silu):
+    """GroupNorm(8, C)(+SiLU) over the concat of two tensors; 384 = 256 + 128 has a group straddling the boundary"""
+    from diffusion_models_collection_b200 import _lib
+
+    C_ = sum(cs)
+    xs = [_q(_rand((B, c, H, H), 60 + i, 1.5) + 0.3) for i, c in enumerate(cs)]
+    gamma, beta = 1 + 0.2 * _rand((C_,), 70), 0.1 * _rand((C_,), 71)
+    ref = F.group_norm(torch.cat(xs, 1), 8, gamma, beta, eps=1e-5)
+    if silu:
+        ref = F.silu(ref)
+    srcs = [nhwc_bf16(v) for v in xs]
+    stats = [torch.zeros((B, c // 8, 2), device="cuda") for c in cs]
+    out = torch.full((B, H, H, C_), float("nan"), device="cuda", dtype=torch.bfloat16)
+    p = Plan()
+    for s, st, c in zip(srcs, stats, cs):
+        d = _lib.GnStatsDesc()
+        d.src, d.B, d.HW, d.C, d.stats = s.data_ptr(), B, H * H, c, st.data_ptr()
+        p.add("gn_stats", d)
+    d = _lib.GnApplyDesc()
+    d.nsrc = len(cs)
+    for i in range(len(cs)):
+        d.src[i], d.src_c[i], d.stats[i] = srcs[i].data_ptr(), cs[i], stats[i].data_ptr()
+    d.B, d.HW, d.groups, d.gamma, d.beta, d.eps, d.silu, d.out = B, H * H, 8, gamma.data_ptr(), beta.data_ptr(), 1e-5, silu, out.data_ptr()
+    p.add("gn_apply", d)
+    p.run()
+    assert rel_l2(nchw_f32(out), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("L,heads,hd,B", [(256, 4, 64, 2), (64, 4, 64, 3), (16, 4, 64, 5), (256, 6, 64, 2), (1024, 6, 64, 1),
+                                          (256, 2, 64, 1)])
+def test_attention(L, heads, hd, B):
+    from diffusion_models_collection_b200 import _lib
+
+    C_ = heads * hd
+    qkv = _q(_rand((B, L, 3 * C_), 80))
+    out = torch.full((B, L, C_), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = _lib.AttnDesc()
+    d.qkv, d.out, d.B, d.L, d.heads, d.C = qkv.to(torch.bfloat16).contiguous().data_ptr(), out.data_ptr(), B, L, heads, C_
+    keep = qkv.to(torch.bfloat16).contiguous()
+    d.qkv = keep.data_ptr()
+    p = Plan()
+    p.add("attention", d)
+    p.run()
+    q, k, v = (qkv[..., i * C_:(i + 1) * C_].reshape(B, L, heads, hd).transpose(1, 2) for i in range(3))
+    a = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    ref = (a @ v).transpose(1, 2).reshape(B, L, C_)
+    assert rel_l2(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("uniform_t,has_y", [(1, True), (0, True), (0, False), (1, False)])
+def test_conditioning_table(uniform_t, has_y):
+    """time_embed + all time_mlp/label_proj projections vs fp32 torch (models/unet.py:18-25,40-48,167-172,256-260)"""
+    import math
+
+    from diffusion_models_collection_b200 import _lib
+
+    B, half, temb, ncols, ncls = 6, 64, 512, 1024, 10
+    t = torch.tensor([500] * B if uniform_t else [0, 1, 20, 500, 979, 999]).cuda()
+    y = torch.tensor([0, 1, 5, 10, 11, 99]).cuda()
+    w1, b1 = _rand((temb, 2 * half), 90, (2 * half) ** -0.5), _rand((temb,), 91, 0.1)
+    w2, b2 = _rand((temb, temb), 92, temb ** -0.5), _rand((temb,), 93, 0.1)
+    wt, bt = _rand((ncols, temb), 94, temb ** -0.5), _rand((ncols,), 95, 0.1)
+    emb = _rand((ncls + 1, temb), 96)
+    emb[0] = 0
+    wy = _rand((ncols, temb), 97, temb ** -0.5)
+    freqs = torch.exp(torch.arange(half, device="cuda") * -(math.log(10000) / (half - 1))).float()
+    arg = t[:, None] * freqs[None]
+    e = torch.cat([arg.sin(), arg.cos()], -1)
+    temb_v = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2)
+    ref = F.linear(F.silu(temb_v), wt, bt)
+    ytab = (F.silu(emb) @ wy.t()).contiguous()
+    if has_y:
+        ref = ref + ytab[y.clamp(0, ncls)]
+    R = 1 if uniform_t else B
+    scratch = torch.empty(2 * R * temb + R * ncols, device="cuda")
+    cond = torch.full((B, ncols), float("nan"), device="cuda")
+    d = _lib.CondDesc()
+    d.t, d.y, d.B, d.uniform_t, d.num_classes = t.data_ptr(), (y.data_ptr() if has_y else None), B, uniform_t, ncls
+    d.half, d.temb, d.ncols, d.freqs = half, temb, ncols, freqs.data_ptr()
+    d.w1, d.b1, d.w2, d.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    d.wt_all, d.bt_all, d.ytab = wt.data_ptr(), bt.data_ptr(), (ytab.data_ptr() if has_y else None)
+    d.scratch, d.cond = scratch.data_ptr(), cond.data_ptr()
+    p = Plan()
+    p.add("cond", d)
+    p.run()
+    assert rel_l2(cond, ref) < 2e-5
+    if has_y:  # null label (row 0 is zero) adds exactly nothing
+        d.y = None
+        d.ytab = None
+        cond2 = torch.empty_like(cond)
+        d.cond = cond2.data_ptr()
+        p2 = Plan()
+        p2.add("cond", d)
+        p2.run()
+        assert torch.equal(cond2[0], cond[0])
+
+
+def test_upsample_nearest():
+    from diffusion_models_collection_b200 import _lib
+
+    x = _q(_rand((3, 64, 8, 8), 99))
+    src = nhwc_bf16(x)
+    out = torch.empty((3, 16, 16, 64), device="cuda", dtype=torch.bfloat16)
+    d = _lib.UpsampleDesc()
+    d.src, d.out, d.B, d.H, d.W, d.C = src.data_ptr(), out.data_ptr(), 3, 8, 8, 64
+    p = Plan()
+    p.add("upsample", d)
+    p.run()
+    assert torch.equal(nchw_f32(out), F.interpolate(x, scale_factor=2, mode="nearest"))
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    from diffusion_models_collection_b200 import _lib
+
+    lib = _lib.load()
+    d = _lib.ConvDesc()
+    d.nsrc = 1
+    p = Plan()
+    with pytest.raises(_lib.DmcError):
+        p.add("conv", d)
+    assert b"conv" in lib.dmc_last_error()
