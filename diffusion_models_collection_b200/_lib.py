@@ -44,7 +44,7 @@ class CondDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32),
-                ("W", C.c_int32), ("Cout", C.c_int32), ("weight", vp), ("bias", vp), ("out", vp), ("stats", vp)]
+                ("W", C.c_int32), ("Cout", C.c_int32), ("weight", vp), ("bias", vp), ("out", vp)]
 
 
 class GnStatsDesc(C.Structure):
@@ -52,8 +52,8 @@ class GnStatsDesc(C.Structure):
 
 
 class GnApplyDesc(C.Structure):
-    _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2), ("B", C.c_int32),
-                ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
+    _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2), ("stats_slots", C.c_int32 * 2),
+                ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
                 ("silu", C.c_int32), ("out", vp)]
 
 
@@ -62,11 +62,12 @@ class ConvDesc(C.Structure):
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("stride", C.c_int32),
                 ("up_phase", C.c_int32), ("weight", vp), ("Cout", C.c_int32), ("Cout_pad", C.c_int32),
                 ("Ktot", C.c_int32), ("bias", vp), ("cond", vp), ("cond_stride", C.c_int32), ("residual", vp),
-                ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("impl", C.c_int32)]
+                ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("stats_slots", C.c_int32), ("impl", C.c_int32)]
 
 
 class AttnDesc(C.Structure):
-    _fields_ = [("qkv", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32), ("C", C.c_int32)]
+    _fields_ = [("qkv", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32), ("C", C.c_int32),
+                ("impl", C.c_int32)]
 
 
 class UpsampleDesc(C.Structure):

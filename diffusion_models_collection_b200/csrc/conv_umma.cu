@@ -49,6 +49,7 @@ struct ConvKParams {
   __nv_bfloat16* out;
   float* out_nchw;
   float* stats;
+  int stats_slots, stats_slot_base;
 };
 
 struct ConvPrepared {
@@ -253,8 +254,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         if (p.stats != nullptr) {
-          // GroupNorm partial sums of the OUTPUT per (image, 8-channel block): reduce over the rows of this warp
-          // that belong to the same image (32 when ppi >= 32, else 16-lane halves), one atomic pair per block.
+          // GroupNorm partial sums of the OUTPUT per (image, 8-channel block): reduce over the rows of this warp that
+          // belong to the same image (32 when ppi >= 32, else 16-lane halves) and store them in this warp's own slot
+          // (plain stores, no atomics: deterministic and batch-invariant; the consumer adds the slots in order).
+          const int wpi = ppi >> 5;  // epilogue warps per image inside one tile (0 when an image is a half-warp)
+          const int slot = p.stats_slot_base + ((ppi >= 32) ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             float s = 0.f, ss = 0.f;
@@ -276,9 +280,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             const bool writer = (ppi >= 32) ? (lane == 0) : ((lane & 15) == 0);
             if (writer && valid) {
-              float* dst = p.stats + (static_cast<size_t>(n) * (p.Cout >> 3) + ((cg >> 3) + b)) * 2;
-              atomicAdd(dst, s);
-              atomicAdd(dst + 1, ss);
+              float2* dst = reinterpret_cast<float2*>(p.stats) +
+                            (static_cast<size_t>(n) * p.stats_slots + slot) * (p.Cout >> 3) + ((cg >> 3) + b);
+              *dst = make_float2(s, ss);
             }
           }
         }
@@ -418,6 +422,18 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   kp.out_nchw = d.out_f32_nchw;
   kp.stats = d.stats;
+  if (d.stats) {
+    const int ppi_img = Hout * Wout;  // iteration pixels per image
+    const int base = ppi_img >= 32 ? ppi_img / 32 : 1;
+    const int want = base * (d.up_phase >= 0 ? 4 : 1);
+    if (ppi_img < 16 || (ppi_img % 32 != 0 && ppi_img != 16) || d.stats_slots != want) {
+      delete P;
+      DMC_REQUIRE(false, "conv: stats_slots=%d but this geometry (%d pixels/image, up_phase %d) writes %d slots",
+                  d.stats_slots, ppi_img, d.up_phase, want);
+    }
+    kp.stats_slots = want;
+    kp.stats_slot_base = d.up_phase >= 0 ? d.up_phase * base : 0;
+  }
   P->grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
   P->smem = BN == 256 ? ConvCfg<256>::SMEM : BN == 128 ? ConvCfg<128>::SMEM : BN == 64 ? ConvCfg<64>::SMEM : ConvCfg<32>::SMEM;
   *out = P;

@@ -102,15 +102,22 @@ int cond_num_launches(const dmc_cond_desc&) { return 4; }
 int launch_cond(const dmc_cond_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.t && d.freqs && d.w1 && d.b1 && d.w2 && d.b2 && d.wt_all && d.bt_all && d.scratch && d.cond,
               "cond: null pointer argument");
-  DMC_REQUIRE(d.B > 0 && d.ncols % 4 == 0 && d.temb == 512, "cond: unsupported shape (B=%d ncols=%d temb=%d)", d.B,
-              d.ncols, d.temb);
+  DMC_REQUIRE(d.B > 0 && d.ncols % 4 == 0 && d.temb > 0 && d.half > 0, "cond: unsupported shape (B=%d ncols=%d temb=%d)",
+              d.B, d.ncols, d.temb);
   const int R = d.uniform_t ? 1 : d.B;
   float* h1 = d.scratch;
   float* sil = d.scratch + static_cast<size_t>(R) * d.temb;
   float* cond_t = d.scratch + 2 * static_cast<size_t>(R) * d.temb;
   cond_hidden_kernel<<<dim3(R, 8), 256, 2 * d.half * sizeof(float), st>>>(d.t, d.freqs, d.w1, d.b1, h1, d.half, d.temb);
   cond_linear_kernel<<<dim3(R, 8), 256, 0, st>>>(h1, d.w2, d.b2, sil, d.temb, d.temb, 1);
-  cond_project_kernel<16><<<(d.ncols + 7) / 8, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols);
+  const int pb = (d.ncols + 7) / 8;
+  switch (d.temb) {  // weight row in registers (temb / 32 floats per lane), all R rows streamed past it
+    case 128: cond_project_kernel<4><<<pb, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols); break;
+    case 256: cond_project_kernel<8><<<pb, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols); break;
+    case 512: cond_project_kernel<16><<<pb, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols); break;
+    case 1024: cond_project_kernel<32><<<pb, 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, R, d.ncols); break;
+    default: cond_linear_kernel<<<dim3(R, 8), 256, 0, st>>>(sil, d.wt_all, d.bt_all, cond_t, d.temb, d.ncols, 0); break;
+  }
   size_t total = static_cast<size_t>(d.B) * (d.ncols / 4);
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   cond_expand_kernel<<<blocks, 256, 0, st>>>(cond_t, d.ytab, d.y, d.cond, d.B, d.ncols, d.uniform_t, d.num_classes);
@@ -121,13 +128,15 @@ int launch_cond(const dmc_cond_desc& d, cudaStream_t st) {
 // =============================================================================================
 // Stem: 3x3 conv with Cin <= 4 from fp32 NCHW straight to bf16 NHWC (models/unet.py:188, 263)
 // =============================================================================================
-constexpr int STEM_MAX_K = 36;
-
+// Memory-bound (AI ~ 26 FLOP/B): fp32 CUDA-core FMAs.  lane = pixel (coalesced fp32 NCHW reads along W), every thread
+// keeps the 9*Cin taps of TWO pixels in registers and walks the output channels 16 at a time; the weights are
+// warp-uniform broadcast reads from shared memory (8 FMAs per 128-bit LDS), bf16 NHWC stores are full 32-byte sectors.
+template <int CIN>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                   int x_batch, int B, int Cin, int H, int W, int Cout) {
+                                                   int x_batch, int B, int H, int W, int Cout) {
+  constexpr int K = CIN * 9;
   extern __shared__ float sw[];  // [K][Cout] transposed weights, then bias[Cout]
-  const int K = Cin * 9;
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
     int k = i / Cout, c = i % Cout;
     sw[i] = w[static_cast<size_t>(c) * K + k];
@@ -135,58 +144,84 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   float* sb = sw + K * Cout;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  const int vec_per_pix = Cout >> 3;
-  const size_t total = static_cast<size_t>(B) * H * W * vec_per_pix;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cb = static_cast<int>(i % vec_per_pix);
-    size_t pix = i / vec_per_pix;
-    const int ww = static_cast<int>(pix % W);
-    const int hh = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
-    const float* xin = x + static_cast<size_t>(n % x_batch) * Cin * H * W;
-    float acc[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const size_t base = (static_cast<size_t>(blockIdx.x) * 8 + warp) * 64;
+  float xv[2][K];
+  size_t pix[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[cb * 8 + j];
-    for (int ci = 0; ci < Cin; ++ci) {
+  for (int u = 0; u < 2; ++u) {
+    pix[u] = base + u * 32 + lane;
+    const bool ok = pix[u] < total;
+    const size_t pp = ok ? pix[u] : 0;
+    const int ww = static_cast<int>(pp % W);
+    const int hh = static_cast<int>((pp / W) % H);
+    const int n = static_cast<int>(pp / (static_cast<size_t>(W) * H));
+    const float* xin = x + static_cast<size_t>(n % x_batch) * CIN * H * W;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int ih = hh + r - 1;
-        if (ih < 0 || ih >= H) continue;
+    for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int iw = ww + s - 1;
-          if (iw < 0 || iw >= W) continue;
-          const float v = __ldg(xin + (static_cast<size_t>(ci) * H + ih) * W + iw);
-          const float* wk = sw + ((ci * 3 + r) * 3 + s) * Cout + cb * 8;
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wk[j], acc[j]);
+        for (int t = 0; t < 3; ++t) {
+          const int ih = hh + r - 1, iw = ww + t - 1;
+          const bool in = ok && ih >= 0 && ih < H && iw >= 0 && iw < W;
+          xv[u][(ci * 3 + r) * 3 + t] = in ? __ldg(xin + (static_cast<size_t>(ci) * H + ih) * W + iw) : 0.f;
         }
+  }
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    float acc[2][16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = sb[c0 + j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4* wk = reinterpret_cast<const float4*>(sw + k * Cout + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = wk[q];
+        acc[0][4 * q] = fmaf(xv[0][k], wv.x, acc[0][4 * q]);
+        acc[0][4 * q + 1] = fmaf(xv[0][k], wv.y, acc[0][4 * q + 1]);
+        acc[0][4 * q + 2] = fmaf(xv[0][k], wv.z, acc[0][4 * q + 2]);
+        acc[0][4 * q + 3] = fmaf(xv[0][k], wv.w, acc[0][4 * q + 3]);
+        acc[1][4 * q] = fmaf(xv[1][k], wv.x, acc[1][4 * q]);
+        acc[1][4 * q + 1] = fmaf(xv[1][k], wv.y, acc[1][4 * q + 1]);
+        acc[1][4 * q + 2] = fmaf(xv[1][k], wv.z, acc[1][4 * q + 2]);
+        acc[1][4 * q + 3] = fmaf(xv[1][k], wv.w, acc[1][4 * q + 3]);
       }
     }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (pix[u] < total) {
+        uint4* o = reinterpret_cast<uint4*>(out + pix[u] * Cout + c0);
+        o[0] = make_uint4(pack_bf16x2(acc[u][0], acc[u][1]), pack_bf16x2(acc[u][2], acc[u][3]),
+                          pack_bf16x2(acc[u][4], acc[u][5]), pack_bf16x2(acc[u][6], acc[u][7]));
+        o[1] = make_uint4(pack_bf16x2(acc[u][8], acc[u][9]), pack_bf16x2(acc[u][10], acc[u][11]),
+                          pack_bf16x2(acc[u][12], acc[u][13]), pack_bf16x2(acc[u][14], acc[u][15]));
+      }
+    }
   }
 }
 
 int launch_stem(const dmc_stem_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.x && d.weight && d.bias && d.out, "stem: null pointer argument");
-  DMC_REQUIRE(d.Cin * 9 <= STEM_MAX_K && d.Cout % 8 == 0 && d.x_batch > 0 && d.B > 0, "stem: unsupported shape");
-  size_t total = static_cast<size_t>(d.B) * d.H * d.W * (d.Cout / 8);
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
-  size_t smem = (static_cast<size_t>(d.Cin) * 9 * d.Cout + d.Cout) * sizeof(float);
-  stem_kernel<<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, reinterpret_cast<__nv_bfloat16*>(d.out), d.x_batch, d.B,
-                                         d.Cin, d.H, d.W, d.Cout);
+  DMC_REQUIRE(d.Cin >= 1 && d.Cin <= 4 && d.Cout % 16 == 0 && d.x_batch > 0 && d.B > 0, "stem: unsupported shape");
+  const size_t total = static_cast<size_t>(d.B) * d.H * d.W;
+  const int blocks = static_cast<int>((total + 511) / 512);
+  const size_t smem = (static_cast<size_t>(d.Cin) * 9 * d.Cout + d.Cout) * sizeof(float);
+  DMC_REQUIRE(smem <= 48 * 1024, "stem: Cout=%d too large", d.Cout);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  switch (d.Cin) {
+    case 1: stem_kernel<1><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    case 2: stem_kernel<2><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    case 3: stem_kernel<3><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    default: stem_kernel<4><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+  }
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // =============================================================================================
-// GroupNorm statistics: (sum, sumsq) per image per 8-channel block (fp32 atomics into a pre-zeroed buffer)
+// GroupNorm statistics: (sum, sumsq) per image, per 128-pixel slab (slot), per 8-channel block
 // =============================================================================================
 constexpr int GN_SLAB = 128;  // pixels per CTA
 
@@ -219,9 +254,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
       s += red[(k * C8 + cb) * 2];
       ss += red[(k * C8 + cb) * 2 + 1];
     }
-    float* dst = stats + (static_cast<size_t>(n) * C8 + cb) * 2;
-    atomicAdd(dst, s);
-    atomicAdd(dst + 1, ss);
+    // slot = this 128-pixel slab: written once, summed in order by the consumer (deterministic)
+    float2* dst = reinterpret_cast<float2*>(stats) + (static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C8 + cb;
+    *dst = make_float2(s, ss);
   }
 }
 
@@ -250,6 +285,7 @@ struct GnApplyArgs {
   const float* beta;
   uint4* out;
   int HW, C0_8, C1_8, groups;
+  int slots0, slots1;
   float eps;
   int silu;
 };
@@ -266,11 +302,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = (c >> 3) / gs8;
     float s = 0.f, ss = 0.f;
-    for (int b = g * gs8; b < (g + 1) * gs8; ++b) {
-      const float* p = (b < a.C0_8) ? a.stats0 + (static_cast<size_t>(n) * a.C0_8 + b) * 2
-                                    : a.stats1 + (static_cast<size_t>(n) * a.C1_8 + (b - a.C0_8)) * 2;
-      s += p[0];
-      ss += p[1];
+    for (int b = g * gs8; b < (g + 1) * gs8; ++b) {  // fixed order: blocks, then slots -> bit-reproducible
+      const bool first = b < a.C0_8;
+      const int slots = first ? a.slots0 : a.slots1;
+      const int c8 = first ? a.C0_8 : a.C1_8;
+      const float2* p = reinterpret_cast<const float2*>(first ? a.stats0 : a.stats1) +
+                        static_cast<size_t>(n) * slots * c8 + (first ? b : b - a.C0_8);
+      for (int sl = 0; sl < slots; ++sl) {
+        const float2 v = __ldg(p + static_cast<size_t>(sl) * c8);
+        s += v.x;
+        ss += v.y;
+      }
     }
     const float mean = s * inv_cnt;
     const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
@@ -319,6 +361,9 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.stats1 = d.nsrc == 2 ? d.stats[1] : d.stats[0];
   a.gamma = d.gamma; a.beta = d.beta; a.out = reinterpret_cast<uint4*>(d.out);
   a.HW = d.HW; a.C0_8 = C0 / 8; a.C1_8 = C1 / 8; a.groups = d.groups; a.eps = d.eps; a.silu = d.silu;
+  a.slots0 = d.stats_slots[0];
+  a.slots1 = d.nsrc == 2 ? d.stats_slots[1] : 0;
+  DMC_REQUIRE(a.slots0 > 0 && (d.nsrc == 1 || a.slots1 > 0), "gn_apply: stats_slots must be positive");
   dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
   gn_apply_kernel<<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(a);
   DMC_CUDA_OK(cudaGetLastError());

@@ -23,8 +23,14 @@ int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st);
 int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st);
 int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
 
-// attention.cu
+// attention.cu : CUDA-core flash kernel (any L; debug / shapes the tensor-core kernel does not cover)
 int launch_attention(const dmc_attn_desc& d, cudaStream_t st);
+// attention_umma.cu : tcgen05 kernel
+struct AttnPrepared;
+bool attention_umma_supported(const dmc_attn_desc& d);
+int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out);
+void attention_release(AttnPrepared* p);
+int launch_attention_umma(const AttnPrepared* p, cudaStream_t st);
 
 // conv_umma.cu : the tcgen05 implicit-GEMM convolution.  `prepared` holds the TMA descriptors and tile geometry
 struct ConvPrepared;

@@ -41,6 +41,7 @@ struct Op {
     dmc_step_desc step;
   };
   ConvPrepared* conv_prep;
+  AttnPrepared* attn_prep;
   double flops;  // algorithmic tensor FLOPs (GEMM-shaped ops)
   double bytes;  // algorithmic HBM bytes (read inputs once + write outputs once)
   Op() {
@@ -65,7 +66,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_GN_STATS: return launch_gn_stats(op.gn_stats, st);
     case OP_GN_APPLY: return launch_gn_apply(op.gn_apply, st);
     case OP_CONV: return op.conv.impl == 1 ? launch_conv_ref(op.conv, st) : launch_conv(op.conv, op.conv_prep, st);
-    case OP_ATTN: return launch_attention(op.attn, st);
+    case OP_ATTN: return op.attn_prep ? launch_attention_umma(op.attn_prep, st) : launch_attention(op.attn, st);
     case OP_UPSAMPLE: return launch_upsample(op.up, st);
     case OP_DDIM: return launch_step(false, op.step, st);
     case OP_DDPM: return launch_step(true, op.step, st);
@@ -131,6 +132,8 @@ int dmc_plan_destroy(dmc_plan* p) {
   if (p == nullptr) return 0;
   for (auto& op : p->ops)
     if (op.conv_prep) conv_release(op.conv_prep);
+  for (auto& op : p->ops)
+    if (op.attn_prep) attention_release(op.attn_prep);
   delete p;
   return 0;
 }
@@ -287,6 +290,11 @@ int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d) {
   Op op;
   op.kind = OP_ATTN;
   op.attn = *d;
+  DMC_REQUIRE(d->impl == 0 || d->impl == 1, "dmc_plan_add_attention: impl=%d", d->impl);
+  if (d->impl == 0 && attention_umma_supported(*d)) {
+    int r = attention_prepare(*d, &op.attn_prep);
+    if (r != 0) return r;
+  }
   op.flops = 4.0 * d->B * static_cast<double>(d->L) * d->L * d->C;  // QK^T and PV
   op.bytes = 2.0 * d->B * d->L * 4.0 * d->C;
   return push(p, op);

@@ -4,6 +4,7 @@
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 
@@ -103,6 +104,12 @@ class DiffusionBase:
         from tqdm import tqdm
 
         return tqdm(it, desc=desc, total=total)
+
+    @staticmethod
+    def _uniform_t(model):
+        """context in which the native denoisers may assume all timesteps of a call are equal (sampling loops)"""
+        ctx = getattr(model, "uniform_timesteps", None)
+        return ctx() if callable(ctx) else contextlib.nullcontext()
 
     @staticmethod
     def _require_cuda(t, what):

@@ -7,6 +7,8 @@ reference's own fp32 expressions, so nothing in the loop synchronises with the h
 
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from .. import _lib
@@ -99,16 +101,17 @@ class DDIM(DiffusionBase):
         nxt = torch.empty_like(img)
         g = guidance(0.0, 1)
         imgs = []
-        for i, t in enumerate(self._bar(timesteps, "DDIM Sampling")):
-            t_batch.fill_(t)
-            eps = model(img, t_batch, y)
-            z = None
-            if self.eta > 0:
-                z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
-            self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
-            img, nxt = nxt, img
-            if return_all_timesteps:
-                imgs.append(img.cpu())
+        with self._uniform_t(model):
+            for i, t in enumerate(self._bar(timesteps, "DDIM Sampling")):
+                t_batch.fill_(t)
+                eps = model(img, t_batch, y)
+                z = None
+                if self.eta > 0:
+                    z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
+                self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
+                img, nxt = nxt, img
+                if return_all_timesteps:
+                    imgs.append(img.cpu())
         if return_all_timesteps:
             return torch.stack(imgs, dim=0)
         return img
@@ -135,16 +138,17 @@ class DDIM(DiffusionBase):
         nxt = torch.empty_like(img)
         g = guidance(cfg_scale, 2, n, p_threshold) if p_threshold is not None else guidance(cfg_scale, 1)
         imgs = []
-        for i, t in enumerate(self._bar(timesteps, f"DDIM sampling with CFG scale {cfg_scale}")):
-            t_batch.fill_(t)
-            eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
-            z = None
-            if self.eta > 0:
-                z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
-            self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
-            img, nxt = nxt, img
-            if return_all_timesteps:
-                imgs.append(img.cpu())
+        with self._uniform_t(model):
+            for i, t in enumerate(self._bar(timesteps, f"DDIM sampling with CFG scale {cfg_scale}")):
+                t_batch.fill_(t)
+                eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
+                z = None
+                if self.eta > 0:
+                    z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
+                self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
+                img, nxt = nxt, img
+                if return_all_timesteps:
+                    imgs.append(img.cpu())
         if return_all_timesteps:
             return torch.stack(imgs, dim=0)
         return img

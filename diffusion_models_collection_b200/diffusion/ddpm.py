@@ -6,6 +6,8 @@ coefficient table built once with the reference's own fp32 expressions."""
 
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
@@ -94,14 +96,15 @@ class DDPM(DiffusionBase):
         nxt = torch.empty_like(img)
         g = guidance(0.0, 1)
         imgs = []
-        for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)), "Sampling", self.num_timesteps)):
-            t_batch.fill_(i)
-            eps = model(img, t_batch, y)
-            z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
-            self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
-            img, nxt = nxt, img
-            if return_all_timesteps:
-                imgs.append(img.cpu())
+        with self._uniform_t(model):
+            for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)), "Sampling", self.num_timesteps)):
+                t_batch.fill_(i)
+                eps = model(img, t_batch, y)
+                z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
+                self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
+                img, nxt = nxt, img
+                if return_all_timesteps:
+                    imgs.append(img.cpu())
         if return_all_timesteps:
             return torch.stack(imgs, dim=0)
         return img
@@ -127,15 +130,16 @@ class DDPM(DiffusionBase):
         nxt = torch.empty_like(img)
         g = guidance(cfg_scale, 2, n, float(p_threshold)) if p_threshold is not None else guidance(cfg_scale, 1)
         imgs = []
-        for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)),
-                                        f"DDPM Sampling with CFG scale {cfg_scale}", self.num_timesteps)):
-            t_batch.fill_(i)
-            eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
-            z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
-            self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
-            img, nxt = nxt, img
-            if return_all_timesteps:
-                imgs.append(img.cpu())
+        with self._uniform_t(model):
+            for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)),
+                                            f"DDPM Sampling with CFG scale {cfg_scale}", self.num_timesteps)):
+                t_batch.fill_(i)
+                eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
+                z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
+                self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
+                img, nxt = nxt, img
+                if return_all_timesteps:
+                    imgs.append(img.cpu())
         if return_all_timesteps:
             return torch.stack(imgs, dim=0)
         return img

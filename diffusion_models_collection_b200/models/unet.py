@@ -14,6 +14,7 @@ bf16 K-major packed copies the kernels read are rebuilt whenever a parameter ver
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -100,10 +101,11 @@ class _Arena:
 class _Act:
     """A bf16 NHWC activation [B, H, W, C] living in the plan workspace."""
 
-    __slots__ = ("blk", "C", "H", "W", "stats")
+    __slots__ = ("blk", "C", "H", "W", "stats", "slots")
 
     def __init__(self, blk, Cc, H, W):
-        self.blk, self.C, self.H, self.W, self.stats = blk, Cc, H, W, None
+        self.blk, self.C, self.H, self.W = blk, Cc, H, W
+        self.stats, self.slots = None, 0  # GroupNorm partial sums [B, slots, C/8, 2] fp32 (workspace block)
 
 
 class _PlanBuilder:
@@ -113,7 +115,6 @@ class _PlanBuilder:
         self.net, self.B, self.x_batch = net, nimg, x_batch
         self.has_y, self.uniform_t, self.conv_impl = has_y, uniform_t, conv_impl
         self.arena = _Arena()
-        self.stats_bytes = 0
         self.ops = []  # (kind, dict)
 
     # -- workspace ---------------------------------------------------------------------------------
@@ -122,33 +123,43 @@ class _PlanBuilder:
 
     def free(self, a: _Act):
         self.arena.release(a.blk)
+        if a.stats is not None:
+            self.arena.release(a.stats)
+
+    def _alloc_stats(self, a: _Act, slots):
+        a.slots = slots
+        a.stats = self.arena.alloc(self.B * slots * (a.C // 8) * 2 * 4)
 
     def stats_of(self, a: _Act):
-        """(offset into the stats arena) of the per-(image, 8-channel block) sums of `a`; emitted once per tensor."""
+        """GroupNorm partial sums of `a`: written by the producing conv's epilogue when it has one, else by a
+        stand-alone pass (stem output; every tensor when the CUDA-core debug conv is selected)."""
         if a.stats is None:
-            a.stats = self.stats_bytes
-            self.stats_bytes += _round_up(self.B * (a.C // 8) * 2 * 4, 256)
-            self.ops.append(("gn_stats", dict(src=a, stats=a.stats)))
-        return a.stats
+            self._alloc_stats(a, (a.H * a.W + 127) // 128)
+            self.ops.append(("gn_stats", dict(src=a)))
+        return a
 
     # -- layers --------------------------------------------------------------------------------------
     def gn_apply(self, srcs, prefix, silu):
         H, W = srcs[0].H, srcs[0].W
         out = self.act(sum(s.C for s in srcs), H, W)
-        self.ops.append(("gn_apply", dict(srcs=list(srcs), stats=[self.stats_of(s) for s in srcs], prefix=prefix,
-                                          silu=silu, out=out)))
+        for s in srcs:
+            self.stats_of(s)
+        self.ops.append(("gn_apply", dict(srcs=list(srcs), prefix=prefix, silu=silu, out=out)))
         return out
 
     def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
-             up_phase=-1, out=None):
+             up_phase=-1, out=None, want_stats=True):
         Ho, Wo = H // stride, W // stride
         if up_phase >= 0:
             Ho, Wo = 2 * H, 2 * W
         if out is None and not out_nchw:
             out = self.act(Cout, Ho, Wo)
+        if out is not None and want_stats and self.conv_impl == 0 and out.stats is None:
+            ppi = (H // stride) * (W // stride)  # iteration pixels per image: one slot per 32-pixel epilogue warp
+            self._alloc_stats(out, max(1, ppi // 32) * (4 if up_phase >= 0 else 1))
         self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), wname=wname, Cout=Cout, H=H, W=W, stride=stride,
                                       bias=bias, cond_col=cond_col, residual=residual, out=out, out_nchw=out_nchw,
-                                      up_phase=up_phase)))
+                                      up_phase=up_phase, want_stats=want_stats)))
         return out
 
     def resblock(self, srcs, prefix, cout, cond_col):
@@ -170,7 +181,7 @@ class _PlanBuilder:
 
     def attnblock(self, x, prefix):
         an = self.gn_apply([x], prefix + ".norm", 0)
-        qkv = self.conv([an], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv")
+        qkv = self.conv([an], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv", want_stats=False)
         self.free(an)
         ao = self.act(x.C, x.H, x.W)
         self.ops.append(("attention", dict(qkv=qkv, out=ao, L=x.H * x.W, C=x.C)))
@@ -234,7 +245,7 @@ class _PlanBuilder:
         assert not hs
         a = self.gn_apply([h], "output.0", 1)
         self.free(h)
-        self.conv([a], [9], "output.2", net.out_channels, H, W, bias="output.2", out_nchw=True)
+        self.conv([a], [9], "output.2", net.out_channels, H, W, bias="output.2", out_nchw=True, want_stats=False)
         self.free(a)
         self.ncols = col
         return self
@@ -466,6 +477,17 @@ class UNet(nn.Module):
                        out[s:s + n], out[B + s:B + s + n] if cfg else None)
         return out
 
+    @contextlib.contextmanager
+    def uniform_timesteps(self):
+        """Promise that every t[n] of the calls inside the block is the same value (what the samplers do): the time
+        part of the conditioning table is then computed once per forward instead of once per image."""
+        prev = self._uniform_t
+        self._uniform_t = True
+        try:
+            yield self
+        finally:
+            self._uniform_t = prev
+
     def forward(self, x, t, y=None):
         """eps = UNet(x, t, y): x fp32 [B, C, H, W], t int64 [B], y int64 [B] in [0, num_classes] (0 = null) or None."""
         return self._run(x, t, y, cfg=False)
@@ -508,13 +530,11 @@ class _UNetPlan:
         conv_impl = int(os.environ.get("DMC_DEBUG_CONV_IMPL", "0"))
         b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl).build()
         self.workspace_bytes = b.arena.peak
-        self.stats_bytes = b.stats_bytes
         Hh, Ww = net._hw
         R = 1 if uniform_t else nimg
         temb, ncols = pk["temb"], pk["ncols"]
         assert ncols == b.ncols
         self.ws = torch.empty(max(b.arena.peak, 16), dtype=torch.uint8, device=device)
-        self.stats = torch.empty(max(b.stats_bytes, 16), dtype=torch.uint8, device=device)
         self.cond = torch.empty((nimg, ncols), dtype=torch.float32, device=device)
         self.cond_scratch = torch.empty((2 * R * temb + R * ncols,), dtype=torch.float32, device=device)
         self.t_stage = torch.zeros((nimg,), dtype=torch.long, device=device)
@@ -525,7 +545,7 @@ class _UNetPlan:
         _lib.check(lib.dmc_plan_create(C.byref(handle)), "dmc_plan_create")
         self.handle = handle
         self.op_names = []
-        wsp, stp = self.ws.data_ptr(), self.stats.data_ptr()
+        wsp = self.ws.data_ptr()
         sd = pk["sd"]
 
         def ap(a):
@@ -536,9 +556,6 @@ class _UNetPlan:
             self.op_names.append(name)
             return idx
 
-        if b.stats_bytes:
-            _lib.check(lib.dmc_plan_add_memset(handle, stp, b.stats_bytes), "memset")
-            self.op_names.append("memset.stats")
         self.stem_idx = self.cond_idx = self.head_idx = -1
         for kind, o in b.ops:
             if kind == "cond":
@@ -559,18 +576,18 @@ class _UNetPlan:
                 d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
                 d.Cin, d.H, d.W, d.Cout = net.in_channels, Hh, Ww, net.model_channels
                 d.weight, d.bias = sd["input_conv.weight"].data_ptr(), sd["input_conv.bias"].data_ptr()
-                d.out, d.stats = ap(o["out"]), None
+                d.out = ap(o["out"])
                 self.stem_idx = add(lib.dmc_plan_add_stem, d, "input_conv")
             elif kind == "gn_stats":
                 a = o["src"]
                 d = _lib.GnStatsDesc()
-                d.src, d.B, d.HW, d.C, d.stats = ap(a), nimg, a.H * a.W, a.C, stp + o["stats"]
+                d.src, d.B, d.HW, d.C, d.stats = ap(a), nimg, a.H * a.W, a.C, wsp + a.stats[0]
                 add(lib.dmc_plan_add_gn_stats, d, "gn_stats")
             elif kind == "gn_apply":
                 d = _lib.GnApplyDesc()
                 d.nsrc = len(o["srcs"])
                 for i, s in enumerate(o["srcs"]):
-                    d.src[i], d.src_c[i], d.stats[i] = ap(s), s.C, stp + o["stats"][i]
+                    d.src[i], d.src_c[i], d.stats[i], d.stats_slots[i] = ap(s), s.C, wsp + s.stats[0], s.slots
                 d.B, d.HW, d.groups = nimg, o["srcs"][0].H * o["srcs"][0].W, 8
                 d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
                 d.eps, d.silu, d.out = 1e-5, o["silu"], ap(o["out"])
@@ -592,13 +609,16 @@ class _UNetPlan:
                     d.out_f32_nchw = self.eps.data_ptr()
                 else:
                     d.out_bf16 = ap(o["out"])
-                d.stats, d.impl = None, conv_impl
+                d.impl = conv_impl
+                if conv_impl == 0 and o["out"] is not None and o["out"].stats is not None and o["want_stats"]:
+                    d.stats, d.stats_slots = wsp + o["out"].stats[0], o["out"].slots
                 idx = add(lib.dmc_plan_add_conv, d, o["wname"])
                 if o["out_nchw"]:
                     self.head_idx = idx
             elif kind == "attention":
                 d = _lib.AttnDesc()
                 d.qkv, d.out, d.B, d.L, d.heads, d.C = ap(o["qkv"]), ap(o["out"]), nimg, o["L"], 4, o["C"]
+                d.impl = int(os.environ.get("DMC_DEBUG_ATTN_IMPL", "0"))
                 add(lib.dmc_plan_add_attention, d, "attention")
             elif kind == "upsample":
                 d = _lib.UpsampleDesc()

@@ -155,15 +155,18 @@ typedef struct {
   const float* weight; /* [Cout, Cin, 3, 3] fp32 */
   const float* bias;   /* [Cout] */
   void* out;           /* bf16 [B, H, W, Cout] */
-  float* stats;        /* optional [B, Cout/8, 2] partial (sum, sumsq) accumulators, pre-zeroed */
 } dmc_stem_desc;
 DMC_API int dmc_plan_add_stem(dmc_plan* p, const dmc_stem_desc* d);
 
-/* GroupNorm statistics: accumulates (sum, sumsq) per image per 8-channel block into stats (pre-zeroed). */
+/* GroupNorm statistics as deterministic partial sums.  A statistics buffer is fp32 [B, slots, C/8, 2]: (sum, sumsq)
+ * of one image over one 8-channel block and one slice ("slot") of its pixels.  Every (image, slot, block) entry is
+ * written exactly once with a plain store (no atomics, no pre-zeroing), and the consumer adds the slots in index
+ * order -- so results are bit-reproducible and independent of what else is in the batch.
+ * This stand-alone kernel writes slots = ceil(HW / 128) (one per 128-pixel slab). */
 typedef struct {
   const void* src; /* bf16 [B, HW, C] */
   int32_t B, HW, C;
-  float* stats;    /* [B, C/8, 2] */
+  float* stats;    /* [B, ceil(HW/128), C/8, 2] */
 } dmc_gn_stats_desc;
 DMC_API int dmc_plan_add_gn_stats(dmc_plan* p, const dmc_gn_stats_desc* d);
 
@@ -173,7 +176,8 @@ typedef struct {
   int32_t nsrc;
   const void* src[2];     /* bf16 [B, HW, c_i] */
   int32_t src_c[2];
-  const float* stats[2];  /* [B, c_i/8, 2] */
+  const float* stats[2];  /* [B, stats_slots[i], c_i/8, 2] */
+  int32_t stats_slots[2];
   int32_t B, HW, groups;
   const float* gamma;     /* [C] */
   const float* beta;      /* [C] */
@@ -208,8 +212,10 @@ typedef struct {
   const void* residual;   /* bf16, same shape as out_bf16, or NULL */
   void* out_bf16;         /* bf16 NHWC [B, Hout*, Wout*, Cout] or NULL */
   float* out_f32_nchw;    /* fp32 [B, Cout, Hout, Wout] or NULL (model output head) */
-  float* stats;           /* optional [B, Cout/8, 2] accumulators of the OUTPUT (pre-zeroed) */
-  int32_t impl;           /* 0: tcgen05/TMA kernel (product path)   1: CUDA-core debug kernel (tests only) */
+  float* stats;           /* optional [B, stats_slots, Cout/8, 2] partial sums of the OUTPUT (see dmc_gn_stats_desc) */
+  int32_t stats_slots;    /* must equal max(1, P/32) * (up_phase >= 0 ? 4 : 1), P = iteration pixels per image
+                             (Hin/stride * Win/stride): one slot per 32-pixel epilogue warp, per phase */
+  int32_t impl;           /* 0: tcgen05/TMA kernel (product path)   1: CUDA-core debug kernel (tests only, no stats) */
 } dmc_conv_desc;
 DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
 
@@ -219,6 +225,8 @@ typedef struct {
   const void* qkv;
   void* out;
   int32_t B, L, heads, C;
+  int32_t impl; /* 0: tcgen05/TMA kernel (head dim 64, L in {16, 32, 64, 128, 256}; other shapes run the CUDA-core
+                   flash kernel)   1: force the CUDA-core flash kernel (tests / debugging) */
 } dmc_attn_desc;
 DMC_API int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d);
 

@@ -76,8 +76,10 @@ def run_conv(srcs, taps, wmat, Cout, *, stride=1, bias=None, cond=None, residual
                                                                    dtype=torch.bfloat16)
         d.out_bf16 = out.data_ptr()
     if stats:
-        st = torch.zeros((B, Cout // 8, 2), device=dev)
-        d.stats = st.data_ptr()
+        ppi = (H // stride) * (W // stride)
+        slots = max(1, ppi // 32) * (4 if up_phase >= 0 else 1)
+        st = torch.full((B, slots, Cout // 8, 2), float("nan"), device=dev)  # every slot must be written
+        d.stats, d.stats_slots = st.data_ptr(), slots
     d.impl = impl
     p = Plan()
     p.add("conv", d)

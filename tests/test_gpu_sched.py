@@ -139,15 +139,38 @@ def _cpu_toy(x, t, y=None):
 
 
 def _with_cpu_tables(d, T=1000):
-    """inject the CPU-computed schedule (linspace + cumprod differ in the last bit between CPU and CUDA; the reference
-    builds them on its own device -- the goldens were written on the CPU)"""
+    """inject the schedule and the per-step coefficient rows computed on the CPU with the same expressions (linspace,
+    cumprod, exp, log differ in the last bit between the CPU and CUDA back ends; the reference builds its tables on its
+    own device, and the goldens were written on the CPU)"""
     tb = so.make_tables(T)
-    for k in ("betas", "alphas", "alphas_cumprod"):
-        setattr(d, k, tb[k].cuda())
-    d._coef_cache = None
     if hasattr(d, "posterior_mean_coef1"):
         d._coef_cache = _ddpm_rows(tb).cuda()
+    else:
+        ts = d.inference_timesteps.cpu()
+        nxt = torch.cat([ts[1:], torch.full((1,), -1, dtype=ts.dtype)])
+        d.alphas_cumprod = tb["alphas_cumprod"]
+        d._coef_cache = d._coef_rows(ts, nxt).cuda()
+    for k in ("betas", "alphas", "alphas_cumprod"):
+        setattr(d, k, tb[k].cuda())
     return d
+
+
+def test_device_coefficient_rows_match_cpu_rows():
+    """the [S, 5] DDIM rows computed on the CUDA device from the SAME alphas_cumprod: sqrt / div / clamp are correctly
+    rounded on both back ends, so they must be bit-equal"""
+    from diffusion_models_collection_b200.diffusion import DDIM
+
+    tb = so.make_tables()
+    for eta in (0.0, 0.3):
+        d = DDIM(1000, 50, eta=eta, device="cuda")
+        ts = d.inference_timesteps
+        nxt = torch.cat([ts[1:], torch.full((1,), -1, dtype=ts.dtype, device=ts.device)])
+        d.alphas_cumprod = tb["alphas_cumprod"].cuda()
+        dev_rows = d._coef_rows(ts, nxt).cpu()
+        d.alphas_cumprod = tb["alphas_cumprod"]
+        cpu_rows = d._coef_rows(ts.cpu(), nxt.cpu())
+        bad = (dev_rows != cpu_rows).nonzero()
+        assert bad.numel() == 0, (eta, bad[:5].tolist(), dev_rows[dev_rows != cpu_rows][:5], cpu_rows[dev_rows != cpu_rows][:5])
 
 
 def test_sampler_loops_bit_exact_vs_golden(lib, golden):
@@ -203,9 +226,11 @@ def test_device_tables_close_to_cpu_tables_and_timesteps_exact(golden):
     d.set_inference_steps(25)
     assert np.array_equal(d.inference_timesteps.cpu().numpy(), g["timesteps.set25"])
     p = DDPM(1000, device="cuda")
-    for k in ("betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_recipm1_alphas_cumprod"):
+    # 1 - alphas_cumprod[0] ~ 1e-4 amplifies a 1-ulp difference of the cumprod ~1e3 times in the posterior coefficients
+    for k, tol in (("betas", 1e-6), ("alphas_cumprod", 1e-6), ("sqrt_recipm1_alphas_cumprod", 1e-3),
+                   ("posterior_mean_coef1", 1e-3), ("posterior_mean_coef2", 1e-3)):
         a, b = getattr(p, k).cpu().double(), torch.from_numpy(g["linear." + k]).double()
-        assert float(((a - b).abs() / b.abs().clamp_min(1e-12)).max()) < 1e-5, k
+        assert float(((a - b).abs() / b.abs().clamp_min(1e-12)).max()) < tol, k
 
 
 def test_api_errors():
