@@ -281,7 +281,8 @@ def roofline_leg(net, dev, nb, pk, ops_out):
     """Per-op device times of ONE forward (CUDA events on the launching stream, each op timed alone -> burst peak),
     aggregated per kernel family.  Dominant kernel: the tcgen05 implicit-GEMM convolution."""
     nimg = min(2 * nb, net.max_images_per_launch)
-    plan = net.plan_info(nimg // 2, cfg=True, device=dev)
+    with net.uniform_timesteps():  # what the sampling loop runs
+        plan = net.plan_info(nimg // 2, cfg=True, device=dev)
     ops = plan.time_ops(iters=3)
     fam = {}
     for o in ops:

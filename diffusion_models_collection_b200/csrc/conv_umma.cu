@@ -10,12 +10,12 @@
 //     map's element strides.  The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle,
 //     i.e. exactly the K-major SWIZZLE_128B operand layout tcgen05.mma consumes.
 //   * W is a bf16 [Cout_pad, Ktot] matrix (K ordered like the K-blocks), loaded as {64, BN} boxes.
-//   * One CTA per SM, persistent over output tiles (128 pixels x BN channels), warp-specialised:
+//   * One CTA per SM, persistent over output tiles (MT x 128 pixels x BN channels), warp-specialised:
 //       warp 0 lane 0 : TMA producer          (smem ring of NST stages, full/empty mbarriers)
-//       warp 1 lane 0 : tcgen05.mma issuer    (UMMA 128 x BN x 16, fp32 accumulate, 2 TMEM accumulators)
+//       warp 1 lane 0 : tcgen05.mma issuer    (UMMA 128 x BN x 16, fp32 accumulate, 2 TMEM accumulator stages)
 //       warp 2        : TMEM allocator
-//       warps 4..7    : epilogue: tcgen05.ld -> +bias +cond +residual -> GroupNorm partial sums -> bf16 NHWC
-//                       (or fp32 NCHW for the model head), overlapped with the next tile's MMAs.
+//       warps 4..11   : epilogue: tcgen05.ld -> +bias +cond +residual -> bf16 NHWC (or fp32 NCHW for the model
+//                       head) -> GroupNorm partial sums, overlapped with the next tile's MMAs.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,26 +56,87 @@ struct ConvPrepared {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
   ConvKParams kp;
-  int BN;
+  int BN, MT;
   int grid;
   size_t smem;
 };
 
-template <int BN>
+template <int BN, int MT>
 struct ConvCfg {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
   static constexpr int B_STAGE_BYTES = BN * KB * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int NST = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int ACC_COLS = MT * BN;  // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr size_t SMEM = static_cast<size_t>(NST) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+constexpr int CONV_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4..11 epilogue
+constexpr int EPI_THREADS = 256;
+
+// Sums each of 8 per-lane values over the 32 lanes of the warp (full) or over each 16-lane half, with 9 (8) shuffles
+// instead of 40: every round halves the number of values a lane carries.  On return `r` is the total of value `idx`.
+__device__ __forceinline__ void reduce8(const float (&v)[8], bool full, int lane, float& r, int& idx) {
+  float w[4];
+  int base;
+  if (full) {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, hi ? v[i] : v[4 + i], 16);
+      w[i] = (hi ? v[4 + i] : v[i]) + recv;
+    }
+    base = hi ? 4 : 0;
+    const bool h8 = (lane & 8) != 0;
+    float u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h8 ? w[i] : w[2 + i], 8);
+      u[i] = (h8 ? w[2 + i] : w[i]) + recv;
+    }
+    base += h8 ? 2 : 0;
+    const bool h4 = (lane & 4) != 0;
+    const float recv = __shfl_xor_sync(0xFFFFFFFFu, h4 ? u[0] : u[1], 4);
+    float t = (h4 ? u[1] : u[0]) + recv;
+    base += h4 ? 1 : 0;
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 2);
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+    r = t;
+    idx = base;
+  } else {
+    const bool h8 = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h8 ? v[i] : v[4 + i], 8);
+      w[i] = (h8 ? v[4 + i] : v[i]) + recv;
+    }
+    base = h8 ? 4 : 0;
+    const bool h4 = (lane & 4) != 0;
+    float u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h4 ? w[i] : w[2 + i], 4);
+      u[i] = (h4 ? w[2 + i] : w[i]) + recv;
+    }
+    base += h4 ? 2 : 0;
+    const bool h2 = (lane & 2) != 0;
+    const float recv = __shfl_xor_sync(0xFFFFFFFFu, h2 ? u[0] : u[1], 2);
+    float t = (h2 ? u[1] : u[0]) + recv;
+    base += h2 ? 1 : 0;
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+    r = t;
+    idx = base;
+  }
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   constexpr int NST = Cfg::NST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -87,7 +148,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_ct = (p.num_m_tiles + MT - 1) / MT;  // CTA tiles along M (MT consecutive 128-pixel tiles each)
+  const int num_tiles = num_ct * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -102,7 +164,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EPI_THREADS);
     }
     mbar_fence_init();
   }
@@ -121,11 +183,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int ti = m_tile / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.BW * p.stride, h0 = th * p.BH * p.stride, n0 = ti * p.BNIMG;
+        const int ct = tile / p.num_n_tiles;
+        int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m_tile = ct * MT + mt;  // may be one past the end: its box is fully out of bounds -> zero fill
+          w0[mt] = (m_tile % p.tiles_w) * p.BW * p.stride;
+          h0[mt] = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH * p.stride;
+          n0[mt] = (m_tile / (p.tiles_w * p.tiles_h)) * p.BNIMG;
+        }
         int seg = 0, kb_in_seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int stage = it % NST;
@@ -133,11 +199,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
           const int chunks = p.seg_chunks[seg];
           const int tap = kb_in_seg / chunks, chunk = kb_in_seg % chunks;
           const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
-          tma_load_4d(sa, tm, &full_bar[stage], chunk * KB, w0 + p.dw[seg][tap], h0 + p.dh[seg][tap], n0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &full_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
+                        h0[mt] + p.dh[seg][tap], n0[mt]);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
           if (++kb_in_seg == p.seg_taps[seg] * chunks) {
             ++seg;
@@ -156,40 +225,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t acc_phase = (local >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int stage = it % NST;
           const uint32_t phase = (it / NST) & 1u;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < KB / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = umma_desc_k_sw128(sa + mt * A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < KB / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit(&tfull_bar[acc]);  // accumulators complete -> epilogue
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;             // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // warp -> TMEM lane quarter q (= warp % 4, the hardware rule) and group grp: with MT == 2 the group is the
+    // 128-pixel sub-tile, with MT == 1 it is the half of the BN output channels this warp converts.
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int row = q * 32 + lane;      // tile row == TMEM lane
-    const int ppi = p.BW * p.BH;        // pixels per image inside one tile
+    const int ppi = p.BW * p.BH;        // pixels per image inside one 128-pixel tile
+    constexpr int COLS = (MT == 2) ? BN : (BN >= 64 ? BN / 2 : BN);
+    const int col0 = (MT == 2) ? 0 : (BN >= 64 ? grp * COLS : 0);
+    const bool idle = (MT == 1 && BN < 64 && grp == 1);
+    const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / ppi;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const uint32_t acc = local & 1u;
       const uint32_t acc_phase = (local >> 1) & 1u;
       const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+      const int m_tile = (tile / p.num_n_tiles) * MT + (MT == 2 ? grp : 0);
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int ti = m_tile / (p.tiles_w * p.tiles_h);
-      const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / ppi;
       const int n = ti * p.BNIMG + ni;
       const int oh = (th * p.BH + hi) * p.oscale + p.ooff_h;
       const int ow = (tw * p.BW + wi) * p.oscale + p.ooff_w;
@@ -198,104 +276,117 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS +
+                             (MT == 2 ? grp * BN : 0) + col0;
+      if (!idle) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c0, r);
-        tmem_ld_wait();
-        const int cg = n_tile * BN + c0;  // first global output channel of this chunk
-        if (cg >= p.Cout) continue;       // padded weight rows (warp-uniform)
-        float v[32];
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          const int cg = n_tile * BN + col0 + c0;  // first global output channel of this chunk
+          // per-channel addends (warp-uniform addresses -> L1 broadcast), fetched while the TMEM load is in flight
+          float add[32];
+          const bool real = cg < p.Cout;  // false only for padded weight rows (warp-uniform)
+          if (p.out_nchw == nullptr && real) {
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.out_nchw != nullptr) {
-          // model head: few real channels, fp32 NCHW, coalesced along W across the warp
-          if (valid) {
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = cg + j;
-              if (c < p.Cout) {
-                float o = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
-                p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+              for (int j = 0; j < 32; ++j) add[j] = 0.f;
+            }
+            if (p.cond != nullptr && valid) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(c4 + j);
+                add[4 * j] += b.x; add[4 * j + 1] += b.y; add[4 * j + 2] += b.z; add[4 * j + 3] += b.w;
               }
             }
           }
-          continue;
-        }
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+          uint4 res[4];
+          const bool has_res = p.residual != nullptr && valid && real && p.out_nchw == nullptr;
+          if (has_res) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            for (int j = 0; j < 4; ++j) res[j] = __ldg(r4 + j);
           }
-        }
-        if (p.cond != nullptr && valid) {
-          const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
+          tmem_ld_wait();
+          if (!real) continue;
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = __ldg(c4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.out_nchw != nullptr) {
+            // model head: few real channels, fp32 NCHW, coalesced along W across the warp
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = cg + j;
+                if (c < p.Cout) {
+                  float o = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
+                  p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+                }
+              }
+            }
+            continue;
           }
-        }
-        if (p.residual != nullptr && valid) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u = __ldg(r4 + j);
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          for (int j = 0; j < 32; ++j) v[j] += add[j];
+          if (has_res) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 f = unpack_bf16x2(w[k]);
-              v[8 * j + 2 * k] += f.x;
-              v[8 * j + 2 * k + 1] += f.y;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16x2(w[k]);
+                v[8 * j + 2 * k] += f.x;
+                v[8 * j + 2 * k + 1] += f.y;
+              }
             }
           }
-        }
-        if (p.stats != nullptr) {
-          // GroupNorm partial sums of the OUTPUT per (image, 8-channel block): reduce over the rows of this warp that
-          // belong to the same image (32 when ppi >= 32, else 16-lane halves) and store them in this warp's own slot
-          // (plain stores, no atomics: deterministic and batch-invariant; the consumer adds the slots in order).
-          const int wpi = ppi >> 5;  // epilogue warps per image inside one tile (0 when an image is a half-warp)
-          const int slot = p.stats_slot_base + ((ppi >= 32) ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
+          if (valid && p.out != nullptr) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            float s = 0.f, ss = 0.f;
-            if (valid) {
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o4[j] = u;
+            }
+          }
+          if (p.stats != nullptr) {
+            // GroupNorm partial sums of the OUTPUT per (image, 8-channel block) over the rows of this warp that belong
+            // to one image (all 32 when ppi >= 32, else each 16-lane half), stored in this warp's own slot: plain
+            // stores, no atomics -> deterministic and batch-invariant; the consumer adds the slots in index order.
+            float sv[8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float s = 0.f, ss = 0.f;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 s += v[8 * b + j];
                 ss = fmaf(v[8 * b + j], v[8 * b + j], ss);
               }
+              sv[b] = valid ? s : 0.f;
+              sv[4 + b] = valid ? ss : 0.f;
             }
-#pragma unroll
-            for (int o = 8; o; o >>= 1) {
-              s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-              ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-            }
-            if (ppi >= 32) {
-              s += __shfl_xor_sync(0xFFFFFFFFu, s, 16);
-              ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 16);
-            }
-            const bool writer = (ppi >= 32) ? (lane == 0) : ((lane & 15) == 0);
+            const bool full = ppi >= 32;
+            float tot;
+            int idx;
+            reduce8(sv, full, lane, tot, idx);
+            const bool writer = full ? ((lane & 3) == 0) : ((lane & 1) == 0);
             if (writer && valid) {
-              float2* dst = reinterpret_cast<float2*>(p.stats) +
-                            (static_cast<size_t>(n) * p.stats_slots + slot) * (p.Cout >> 3) + ((cg >> 3) + b);
-              *dst = make_float2(s, ss);
+              const int wpi = ppi >> 5;  // epilogue warps per image inside one tile (0: an image is a half-warp)
+              const int slot = p.stats_slot_base + (full ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
+              float* dst = p.stats + ((static_cast<size_t>(n) * p.stats_slots + slot) * (p.Cout >> 3) + ((cg >> 3) + (idx & 3))) * 2;
+              dst[idx >> 2] = tot;
             }
-          }
-        }
-        if (valid && p.out != nullptr) {
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            o4[j] = u;
           }
         }
       }
@@ -326,14 +417,21 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return 0;
 }
 
-static int pick_bn(int cout_pad, int m_tiles) {
+// Tile configuration (BN output channels x MT 128-pixel sub-tiles per CTA tile).  Bytes staged per MAC fall with
+// MT * BN (the A tile is reused by BN channels, the B tile by MT * 128 pixels): prefer 256 TMEM columns per
+// accumulator when that still yields at least one tile per SM.
+struct TileCfg { int bn, mt; };
+static TileCfg pick_cfg(int cout_pad, int m_tiles) {
   const int sms = num_sms();
-  const int cands[3] = {256, 128, 64};
-  for (int bn : cands)
-    if (cout_pad % bn == 0 && static_cast<long long>(m_tiles) * (cout_pad / bn) >= sms) return bn;
-  for (int i = 2; i >= 0; --i)
-    if (cout_pad % cands[i] == 0) return cands[i];
-  return 32;
+  const TileCfg cands[5] = {{256, 1}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
+  for (const TileCfg& c : cands) {
+    if (cout_pad % c.bn != 0) continue;
+    const long long tiles = static_cast<long long>((m_tiles + c.mt - 1) / c.mt) * (cout_pad / c.bn);
+    if (tiles >= sms) return c;
+  }
+  for (int i = 4; i >= 0; --i)
+    if (cout_pad % cands[i].bn == 0) return cands[i];
+  return {32, 1};
 }
 
 int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
@@ -406,8 +504,10 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     DMC_REQUIRE(false, "conv: Ktot=%d does not match the sources (%d)", d.Ktot, kb * KB);
   }
 
-  const int BN = pick_bn(d.Cout_pad, kp.num_m_tiles);
+  const TileCfg tc = pick_cfg(d.Cout_pad, kp.num_m_tiles);
+  const int BN = tc.bn;
   P->BN = BN;
+  P->MT = tc.mt;
   kp.num_n_tiles = d.Cout_pad / BN;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Ktot), static_cast<cuuint64_t>(d.Cout_pad)};
@@ -434,23 +534,23 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     kp.stats_slots = want;
     kp.stats_slot_base = d.up_phase >= 0 ? d.up_phase * base : 0;
   }
-  P->grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
-  P->smem = BN == 256 ? ConvCfg<256>::SMEM : BN == 128 ? ConvCfg<128>::SMEM : BN == 64 ? ConvCfg<64>::SMEM : ConvCfg<32>::SMEM;
+  P->grid = std::min(((kp.num_m_tiles + tc.mt - 1) / tc.mt) * kp.num_n_tiles, num_sms());
+  P->smem = 0;
   *out = P;
   return 0;
 }
 
 void conv_release(ConvPrepared* p) { delete p; }
 
-template <int BN>
-static int launch_bn(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
+template <int BN, int MT>
+static int launch_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(ConvCfg<BN>::SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(ConvCfg<BN, MT>::SMEM)));
     attr_set = true;
   }
-  conv_umma_kernel<BN><<<P->grid, 256, ConvCfg<BN>::SMEM, st>>>(P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp);
+  conv_umma_kernel<BN, MT><<<P->grid, CONV_THREADS, ConvCfg<BN, MT>::SMEM, st>>>(P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -458,11 +558,12 @@ static int launch_bn(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t 
 int launch_conv(const dmc_conv_desc& d, const ConvPrepared* P, cudaStream_t st) {
   ConvKParams kp = P->kp;
   kp.out_nchw = d.out_f32_nchw;  // the only re-bindable pointer (dmc_plan_rebind which=2)
+  if (P->MT == 2) return launch_cfg<128, 2>(P, kp, st);
   switch (P->BN) {
-    case 256: return launch_bn<256>(P, kp, st);
-    case 128: return launch_bn<128>(P, kp, st);
-    case 64: return launch_bn<64>(P, kp, st);
-    default: return launch_bn<32>(P, kp, st);
+    case 256: return launch_cfg<256, 1>(P, kp, st);
+    case 128: return launch_cfg<128, 1>(P, kp, st);
+    case 64: return launch_cfg<64, 1>(P, kp, st);
+    default: return launch_cfg<32, 1>(P, kp, st);
   }
 }
 

@@ -290,59 +290,103 @@ struct GnApplyArgs {
   int silu;
 };
 
+// Phase 1 (per CTA, cheap): warp g reduces the partial sums of group g (slots x 8-channel blocks, possibly from both
+// sources of a concat) with lane-strided loads and a fixed shuffle tree -> mean / rstd, bit-reproducible.
+// Phase 2: every thread owns ONE 8-channel block (its 8 scales / shifts live in registers) and walks the pixels of the
+// slab: one 128-bit load, 8 FMAs (+ SiLU), one 128-bit store per pixel, four pixels in flight.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
-  extern __shared__ float sc[];  // scale[C], shift[C]
+  __shared__ float s_mean[32], s_rstd[32];
   const int C8 = a.C0_8 + a.C1_8;
-  const int C = C8 * 8;
-  float* scale = sc;
-  float* shift = sc + C;
   const int n = blockIdx.y;
   const int gs8 = C8 / a.groups;  // 8-channel blocks per group
-  const float inv_cnt = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.HW));
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = (c >> 3) / gs8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < a.groups; g += 8) {
+    const int blo = g * gs8, bhi = blo + gs8;
     float s = 0.f, ss = 0.f;
-    for (int b = g * gs8; b < (g + 1) * gs8; ++b) {  // fixed order: blocks, then slots -> bit-reproducible
-      const bool first = b < a.C0_8;
-      const int slots = first ? a.slots0 : a.slots1;
-      const int c8 = first ? a.C0_8 : a.C1_8;
-      const float2* p = reinterpret_cast<const float2*>(first ? a.stats0 : a.stats1) +
-                        static_cast<size_t>(n) * slots * c8 + (first ? b : b - a.C0_8);
-      for (int sl = 0; sl < slots; ++sl) {
-        const float2 v = __ldg(p + static_cast<size_t>(sl) * c8);
+    {  // blocks of this group that live in source 0
+      const int lo = min(blo, a.C0_8), hi = min(bhi, a.C0_8), nb = hi - lo;
+      const float2* base = reinterpret_cast<const float2*>(a.stats0) + static_cast<size_t>(n) * a.slots0 * a.C0_8;
+      for (int e = lane; e < nb * a.slots0; e += 32) {
+        const float2 v = __ldg(base + static_cast<size_t>(e / nb) * a.C0_8 + lo + e % nb);
         s += v.x;
         ss += v.y;
       }
     }
-    const float mean = s * inv_cnt;
-    const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + a.eps);
-    const float gsc = rstd * a.gamma[c];
-    scale[c] = gsc;
-    shift[c] = a.beta[c] - mean * gsc;
+    if (a.C1_8 > 0) {  // ... and in source 1
+      const int lo = max(blo, a.C0_8) - a.C0_8, hi = max(bhi, a.C0_8) - a.C0_8, nb = hi - lo;
+      const float2* base = reinterpret_cast<const float2*>(a.stats1) + static_cast<size_t>(n) * a.slots1 * a.C1_8;
+      for (int e = lane; e < nb * a.slots1; e += 32) {
+        const float2 v = __ldg(base + static_cast<size_t>(e / nb) * a.C1_8 + lo + e % nb);
+        s += v.x;
+        ss += v.y;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    }
+    if (lane == 0) {
+      const float inv_cnt = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.HW));
+      const float mean = s * inv_cnt;
+      const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + a.eps);
+    }
   }
   __syncthreads();
+  const int cb = threadIdx.x % C8, r0 = threadIdx.x / C8;
+  const int rpi = blockDim.x / C8;  // pixel rows per iteration
+  if (r0 >= rpi) return;
+  float sc[8], sh[8];
+  {
+    const int g = cb / gs8;
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma + cb * 8);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta + cb * 8);
+    const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), ba = __ldg(b4), bb = __ldg(b4 + 1);
+    const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = rstd * gam[j];
+      sh[j] = bet[j] - mean * sc[j];
+    }
+  }
+  const bool first = cb < a.C0_8;
+  const uint4* src = first ? a.src0 + static_cast<size_t>(n) * a.HW * a.C0_8 + cb
+                           : a.src1 + static_cast<size_t>(n) * a.HW * a.C1_8 + (cb - a.C0_8);
+  const int sstride = first ? a.C0_8 : a.C1_8;
+  uint4* dst = a.out + static_cast<size_t>(n) * a.HW * C8 + cb;
   const int p0 = blockIdx.x * GN_SLAB;
   const int p1 = min(p0 + GN_SLAB, a.HW);
-  const int nvec = (p1 - p0) * C8;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    const int p = p0 + v / C8, cb = v % C8;
-    uint4 in = (cb < a.C0_8) ? a.src0[(static_cast<size_t>(n) * a.HW + p) * a.C0_8 + cb]
-                             : a.src1[(static_cast<size_t>(n) * a.HW + p) * a.C1_8 + (cb - a.C0_8)];
-    uint32_t u[4] = {in.x, in.y, in.z, in.w}, o[4];
+  for (int pb = p0 + r0; pb < p1; pb += 4 * rpi) {
+    uint4 in[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = unpack_bf16x2(u[j]);
-      const int c = cb * 8 + 2 * j;
-      float y0 = fmaf(f.x, scale[c], shift[c]);
-      float y1 = fmaf(f.y, scale[c + 1], shift[c + 1]);
-      if (a.silu) {
-        y0 = silu_f(y0);
-        y1 = silu_f(y1);
-      }
-      o[j] = pack_bf16x2(y0, y1);
+    for (int u = 0; u < 4; ++u) {
+      const int p = pb + u * rpi;
+      if (p < p1) in[u] = __ldg(src + static_cast<size_t>(p) * sstride);
     }
-    a.out[(static_cast<size_t>(n) * a.HW + p) * C8 + cb] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = pb + u * rpi;
+      if (p < p1) {
+        const uint32_t w[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
+          float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+          if (a.silu) {
+            y0 = silu_f(y0);
+            y1 = silu_f(y1);
+          }
+          o[j] = pack_bf16x2(y0, y1);
+        }
+        dst[static_cast<size_t>(p) * C8] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
 }
 
@@ -351,8 +395,9 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.src[0] && d.stats[0] && d.gamma && d.beta && d.out, "gn_apply: null pointer argument");
   const int C0 = d.src_c[0], C1 = d.nsrc == 2 ? d.src_c[1] : 0;
   const int C = C0 + C1;
-  DMC_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && d.groups > 0 && (C / 8) % d.groups == 0,
-              "gn_apply: channels (%d + %d) must split into %d groups of a multiple of 8", C0, C1, d.groups);
+  DMC_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && d.groups > 0 && d.groups <= 32 && (C / 8) % d.groups == 0 && C / 8 <= 256,
+              "gn_apply: channels (%d + %d) must split into %d (<= 32) groups of a multiple of 8, C <= 2048", C0, C1,
+              d.groups);
   if (d.nsrc == 2) DMC_REQUIRE(d.src[1] && d.stats[1], "gn_apply: second source missing");
   GnApplyArgs a;
   a.src0 = reinterpret_cast<const uint4*>(d.src[0]);
@@ -365,7 +410,7 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.slots1 = d.nsrc == 2 ? d.stats_slots[1] : 0;
   DMC_REQUIRE(a.slots0 > 0 && (d.nsrc == 1 || a.slots1 > 0), "gn_apply: stats_slots must be positive");
   dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
-  gn_apply_kernel<<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(a);
+  gn_apply_kernel<<<grid, 256, 0, st>>>(a);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

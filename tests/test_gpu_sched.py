@@ -156,8 +156,9 @@ def _with_cpu_tables(d, T=1000):
 
 
 def test_device_coefficient_rows_match_cpu_rows():
-    """the [S, 5] DDIM rows computed on the CUDA device from the SAME alphas_cumprod: sqrt / div / clamp are correctly
-    rounded on both back ends, so they must be bit-equal"""
+    """the [S, 5] DDIM rows computed on the CUDA device from the SAME alphas_cumprod, with the reference's own torch
+    expressions: equal to the CPU rows up to 1 ulp (torch's CUDA sqrt differs from the CPU's in the last bit for a few
+    arguments -- the reference run on this device has the same rows as we do; tolerance 2e-7 relative)"""
     from diffusion_models_collection_b200.diffusion import DDIM
 
     tb = so.make_tables()
@@ -169,8 +170,8 @@ def test_device_coefficient_rows_match_cpu_rows():
         dev_rows = d._coef_rows(ts, nxt).cpu()
         d.alphas_cumprod = tb["alphas_cumprod"]
         cpu_rows = d._coef_rows(ts.cpu(), nxt.cpu())
-        bad = (dev_rows != cpu_rows).nonzero()
-        assert bad.numel() == 0, (eta, bad[:5].tolist(), dev_rows[dev_rows != cpu_rows][:5], cpu_rows[dev_rows != cpu_rows][:5])
+        rel = ((dev_rows - cpu_rows).abs() / cpu_rows.abs().clamp_min(1e-30)).max()
+        assert float(rel) < 2e-7, (eta, float(rel))
 
 
 def test_sampler_loops_bit_exact_vs_golden(lib, golden):

@@ -17,7 +17,7 @@ for k in conv3x3 conv1x1 shortcut head_conv phase stem groupnorm attention condi
 done
 run unet tests/test_gpu_unet.py
 if [ "$1" != "nobench" ]; then
-  timeout 900 python bench.py --batch 256 --steps 1 --warmup 3 --ops-out $OUT/ops_b256.json > $OUT/bench_b256.log 2>&1
-  echo "bench_b256 exit $? :: $(tail -c 300 $OUT/bench_b256.log)" >> $OUT/summary.txt
+  timeout 900 python bench.py --batch ${BENCH_BATCH:-1024} --steps 1 --warmup 3 --ops-out $OUT/ops.json > $OUT/bench.log 2>&1
+  echo "bench exit $? :: $(tail -c 300 $OUT/bench.log)" >> $OUT/summary.txt
 fi
 cat $OUT/summary.txt
