@@ -9,12 +9,12 @@
 //              back to back by the same CTA and share the K / V tiles in shared memory.
 //   L <  128 : the tile holds 128/L whole images; scores are computed for the 128 x 128 block and everything outside
 //              the block diagonal (other images) is masked to probability 0.
-// Pipeline of one CTA (192 threads):
-//   warp 4 lane 0 : TMA producer  (Q tile {64 x 128}, K and V tiles {64 x keys}, SWIZZLE_128B)
-//   warp 5 lane 0 : tcgen05.mma issuer:  S[128 x keys] = Q K^T  (A, B K-major)   -> TMEM columns [0, keys)
-//                                        O[128 x 64]   = P V    (A = P from smem, B = V MN-major) -> columns [256, 320)
-//   warps 0..3    : softmax: tcgen05.ld S row (thread = query row), max / exp2 / sum in fp32, P as bf16 into shared
-//                   memory in the K-major SWIZZLE_128B operand layout; then O * (1/sum) -> bf16 -> global.
+// Pipeline of one CTA (320 threads), two q-tiles ("slots") in flight:
+//   warp 8 lane 0 : TMA producer  (Q tile {64 x 128} per slot, K and V tiles {64 x keys}, SWIZZLE_128B)
+//   warp 9 lane 0 : tcgen05.mma issuer:  S[128 x keys] = Q K^T  (A, B K-major)
+//                                        O[128 x 64]   = P V    (A = P from smem, B = V MN-major)
+//   warps 0..3 / 4..7 : softmax of slot 0 / 1: tcgen05.ld S row (thread = query row), max / exp2 / sum in fp32, P as
+//                   bf16 into shared memory in the K-major SWIZZLE_128B operand layout; then O * (1/sum) -> bf16.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,17 +25,17 @@ namespace dmc {
 constexpr int AT_M = 128;
 constexpr int AT_HD = 64;
 constexpr int AT_MAXKEYS = 256;
-constexpr int AT_Q_BYTES = AT_M * AT_HD * 2;             // 16 KB
-constexpr int AT_KV_BYTES = AT_MAXKEYS * AT_HD * 2;      // 32 KB each
-constexpr int AT_P_BYTES = AT_M * AT_MAXKEYS * 2;        // 64 KB
-constexpr int AT_O_COL = 256;
-constexpr size_t AT_SMEM = AT_Q_BYTES + 2 * AT_KV_BYTES + AT_P_BYTES + 1024 + 256;
+constexpr int AT_Q_BYTES = AT_M * AT_HD * 2;             // 16 KB per slot
+constexpr int AT_KV_BYTES = AT_MAXKEYS * AT_HD * 2;      // 32 KB each (K, V): one 256-key tile or two 128-key tiles
+constexpr int AT_P_BYTES = AT_M * AT_MAXKEYS * 2;        // 64 KB per slot
+constexpr int AT_THREADS = 320;                          // warps 0-3 softmax slot 0, 4-7 softmax slot 1, 8 TMA, 9 MMA
+constexpr size_t AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KV_BYTES + 2 * AT_P_BYTES + 1024 + 256;
 
 struct AttnParams {
   int L, heads, C;
-  int keys;            // key rows per tile: max(L, 128)
-  int qtiles;          // q tiles per item group: L / 128 (>= 1)
-  int groups;          // item groups: L >= 128 ? B * heads : ceil(B*L / 128) * heads
+  int keys;            // key rows per q-tile: max(L, 128)
+  int tiles;           // q-tiles (128 token rows x one head) in total
+  int items;           // work items = pairs of q-tiles (slot 0, slot 1): ceil(tiles / 2)
   int total_rows;      // B * L
   float scale_log2e;
   __nv_bfloat16* out;
@@ -58,43 +58,76 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// q-tile t -> (head, first token row of its queries, first token row of its keys)
+__device__ __forceinline__ void tile_coords(const AttnParams& p, int t, int& h, int& q_row0, int& key_row0) {
+  if (p.L >= AT_M) {
+    const int qpi = p.L / AT_M;  // q-tiles per (image, head); the two tiles of a pair share K / V when qpi == 2
+    const int qt = t % qpi;
+    const int g = t / qpi;
+    h = g % p.heads;
+    key_row0 = (g / p.heads) * p.L;
+    q_row0 = key_row0 + qt * AT_M;
+  } else {
+    h = t % p.heads;
+    key_row0 = (t / p.heads) * AT_M;
+    q_row0 = key_row0;
+  }
+}
+
+// Two q-tiles are in flight per CTA (slot 0 / slot 1, one softmax warpgroup each): while one warpgroup runs its
+// exponentials the tensor core computes the other slot's S = Q K^T or O = P V, and the TMA warp prefetches the next
+// pair's Q / K / V.  TMEM: slot s owns columns [256 s, 256 s + 256): S first, then (S is dead once P is in shared
+// memory) O in its first 64 columns.
+template <bool SMALL>
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_Q_BYTES;
-  uint8_t* sV = sK + AT_KV_BYTES;
-  uint8_t* sP = sV + AT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* kv_empty = bars + 1;
-  uint64_t* q_full = bars + 2;
-  uint64_t* q_empty = bars + 3;
-  uint64_t* s_full = bars + 4;
-  uint64_t* s_empty = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sQ = smem;                      // 2 x 16 KB
+  uint8_t* sK = sQ + 2 * AT_Q_BYTES;       // 32 KB
+  uint8_t* sV = sK + AT_KV_BYTES;          // 32 KB
+  uint8_t* sP = sV + AT_KV_BYTES;          // 2 x 64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
+  uint64_t* k_full = bars + 0;
+  uint64_t* k_empty = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_empty = bars + 3;
+  uint64_t* q_full = bars + 4;    // [2]
+  uint64_t* q_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;    // [2]
+  uint64_t* s_empty = bars + 10;  // [2]
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* o_full = bars + 14;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_empty, 1);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_full[s], 1);
+    }
     mbar_fence_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -104,150 +137,179 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   const int keys = p.keys;
-  const bool small = p.L < AT_M;
+  const bool shared_kv = (p.L == 2 * AT_M);            // both slots of an item read the same 256-key K / V tiles
+  const int kv_slot_bytes = shared_kv ? 0 : AT_KV_BYTES / 2;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0, qi = 0;
-      for (int g = blockIdx.x; g < p.groups; g += gridDim.x, ++it) {
-        const int h = g % p.heads;
-        const int blk = g / p.heads;  // image (L >= 128) or 128-row block (L < 128)
-        const int key_row0 = small ? blk * AT_M : blk * p.L;
-        mbar_wait(kv_empty, (it & 1u) ^ 1u);
-        mbar_expect_tx(kv_full, static_cast<uint32_t>(2 * keys * AT_HD * 2));
-        tma_load_2d(sK, &tmKV, kv_full, p.C + h * AT_HD, key_row0);
-        tma_load_2d(sV, &tmKV, kv_full, 2 * p.C + h * AT_HD, key_row0);
-        for (int qt = 0; qt < p.qtiles; ++qt, ++qi) {
-          mbar_wait(q_empty, (qi & 1u) ^ 1u);
-          mbar_expect_tx(q_full, AT_Q_BYTES);
-          tma_load_2d(sQ, &tmQ, q_full, h * AT_HD, key_row0 + qt * AT_M);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        const int t0 = 2 * item;
+        const bool two = t0 + 1 < p.tiles;
+        int h[2], qr[2], kr[2];
+        tile_coords(p, t0, h[0], qr[0], kr[0]);
+        tile_coords(p, two ? t0 + 1 : t0, h[1], qr[1], kr[1]);
+        const int nload = (shared_kv || !two) ? 1 : 2;
+        const uint32_t kv_bytes = static_cast<uint32_t>(nload * keys * AT_HD * 2);
+        mbar_wait(k_empty, ph ^ 1u);
+        mbar_expect_tx(k_full, kv_bytes);
+        for (int s = 0; s < nload; ++s) tma_load_2d(sK + s * kv_slot_bytes, &tmKV, k_full, p.C + h[s] * AT_HD, kr[s]);
+        for (int s = 0; s < (two ? 2 : 1); ++s) {
+          mbar_wait(&q_empty[s], ph ^ 1u);
+          mbar_expect_tx(&q_full[s], AT_Q_BYTES);
+          tma_load_2d(sQ + s * AT_Q_BYTES, &tmQ, &q_full[s], h[s] * AT_HD, qr[s]);
         }
+        mbar_wait(v_empty, ph ^ 1u);
+        mbar_expect_tx(v_full, kv_bytes);
+        for (int s = 0; s < nload; ++s) tma_load_2d(sV + s * kv_slot_bytes, &tmKV, v_full, 2 * p.C + h[s] * AT_HD, kr[s]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_M, keys);
       const uint32_t idesc_o = umma_idesc_bf16(AT_M, AT_HD, /*b_mn_major=*/1);
-      const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ));
-      const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK));
-      uint32_t it = 0, qi = 0;
-      for (int g = blockIdx.x; g < p.groups; g += gridDim.x, ++it) {
-        mbar_wait(kv_full, it & 1u);
-        for (int qt = 0; qt < p.qtiles; ++qt, ++qi) {
-          mbar_wait(q_full, qi & 1u);
-          mbar_wait(s_empty, (qi & 1u) ^ 1u);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        const int ns = (2 * item + 1 < p.tiles) ? 2 : 1;
+        mbar_wait(k_full, ph);
+        for (int s = 0; s < ns; ++s) {
+          mbar_wait(&q_full[s], ph);
+          mbar_wait(&s_empty[s], ph ^ 1u);
           tc_fence_after();
+          const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + s * AT_Q_BYTES));
+          const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + s * kv_slot_bytes));
 #pragma unroll
-          for (int k = 0; k < AT_HD / 16; ++k) umma_bf16(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(q_empty);
-          umma_commit(s_full);
-          mbar_wait(p_full, qi & 1u);
-          tc_fence_after();
-          for (int j = 0; j < keys / 16; ++j) {
-            const uint64_t pdesc = umma_desc_k_sw128(smem_u32(sP) + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
-            const uint64_t vdesc = umma_desc_mn_sw128(smem_u32(sV) + j * 16 * 128);
-            umma_bf16(tmem_base + AT_O_COL, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
-          }
-          umma_commit(o_full);
-          if (qt == p.qtiles - 1) umma_commit(kv_empty);
+          for (int k = 0; k < AT_HD / 16; ++k)
+            umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&q_empty[s]);
+          umma_commit(&s_full[s]);
         }
+        umma_commit(k_empty);
+        mbar_wait(v_full, ph);
+        for (int s = 0; s < ns; ++s) {
+          mbar_wait(&p_full[s], ph);
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(sP + s * AT_P_BYTES);
+          const uint32_t vbase = smem_u32(sV + s * kv_slot_bytes);
+          for (int j = 0; j < keys / 16; ++j) {
+            const uint64_t pdesc = umma_desc_k_sw128(pbase + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
+            const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
+            umma_bf16(tmem_base + s * 256, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[s]);
+        }
+        umma_commit(v_empty);
       }
     }
   } else {
-    // ===================== softmax + output (thread = query row) =====================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint32_t qi = 0;
-    for (int g = blockIdx.x; g < p.groups; g += gridDim.x) {
-      const int h = g % p.heads;
-      const int blk = g / p.heads;
-      const int key_row0 = small ? blk * AT_M : blk * p.L;
-      // valid key columns of this row: the block-diagonal segment when several images share the tile
-      const int c_lo = small ? (row / p.L) * p.L : 0;
-      const int c_hi = small ? c_lo + p.L : keys;
-      // warp-uniform hull of the valid columns (tcgen05.ld is warp-collective: the skip test below must not diverge)
-      const int w_lo = small ? ((warp * 32) / p.L) * p.L : 0;
-      const int w_hi = small ? ((warp * 32 + 31) / p.L + 1) * p.L : keys;
-      for (int qt = 0; qt < p.qtiles; ++qt, ++qi) {
-        mbar_wait(s_full, qi & 1u);
-        tc_fence_after();
-        // pass 1: row max
-        float m = -INFINITY;
-        for (int c0 = 0; c0 < keys; c0 += 32) {
-          if (c0 + 32 <= w_lo || c0 >= w_hi) continue;
-          uint32_t r[32];
-          tmem_ld_32x32(lane_addr + c0, r);
-          tmem_ld_wait();
+    // ===================== softmax + output: warpgroup = slot, thread = query row =====================
+    const int slot = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256;
+    uint8_t* sPs = sP + slot * AT_P_BYTES;
+    // valid key columns of this row when several images share the tile (block diagonal), and their warp-uniform hull
+    // (tcgen05.ld is warp-collective: whole 32-column chunks may only be skipped by all lanes together)
+    const int c_lo = SMALL ? (row / p.L) * p.L : 0;
+    const int c_hi = SMALL ? c_lo + p.L : keys;
+    const int w_lo = SMALL ? ((q * 32) / p.L) * p.L : 0;
+    const int w_hi = SMALL ? ((q * 32 + 31) / p.L + 1) * p.L : keys;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int t = 2 * item + slot;
+      if (t >= p.tiles) continue;  // odd tail: slot 1 has no tile in the last item (warpgroup-uniform)
+      int h, q_row0, key_row0;
+      tile_coords(p, t, h, q_row0, key_row0);
+      mbar_wait(&s_full[slot], ph);
+      tc_fence_after();
+      // pass 1: row max
+      float m = -INFINITY;
+      for (int c0 = w_lo & ~31; c0 < w_hi; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + c0, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 32; ++j) {
+          if (SMALL) {
             const int c = c0 + j;
             if (c >= c_lo && c < c_hi) m = fmaxf(m, __uint_as_float(r[j]));
+          } else {
+            m = fmaxf(m, __uint_as_float(r[j]));
           }
         }
-        const float ms = m * p.scale_log2e;
-        // pass 2: p = exp2(s * scale - max * scale), row sum, bf16 P into the swizzled operand layout
-        float sum = 0.f;
-        for (int c0 = 0; c0 < keys; c0 += 32) {
+      }
+      const float ms = m * p.scale_log2e;
+      // pass 2: p = 2^(s * scale - max * scale), row sum, bf16 P into the K-major SWIZZLE_128B operand layout
+      float sum = 0.f;
+      for (int c0 = 0; c0 < keys; c0 += 32) {
+        uint32_t pk[16];
+        if (SMALL && (c0 + 32 <= w_lo || c0 >= w_hi)) {  // chunk outside every row's block: probabilities are zero
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        } else {
           uint32_t r[32];
           tmem_ld_32x32(lane_addr + c0, r);
           tmem_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const int c = c0 + j;
-            float e0 = (c >= c_lo && c < c_hi) ? exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms)) : 0.f;
-            float e1 = (c + 1 >= c_lo && c + 1 < c_hi) ? exp2f(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms)) : 0.f;
-            // the row sum uses the bf16-rounded probabilities the tensor core will actually multiply
-            __nv_bfloat162 b = __floats2bfloat162_rn(e0, e1);
-            float2 f = __bfloat1622float2(b);
-            sum += f.x + f.y;
-            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b);
+            float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms));
+            float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms));
+            if (SMALL) {
+              const int c = c0 + j;
+              e0 = (c >= c_lo && c < c_hi) ? e0 : 0.f;
+              e1 = (c + 1 >= c_lo && c + 1 < c_hi) ? e1 : 0.f;
+            }
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
           }
-          uint8_t* sub = sP + (c0 >> 6) * (AT_M * 128) + row * 128;
-          const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk of these 32 keys inside the 128-byte row
+        }
+        uint8_t* sub = sPs + (c0 >> 6) * (AT_M * 128) + row * 128;
+        const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk of these 32 keys inside the 128-byte row
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (chunk0 + q4) ^ (row & 7);
+          *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[slot]);
+      // O = P V done -> normalise, store
+      mbar_wait(&o_full[slot], ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const int grow = q_row0 + row;
+      __nv_bfloat16* op = p.out + static_cast<size_t>(grow) * p.C + h * AT_HD;
+#pragma unroll
+      for (int c0 = 0; c0 < AT_HD; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + c0, r);
+        tmem_ld_wait();
+        if (grow < p.total_rows) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const int chunk = (chunk0 + q4) ^ (row & 7);
-            *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * q4]) * inv, __uint_as_float(r[8 * q4 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv, __uint_as_float(r[8 * q4 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv, __uint_as_float(r[8 * q4 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv, __uint_as_float(r[8 * q4 + 7]) * inv);
+            reinterpret_cast<uint4*>(op + c0)[q4] = u;
           }
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(p_full);
-        // O = P V done -> normalise, store
-        mbar_wait(o_full, qi & 1u);
-        tc_fence_after();
-        const float inv = 1.0f / sum;
-        const int grow = key_row0 + qt * AT_M + row;
-        __nv_bfloat16* op = p.out + static_cast<size_t>(grow) * p.C + h * AT_HD;
-#pragma unroll
-        for (int c0 = 0; c0 < AT_HD; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(lane_addr + AT_O_COL + c0, r);
-          tmem_ld_wait();
-          if (grow < p.total_rows) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(r[8 * q4]) * inv, __uint_as_float(r[8 * q4 + 1]) * inv);
-              u.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv, __uint_as_float(r[8 * q4 + 3]) * inv);
-              u.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv, __uint_as_float(r[8 * q4 + 5]) * inv);
-              u.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv, __uint_as_float(r[8 * q4 + 7]) * inv);
-              reinterpret_cast<uint4*>(op + c0)[q4] = u;
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(s_empty);
       }
+      tc_fence_before();
+      mbar_arrive(&s_empty[slot]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -283,9 +345,9 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
   AttnParams& p = P->p;
   p.L = d.L; p.heads = d.heads; p.C = d.C;
   p.keys = d.L < AT_M ? AT_M : d.L;
-  p.qtiles = d.L < AT_M ? 1 : d.L / AT_M;
   p.total_rows = d.B * d.L;
-  p.groups = (d.L < AT_M ? (p.total_rows + AT_M - 1) / AT_M : d.B) * d.heads;
+  p.tiles = ((p.total_rows + AT_M - 1) / AT_M) * d.heads;
+  p.items = (p.tiles + 1) / 2;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(AT_HD));
   p.out = reinterpret_cast<__nv_bfloat16*>(d.out);
   const uint64_t cols = 3ull * d.C, rows = static_cast<uint64_t>(p.total_rows);
@@ -293,7 +355,7 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
     delete P;
     return -1;
   }
-  P->grid = std::min(p.groups, num_sms());
+  P->grid = std::min(p.items, num_sms());
   *out = P;
   return 0;
 }
@@ -303,11 +365,14 @@ void attention_release(AttnPrepared* p) { delete p; }
 int launch_attention_umma(const AttnPrepared* P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(AT_SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
     attr_set = true;
   }
-  attention_umma_kernel<<<P->grid, 192, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
+  if (P->p.L < AT_M) attention_umma_kernel<true><<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
+  else attention_umma_kernel<false><<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -37,7 +37,9 @@ int num_sms();
 // ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with two SFU ops (ex2.approx, rcp.approx; relative error ~1e-6, far below the bf16 rounding of the
+// result).  A full-precision division here halves the bandwidth of the GroupNorm-apply pass.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
