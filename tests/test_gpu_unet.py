@@ -35,6 +35,10 @@ def test_unet_eps_vs_reference_golden(golden, name):
     assert eps.shape == x.shape and eps.dtype == torch.float32 and torch.isfinite(eps).all()
     err = rel_l2(eps, torch.from_numpy(golden["unet"][name]))
     print(f"{name}: eps rel-L2 vs reference = {err:.3e}")
+    import os
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/eps_errors.txt", "a") as fh:
+            fh.write(f"{name} {err:.4e}\n")
     assert err < TOL_EPS_BF16
 
 
