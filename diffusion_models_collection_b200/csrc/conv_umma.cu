@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 #include <new>
 
 namespace dmc {
@@ -56,17 +58,17 @@ struct ConvPrepared {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
   ConvKParams kp;
-  int BN, MT;
+  int BN, MT, CG;
   int grid;
   size_t smem;
 };
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 struct ConvCfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
-  static constexpr int B_STAGE_BYTES = BN * KB * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * KB * 2;  // a CTA pair splits the weight tile: N/2 rows each
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
-  static constexpr int NST = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int NST = (216 * 1024) / STAGE_BYTES > 8 ? 8 : (216 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = MT * BN;  // TMEM columns of one accumulator stage
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr size_t SMEM = static_cast<size_t>(NST) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -131,13 +133,16 @@ __device__ __forceinline__ void reduce8(const float (&v)[8], bool full, int lane
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN, MT>;
+  using Cfg = ConvCfg<BN, MT, CG>;
   constexpr int NST = Cfg::NST;
+  constexpr int MTG = MT * CG;  // 128-pixel tiles per CTA-group tile
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
@@ -148,7 +153,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_ct = (p.num_m_tiles + MT - 1) / MT;  // CTA tiles along M (MT consecutive 128-pixel tiles each)
+  const int num_ct = (p.num_m_tiles + MTG - 1) / MTG;  // group tiles along M (MTG consecutive 128-pixel tiles each)
   const int num_tiles = num_ct * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -164,16 +169,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_THREADS);
+      mbar_init(&tempty_bar[i], CG * (EPI_THREADS / 32));  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -181,13 +192,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int n_tile = tile % p.num_n_tiles;
         const int ct = tile / p.num_n_tiles;
         int w0[MT], h0[MT], n0[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const int m_tile = ct * MT + mt;  // may be one past the end: its box is fully out of bounds -> zero fill
+          const int m_tile = ct * MTG + rank * MT + mt;  // may be past the end: its box is fully out of bounds -> zero fill
           w0[mt] = (m_tile % p.tiles_w) * p.BW * p.stride;
           h0[mt] = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH * p.stride;
           n0[mt] = (m_tile / (p.tiles_w * p.tiles_h)) * p.BNIMG;
@@ -197,17 +208,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int stage = it % NST;
           const uint32_t phase = (it / NST) & 1u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          // the leader's barrier counts the bytes of BOTH CTAs of a pair (the MMAs it issues read both)
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int chunks = p.seg_chunks[seg];
           const int tap = kb_in_seg / chunks, chunk = kb_in_seg % chunks;
           const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+          if (CG == 2) {
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &full_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
-                        h0[mt] + p.dh[seg][tap], n0[mt]);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_4d_cg2(sa + mt * A_STAGE_BYTES, tm, lbar, chunk * KB, w0[mt] + p.dw[seg][tap],
+                              h0[mt] + p.dh[seg][tap], n0[mt]);
+            tma_load_2d_cg2(sb, &tmB, lbar, kb * KB, n_tile * BN + rank * (BN / 2));
+          } else {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &full_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
+                          h0[mt] + p.dh[seg][tap], n0[mt]);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+          }
           if (++kb_in_seg == p.seg_taps[seg] * chunks) {
             ++seg;
             kb_in_seg = 0;
@@ -217,10 +238,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M * CG, BN);
       uint32_t it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
         const uint32_t acc = local & 1u;
         const uint32_t acc_phase = (local >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -239,12 +260,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int k = 0; k < KB / 16; ++k) {
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (CG == 2) umma_bf16_cg2(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) umma_commit_cg2(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&tfull_bar[acc]);  // accumulators complete -> epilogue
+        // accumulators complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_cg2(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -260,11 +286,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool idle = (MT == 1 && BN < 64 && grp == 1);
     const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / ppi;
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
       const uint32_t acc = local & 1u;
       const uint32_t acc_phase = (local >> 1) & 1u;
       const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = (tile / p.num_n_tiles) * MT + (MT == 2 ? grp : 0);
+      const int m_tile = (tile / p.num_n_tiles) * MTG + rank * MT + (MT == 2 ? grp : 0);
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int ti = m_tile / (p.tiles_w * p.tiles_h);
@@ -391,15 +417,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {  // one arrival per warp, on the leader's barrier (its MMA warp reuses the accumulator stage)
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal / read it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -420,18 +452,25 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // Tile configuration (BN output channels x MT 128-pixel sub-tiles per CTA tile).  Bytes staged per MAC fall with
 // MT * BN (the A tile is reused by BN channels, the B tile by MT * 128 pixels): prefer 256 TMEM columns per
 // accumulator when that still yields at least one tile per SM.
-struct TileCfg { int bn, mt; };
+struct TileCfg { int bn, mt, cg; };
 static TileCfg pick_cfg(int cout_pad, int m_tiles) {
   const int sms = num_sms();
-  const TileCfg cands[5] = {{256, 1}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
+  // DMC_CONV_CG (debug / tests): "1" never pairs SMs, "2" pairs them whenever the channel count allows
+  const char* e = getenv("DMC_CONV_CG");
+  const bool allow_pairs = !(e && e[0] == '1');
+  const bool force_pairs = e && e[0] == '2';
+  const TileCfg cands[7] = {{256, 1, 2}, {128, 2, 2}, {256, 1, 1}, {128, 2, 1}, {128, 1, 1}, {64, 1, 1}, {32, 1, 1}};
+  if (force_pairs)
+    for (int i = 0; i < 2; ++i)
+      if (cout_pad % cands[i].bn == 0) return cands[i];
   for (const TileCfg& c : cands) {
-    if (cout_pad % c.bn != 0) continue;
-    const long long tiles = static_cast<long long>((m_tiles + c.mt - 1) / c.mt) * (cout_pad / c.bn);
-    if (tiles >= sms) return c;
+    if (cout_pad % c.bn != 0 || (c.cg == 2 && !allow_pairs)) continue;
+    const long long ctas = static_cast<long long>((m_tiles + c.mt * c.cg - 1) / (c.mt * c.cg)) * (cout_pad / c.bn) * c.cg;
+    if (ctas >= sms) return c;
   }
-  for (int i = 4; i >= 0; --i)
+  for (int i = 6; i >= 2; --i)
     if (cout_pad % cands[i].bn == 0) return cands[i];
-  return {32, 1};
+  return {32, 1, 1};
 }
 
 int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
@@ -508,11 +547,12 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   const int BN = tc.bn;
   P->BN = BN;
   P->MT = tc.mt;
+  P->CG = tc.cg;
   kp.num_n_tiles = d.Cout_pad / BN;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Ktot), static_cast<cuuint64_t>(d.Cout_pad)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.Ktot) * 2};
-    cuuint32_t box[2] = {KB, static_cast<cuuint32_t>(BN)};
+    cuuint32_t box[2] = {KB, static_cast<cuuint32_t>(BN / tc.cg)};
     cuuint32_t estr[2] = {1, 1};
     if (encode_map(&P->tmB, d.weight, 2, dims, strides, box, estr) != 0) { delete P; return -1; }
   }
@@ -534,7 +574,11 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     kp.stats_slots = want;
     kp.stats_slot_base = d.up_phase >= 0 ? d.up_phase * base : 0;
   }
-  P->grid = std::min(((kp.num_m_tiles + tc.mt - 1) / tc.mt) * kp.num_n_tiles, num_sms());
+  {
+    const int mtg = tc.mt * tc.cg;
+    const int group_tiles = ((kp.num_m_tiles + mtg - 1) / mtg) * kp.num_n_tiles;
+    P->grid = tc.cg * std::min(group_tiles, num_sms() / tc.cg);
+  }
   P->smem = 0;
   *out = P;
   return 0;
@@ -542,28 +586,41 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
 
 void conv_release(ConvPrepared* p) { delete p; }
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 static int launch_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(ConvCfg<BN, MT>::SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(ConvCfg<BN, MT, CG>::SMEM)));
     attr_set = true;
   }
-  conv_umma_kernel<BN, MT><<<P->grid, CONV_THREADS, ConvCfg<BN, MT>::SMEM, st>>>(P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp);
-  DMC_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(P->grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = ConvCfg<BN, MT, CG>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DMC_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MT, CG>, P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp));
   return 0;
 }
 
 int launch_conv(const dmc_conv_desc& d, const ConvPrepared* P, cudaStream_t st) {
   ConvKParams kp = P->kp;
   kp.out_nchw = d.out_f32_nchw;  // the only re-bindable pointer (dmc_plan_rebind which=2)
-  if (P->MT == 2) return launch_cfg<128, 2>(P, kp, st);
+  if (P->CG == 2) return P->BN == 256 ? launch_cfg<256, 1, 2>(P, kp, st) : launch_cfg<128, 2, 2>(P, kp, st);
+  if (P->MT == 2) return launch_cfg<128, 2, 1>(P, kp, st);
   switch (P->BN) {
-    case 256: return launch_cfg<256, 1>(P, kp, st);
-    case 128: return launch_cfg<128, 1>(P, kp, st);
-    case 64: return launch_cfg<64, 1>(P, kp, st);
-    default: return launch_cfg<32, 1>(P, kp, st);
+    case 256: return launch_cfg<256, 1, 1>(P, kp, st);
+    case 128: return launch_cfg<128, 1, 1>(P, kp, st);
+    case 64: return launch_cfg<64, 1, 1>(P, kp, st);
+    default: return launch_cfg<32, 1, 1>(P, kp, st);
   }
 }
 

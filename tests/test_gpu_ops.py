@@ -42,8 +42,11 @@ CONV3 = [
 ]
 
 
+@pytest.mark.parametrize("pairs", ["1", "2"])
 @pytest.mark.parametrize("cins,cout,H,stride,B", CONV3)
-def test_conv3x3_classes(cins, cout, H, stride, B):
+def test_conv3x3_classes(cins, cout, H, stride, B, pairs, monkeypatch):
+    """pairs = "2": force the cta_group::2 kernel (two SMs per 256-pixel tile) wherever Cout allows it; "1": never"""
+    monkeypatch.setenv("DMC_CONV_CG", pairs)
     cin = sum(cins)
     x = _q(_rand((B, cin, H, H), 1))
     w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
@@ -77,7 +80,8 @@ def test_conv3x3_classes(cins, cout, H, stride, B):
 
 @pytest.mark.parametrize("cin,cout,H,B", [(256, 768, 16, 2), (256, 768, 8, 3), (256, 768, 4, 5), (256, 256, 16, 1),
                                           (256, 256, 4, 9), (128, 256, 16, 2), (64, 192, 16, 3)])
-def test_conv1x1_with_residual(cin, cout, H, B):
+def test_conv1x1_with_residual(cin, cout, H, B, monkeypatch):
+    monkeypatch.setenv("DMC_CONV_CG", "2" if B % 2 else "1")
     x = _q(_rand((B, cin, H, H), 5))
     w = _q(_rand((cout, cin, 1, 1), 6, cin ** -0.5))
     bias = _rand((cout,), 7, 0.1)
@@ -89,7 +93,8 @@ def test_conv1x1_with_residual(cin, cout, H, B):
 
 @pytest.mark.parametrize("cins,cout,H,B", [([128], 256, 16, 2), ([256, 256], 256, 4, 3), ([256, 128], 128, 32, 1),
                                            ([256, 128], 256, 16, 2)])
-def test_conv2_with_fused_shortcut(cins, cout, H, B):
+def test_conv2_with_fused_shortcut(cins, cout, H, B, monkeypatch):
+    monkeypatch.setenv("DMC_CONV_CG", "2")
     """conv2(3x3 over a2) + shortcut(1x1 over the raw concat inputs) as one GEMM with extra K columns"""
     a2 = _q(_rand((B, cout, H, H), 9))
     xs = [_q(_rand((B, c, H, H), 10 + i)) for i, c in enumerate(cins)]
