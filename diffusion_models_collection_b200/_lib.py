@@ -76,7 +76,7 @@ class UpsampleDesc(C.Structure):
 
 class StepDesc(C.Structure):
     _fields_ = [("x", vp), ("eps_c", vp), ("eps_u", vp), ("noise", vp), ("x_out", vp), ("B", C.c_int32),
-                ("n_per_sample", C.c_int32), ("coef_dev", vp), ("g", Guidance)]
+                ("n_per_sample", C.c_int32), ("coef_dev", vp), ("g", Guidance), ("step_index_dev", vp)]
 
 
 # every symbol include/dmc.h declares: (restype, argtypes)
@@ -86,10 +86,14 @@ SYMBOLS = {
     "dmc_init": (C.c_int, []),
     "dmc_ddim_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(Guidance), vp]),
     "dmc_ddpm_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(Guidance), vp]),
+    "dmc_ddim_step_at": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(Guidance), vp]),
+    "dmc_ddpm_step_at": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(Guidance), vp]),
+    "dmc_advance": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "dmc_q_sample": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]),
     "dmc_plan_create": (C.c_int, [C.POINTER(vp)]),
     "dmc_plan_destroy": (C.c_int, [vp]),
     "dmc_plan_run": (C.c_int, [vp, vp]),
+    "dmc_plan_run_op": (C.c_int, [vp, C.c_int32, vp]),
     "dmc_plan_num_launches": (C.c_int, [vp]),
     "dmc_plan_gemm_flops": (C.c_double, [vp]),
     "dmc_plan_rebind": (C.c_int, [vp, C.c_int32, C.c_int32, vp]),

@@ -12,6 +12,7 @@ namespace dmc {
 
 // sched.cu
 int launch_step(bool ddpm, const dmc_step_desc& d, cudaStream_t st);
+int launch_advance(int* counter, const int64_t* t_table, int64_t* t_out, int n, cudaStream_t st);
 int launch_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sa, const float* s1, float* out,
                     int B, int n, cudaStream_t st);
 

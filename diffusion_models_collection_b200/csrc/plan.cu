@@ -105,14 +105,34 @@ int dmc_init(void) {
 int dmc_ddim_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
                   int32_t n_per_sample, const dmc_ddim_coef* coef_dev, const dmc_guidance* g, void* stream) {
   DMC_REQUIRE(g != nullptr, "dmc_ddim_step: guidance is null");
-  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g};
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g, nullptr};
   return launch_step(false, d, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_ddim_step_at(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
+                     int32_t n_per_sample, const dmc_ddim_coef* coef_table_dev, const int32_t* step_index_dev,
+                     const dmc_guidance* g, void* stream) {
+  DMC_REQUIRE(g != nullptr && step_index_dev != nullptr, "dmc_ddim_step_at: null guidance / step index");
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_table_dev, *g, step_index_dev};
+  return launch_step(false, d, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_ddpm_step_at(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
+                     int32_t n_per_sample, const dmc_ddpm_coef* coef_table_dev, const int32_t* step_index_dev,
+                     const dmc_guidance* g, void* stream) {
+  DMC_REQUIRE(g != nullptr && step_index_dev != nullptr, "dmc_ddpm_step_at: null guidance / step index");
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_table_dev, *g, step_index_dev};
+  return launch_step(true, d, static_cast<cudaStream_t>(stream));
+}
+
+int dmc_advance(int32_t* counter_dev, const int64_t* t_table_dev, int64_t* t_out_dev, int32_t n, void* stream) {
+  return launch_advance(counter_dev, t_table_dev, t_out_dev, n, static_cast<cudaStream_t>(stream));
 }
 
 int dmc_ddpm_step(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out, int32_t B,
                   int32_t n_per_sample, const dmc_ddpm_coef* coef_dev, const dmc_guidance* g, void* stream) {
   DMC_REQUIRE(g != nullptr, "dmc_ddpm_step: guidance is null");
-  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g};
+  dmc_step_desc d{x, eps_c, eps_u, noise, x_out, B, n_per_sample, coef_dev, *g, nullptr};
   return launch_step(true, d, static_cast<cudaStream_t>(stream));
 }
 
@@ -146,6 +166,11 @@ int dmc_plan_run(dmc_plan* p, void* stream) {
     if (r != 0) return r;
   }
   return 0;
+}
+
+int dmc_plan_run_op(dmc_plan* p, int32_t op_index, void* stream) {
+  DMC_REQUIRE(p && op_index >= 0 && op_index < static_cast<int>(p->ops.size()), "dmc_plan_run_op: bad op index");
+  return run_op(p->ops[op_index], static_cast<cudaStream_t>(stream));
 }
 
 int dmc_plan_num_ops(const dmc_plan* p) { return p ? static_cast<int>(p->ops.size()) : -1; }

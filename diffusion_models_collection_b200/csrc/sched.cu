@@ -18,7 +18,8 @@ struct StepArgs {
   float* out;
   int B;
   int n;  // elements per sample
-  const float* coef;  // device: 5 floats (dmc_ddim_coef / dmc_ddpm_coef)
+  const float* coef;  // device: 5 floats (dmc_ddim_coef / dmc_ddpm_coef) per row
+  const int* step_index;  // optional device scalar: row to use
   float cfg_scale;
   int clip_mode;
   int q_lo, q_hi;
@@ -59,8 +60,9 @@ __device__ __forceinline__ float finish(float x, float eps, float x0, float nz, 
 template <bool DDPM>
 __global__ void __launch_bounds__(256) step_elementwise_kernel(StepArgs a) {
   float c[5];
+  const float* crow = a.coef + (a.step_index ? 5 * static_cast<size_t>(__ldg(a.step_index)) : 0);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) c[i] = __ldg(a.coef + i);
+  for (int i = 0; i < 5; ++i) c[i] = __ldg(crow + i);
   const bool has_u = a.eps_u != nullptr;
   const bool has_noise = DDPM ? true : (a.noise != nullptr && c[4] != 0.0f);
   const size_t total4 = (static_cast<size_t>(a.B) * a.n) >> 2;
@@ -91,8 +93,9 @@ __global__ void __launch_bounds__(256) step_elementwise_kernel(StepArgs a) {
 template <bool DDPM>
 __global__ void __launch_bounds__(256) step_scalar_kernel(StepArgs a) {
   float c[5];
+  const float* crow = a.coef + (a.step_index ? 5 * static_cast<size_t>(__ldg(a.step_index)) : 0);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) c[i] = __ldg(a.coef + i);
+  for (int i = 0; i < 5; ++i) c[i] = __ldg(crow + i);
   const bool has_u = a.eps_u != nullptr;
   const bool has_noise = DDPM ? true : (a.noise != nullptr && c[4] != 0.0f);
   const size_t total = static_cast<size_t>(a.B) * a.n;
@@ -121,8 +124,9 @@ __global__ void __launch_bounds__(THR_THREADS) step_threshold_kernel(StepArgs a)
   __shared__ unsigned int red_min[THR_THREADS / 32];
 
   float c[5];
+  const float* crow = a.coef + (a.step_index ? 5 * static_cast<size_t>(__ldg(a.step_index)) : 0);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) c[i] = __ldg(a.coef + i);
+  for (int i = 0; i < 5; ++i) c[i] = __ldg(crow + i);
   const bool has_u = a.eps_u != nullptr;
   const bool has_noise = DDPM ? true : (a.noise != nullptr && c[4] != 0.0f);
   const int n = a.n;
@@ -235,9 +239,28 @@ int launch_step(bool ddpm, const dmc_step_desc& d, cudaStream_t st) {
   StepArgs a;
   a.x = d.x; a.eps_c = d.eps_c; a.eps_u = d.eps_u; a.noise = d.noise; a.out = d.x_out;
   a.B = d.B; a.n = d.n_per_sample; a.coef = reinterpret_cast<const float*>(d.coef_dev);
+  a.step_index = d.step_index_dev;
   a.cfg_scale = d.g.cfg_scale; a.clip_mode = d.g.clip_mode; a.q_lo = d.g.q_lo; a.q_hi = d.g.q_hi; a.q_w = d.g.q_weight;
   DMC_REQUIRE(a.clip_mode >= 0 && a.clip_mode <= 2, "sched step: clip_mode %d", a.clip_mode);
   return ddpm ? launch_step_t<true>(a, st) : launch_step_t<false>(a, st);
+}
+
+__global__ void advance_kernel(int* counter, const int64_t* __restrict__ t_table, int64_t* __restrict__ t_out, int n) {
+  const int cur = counter[0];
+  const int64_t t = t_table[cur];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t_out[i] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counter[1] = cur;
+    counter[0] = cur + 1;
+  }
+}
+
+int launch_advance(int* counter, const int64_t* t_table, int64_t* t_out, int n, cudaStream_t st) {
+  DMC_REQUIRE(counter && t_table && t_out && n > 0, "advance: bad arguments");
+  advance_kernel<<<1, 256, 0, st>>>(counter, t_table, t_out, n);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,

@@ -7,6 +7,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -52,6 +53,9 @@ class DiffusionBase:
     diffusion/ddim.py:27-152)."""
 
     progress = True  # show the reference's tqdm bars
+    # Replay ONE captured CUDA graph ("advance counter -> denoiser forward -> fused scheduler step") per sampling step
+    # when the denoiser is one of the native models; DMC_CUDA_GRAPH=0 keeps the launch-by-launch loop.
+    use_cuda_graph = os.environ.get("DMC_CUDA_GRAPH", "1") != "0"
 
     def _init_common(self, num_timesteps, beta_start, beta_end, beta_schedule, device):
         self.num_timesteps = num_timesteps
@@ -104,6 +108,68 @@ class DiffusionBase:
         from tqdm import tqdm
 
         return tqdm(it, desc=desc, total=total)
+
+    # ---- whole-loop CUDA graph ------------------------------------------------------------------
+    def _graph_ok(self, model, return_all_timesteps, step_noise):
+        return (self.use_cuda_graph and not return_all_timesteps and step_noise is None
+                and getattr(model, "graph_capturable", False))
+
+    def _graph_loop(self, model, img, y, ddpm, t_seq, coef_seq, g, cfg, draw_noise, desc):
+        """Runs `len(t_seq)` sampling steps by replaying one captured graph.  Step k reads its timestep t_seq[k] and its
+        coefficient row coef_seq[k] on the DEVICE (dmc_advance / dmc_*_step_at), so nothing in the loop touches the
+        host; x_t is updated in place.  Per-step noise (DDPM, DDIM eta > 0) is torch.randn_like inside the graph: the
+        same Philox stream, in the same order, as the launch-by-launch loop and the reference (ddpm.py:216)."""
+        lib = _lib.load()
+        B = img.shape[0]
+        n = img.numel() // B
+        S = int(t_seq.numel())
+        packed = getattr(model, "_packed", None)
+        key = (id(model), bool(ddpm), bool(cfg), tuple(img.shape), y is not None, float(g.cfg_scale), int(g.clip_mode),
+               int(g.q_lo), int(g.q_hi), float(g.q_weight), bool(draw_noise), S, id(coef_seq), id(t_seq), str(img.device))
+        ent = getattr(self, "_graph_cache", None)
+        if ent is not None and (ent["key"] != key or ent["packed"] is not getattr(model, "_packed", None)):
+            ent = self._graph_cache = None
+        if ent is None:
+            dev = img.device
+            x = torch.empty_like(img)
+            t_batch = torch.zeros((B,), device=dev, dtype=torch.long)
+            counter = torch.zeros((2,), device=dev, dtype=torch.int32)
+            ybuf = torch.zeros((B,), device=dev, dtype=torch.long) if y is not None else None
+            yzero = torch.zeros_like(ybuf) if cfg else None
+            step_at = lib.dmc_ddpm_step_at if ddpm else lib.dmc_ddim_step_at
+
+            def model_call():
+                if cfg:
+                    return self._eps_pair(model, x, t_batch, ybuf, yzero)
+                return model(x, t_batch, ybuf), None
+
+            def one_step():
+                _lib.check(lib.dmc_advance(counter.data_ptr(), t_seq.data_ptr(), t_batch.data_ptr(), B,
+                                           _lib.stream_ptr()), "dmc_advance")
+                eps_c, eps_u = model_call()
+                z = torch.randn_like(x) if draw_noise else None
+                _lib.check(step_at(x.data_ptr(), eps_c.data_ptr(), _lib.ptr(eps_u), _lib.ptr(z), x.data_ptr(), B, n,
+                                   coef_seq.data_ptr(), counter.data_ptr() + 4, g, _lib.stream_ptr()), "dmc_step_at")
+
+            x.zero_()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                model_call()  # builds the plans / sets kernel attributes outside the capture; draws no random numbers
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one_step()
+            packed = getattr(model, "_packed", None)
+            ent = self._graph_cache = dict(key=key, packed=packed, graph=graph, x=x, t_batch=t_batch, counter=counter,
+                                           ybuf=ybuf, yzero=yzero, t_seq=t_seq, coef_seq=coef_seq, g=g)
+        ent["x"].copy_(img)
+        if y is not None:
+            ent["ybuf"].copy_(y)
+        ent["counter"].zero_()
+        for _ in self._bar(range(S), desc, S):
+            ent["graph"].replay()
+        return ent["x"].clone()
 
     @staticmethod
     def _uniform_t(model):

@@ -51,6 +51,15 @@ class DDIM(DiffusionBase):
             self._coef_cache = self._coef_rows(ts, nxt)
         return self._coef_cache
 
+    def _seq_tables(self, device):
+        """(timesteps int64 [S], coefficient rows fp32 [S, 5]) on `device`, one row per sampling step"""
+        c = getattr(self, "_seq_cache", None)
+        coefs = self._coef_table()
+        if c is None or c[0] is not coefs or c[1] != str(device):
+            c = self._seq_cache = (coefs, str(device), self.inference_timesteps.to(device).contiguous(),
+                                   coefs.to(device).contiguous())
+        return c[2], c[3]
+
     def _step(self, lib, x, eps_c, eps_u, noise, out, coef_row_ptr, g):
         B = x.shape[0]
         _lib.check(lib.dmc_ddim_step(x.data_ptr(), eps_c.data_ptr(), _lib.ptr(eps_u), _lib.ptr(noise), out.data_ptr(), B,
@@ -100,6 +109,11 @@ class DDIM(DiffusionBase):
         t_batch = torch.empty((B,), device=img.device, dtype=torch.long)
         nxt = torch.empty_like(img)
         g = guidance(0.0, 1)
+        if self._graph_ok(model, return_all_timesteps, step_noise):
+            t_seq, coef_seq = self._seq_tables(img.device)
+            with self._uniform_t(model):
+                return self._graph_loop(model, img, None if y is None else y.to(img.device), False, t_seq, coef_seq, g,
+                                        cfg=False, draw_noise=self.eta > 0, desc="DDIM Sampling")
         imgs = []
         with self._uniform_t(model):
             for i, t in enumerate(self._bar(timesteps, "DDIM Sampling")):
@@ -137,6 +151,11 @@ class DDIM(DiffusionBase):
         t_batch = torch.empty((B,), device=img.device, dtype=torch.long)
         nxt = torch.empty_like(img)
         g = guidance(cfg_scale, 2, n, p_threshold) if p_threshold is not None else guidance(cfg_scale, 1)
+        if self._graph_ok(model, return_all_timesteps, step_noise) and hasattr(model, "forward_cfg"):
+            t_seq, coef_seq = self._seq_tables(img.device)
+            with self._uniform_t(model):
+                return self._graph_loop(model, img, y, False, t_seq, coef_seq, g, cfg=True, draw_noise=self.eta > 0,
+                                        desc=f"DDIM sampling with CFG scale {cfg_scale}")
         imgs = []
         with self._uniform_t(model):
             for i, t in enumerate(self._bar(timesteps, f"DDIM sampling with CFG scale {cfg_scale}")):

@@ -42,6 +42,15 @@ class DDPM(DiffusionBase):
             ], dim=1).contiguous()
         return self._coef_cache
 
+    def _seq_tables(self, device):
+        """(timesteps int64 [T] = T-1..0, coefficient rows fp32 [T, 5] in that order) on `device`"""
+        c = getattr(self, "_seq_cache", None)
+        coefs = self._coef_table()
+        if c is None or c[0] is not coefs or c[1] != str(device):
+            t_seq = torch.arange(self.num_timesteps - 1, -1, -1, device=device, dtype=torch.long)
+            c = self._seq_cache = (coefs, str(device), t_seq, coefs.to(device)[t_seq].contiguous())
+        return c[2], c[3]
+
     def _step(self, lib, x, eps_c, eps_u, noise, out, coef_row_ptr, g):
         B = x.shape[0]
         _lib.check(lib.dmc_ddpm_step(x.data_ptr(), eps_c.data_ptr(), _lib.ptr(eps_u), noise.data_ptr(), out.data_ptr(), B,
@@ -95,6 +104,11 @@ class DDPM(DiffusionBase):
         t_batch = torch.empty((B,), device=img.device, dtype=torch.long)
         nxt = torch.empty_like(img)
         g = guidance(0.0, 1)
+        if self._graph_ok(model, return_all_timesteps, step_noise):
+            t_seq, coef_seq = self._seq_tables(img.device)
+            with self._uniform_t(model):
+                return self._graph_loop(model, img, None if y is None else y.to(img.device), True, t_seq, coef_seq, g,
+                                        cfg=False, draw_noise=True, desc="Sampling")
         imgs = []
         with self._uniform_t(model):
             for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)), "Sampling", self.num_timesteps)):
@@ -129,6 +143,11 @@ class DDPM(DiffusionBase):
         t_batch = torch.empty((B,), device=img.device, dtype=torch.long)
         nxt = torch.empty_like(img)
         g = guidance(cfg_scale, 2, n, float(p_threshold)) if p_threshold is not None else guidance(cfg_scale, 1)
+        if self._graph_ok(model, return_all_timesteps, step_noise) and hasattr(model, "forward_cfg"):
+            t_seq, coef_seq = self._seq_tables(img.device)
+            with self._uniform_t(model):
+                return self._graph_loop(model, img, y, True, t_seq, coef_seq, g, cfg=True, draw_noise=True,
+                                        desc=f"DDPM Sampling with CFG scale {cfg_scale}")
         imgs = []
         with self._uniform_t(model):
             for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)),

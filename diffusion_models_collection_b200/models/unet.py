@@ -254,6 +254,7 @@ class _PlanBuilder:
 class UNet(nn.Module):
     """UNet model for diffusion (reference: models/unet.py:126-292); see the module docstring."""
 
+    graph_capturable = True  # a forward is a fixed, allocation-free, sync-free launch list (samplers capture it)
     max_images_per_launch = 2048  # activations of larger batches are processed in chunks of this many images
     upsample_phases = os.environ.get("DMC_UPSAMPLE_PHASES", "1") != "0"  # Upsample as four 2x2 phase convolutions
 

@@ -86,6 +86,18 @@ DMC_API int dmc_ddpm_step(const float* x, const float* eps_c, const float* eps_u
                   int32_t B, int32_t n_per_sample, const dmc_ddpm_coef* coef_dev, const dmc_guidance* g,
                   void* stream);
 
+/* The same two steps with the coefficient row chosen on the DEVICE: row = coef_table_dev + step_index_dev[0].  Lets one
+ * captured CUDA graph of "forward + step" be replayed for every step of a sampling loop (x_out may alias x). */
+DMC_API int dmc_ddim_step_at(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out,
+                     int32_t B, int32_t n_per_sample, const dmc_ddim_coef* coef_table_dev,
+                     const int32_t* step_index_dev, const dmc_guidance* g, void* stream);
+DMC_API int dmc_ddpm_step_at(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_out,
+                     int32_t B, int32_t n_per_sample, const dmc_ddpm_coef* coef_table_dev,
+                     const int32_t* step_index_dev, const dmc_guidance* g, void* stream);
+/* Loop counter of a replayed step graph: cur = counter[0]; counter[1] = cur; counter[0] = cur + 1;
+ * t_out[0..n) = t_table[cur]  (the timestep tensor the denoiser reads; replaces torch.full, ddim.py:287-297). */
+DMC_API int dmc_advance(int32_t* counter_dev, const int64_t* t_table_dev, int64_t* t_out_dev, int32_t n, void* stream);
+
 /* x_t = sqrt_acp[t_n] * x0 + sqrt_1m_acp[t_n] * noise with per-sample t (training).  Replaces q_sample
  * (diffusion/ddpm.py:84-104, ddim.py:87-107). */
 DMC_API int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
@@ -101,6 +113,8 @@ typedef struct dmc_plan dmc_plan;
 DMC_API int dmc_plan_create(dmc_plan** out);
 DMC_API int dmc_plan_destroy(dmc_plan* p);
 DMC_API int dmc_plan_run(dmc_plan* p, void* stream);
+/* runs only op `op_index` (profiling / debugging aid: lets ncu capture one layer with realistic inputs in place) */
+DMC_API int dmc_plan_run_op(dmc_plan* p, int32_t op_index, void* stream);
 /* number of kernel launches (and memsets) one dmc_plan_run() performs */
 DMC_API int dmc_plan_num_launches(const dmc_plan* p);
 /* algorithmic tensor-core FLOPs (2*M*N*K summed over GEMM-shaped ops, real channels only) per run */
@@ -249,6 +263,7 @@ typedef struct {
   int32_t B, n_per_sample;
   const void* coef_dev; /* dmc_ddim_coef* or dmc_ddpm_coef* (device) */
   dmc_guidance g;
+  const int32_t* step_index_dev; /* optional: use row coef_dev[step_index_dev[0]] */
 } dmc_step_desc;
 DMC_API int dmc_plan_add_ddim_step(dmc_plan* p, const dmc_step_desc* d);
 DMC_API int dmc_plan_add_ddpm_step(dmc_plan* p, const dmc_step_desc* d);

@@ -145,3 +145,39 @@ def test_ddim_teacher_forced_step_parity(golden):
         got = d.p_sample(net, x.cuda(), t.cuda(), tn.cuda())
     want = so.ddim_step(so.make_tables(), x, torch.from_numpy(golden["unet"]["uncond_t500"]), t, tn)
     assert float((got.cpu() - want).abs().max()) < 3e-2
+
+
+@pytest.mark.parametrize("kind", ["ddim_cfg", "ddim_eta", "ddpm", "ddpm_cfg", "ddim_uncond_two_chunks"])
+def test_cuda_graph_loop_is_bit_identical_to_the_launch_loop(kind, monkeypatch):
+    """the whole sampling loop as ONE captured graph replayed per step (device-side step counter, timestep and
+    coefficient row; per-step noise drawn by torch.randn_like inside the graph) returns exactly what the launch-by-launch
+    loop returns from the same seed -- same kernels, same Philox stream, same order as the reference's loop"""
+    from diffusion_models_collection_b200.diffusion import DDIM, DDPM
+    from diffusion_models_collection_b200.models import UNet
+
+    cond = kind in ("ddim_cfg", "ddpm_cfg", "ddim_eta")
+    net = build_unet(SMALL_UNET, 10 if cond else None, 4 if cond else 5)
+    if kind == "ddim_uncond_two_chunks":
+        monkeypatch.setattr(UNet, "max_images_per_launch", 4)  # 6 images -> chunks of 4 + 2 inside the captured step
+    B = 6
+    y = torch.tensor([1, 10, 3, 0, 7, 2]).cuda()
+    outs = []
+    for use_graph in (False, True, True):  # the third run replays the cached graph
+        if kind.startswith("ddim"):
+            d = outs[1][1] if len(outs) == 2 else DDIM(1000, 7, eta=0.4 if kind == "ddim_eta" else 0.0, device="cuda")
+        else:
+            d = outs[1][1] if len(outs) == 2 else DDPM(12, device="cuda")
+        d.progress = False
+        d.use_cuda_graph = use_graph
+        torch.manual_seed(123)
+        if kind in ("ddim_cfg", "ddpm_cfg"):
+            img = d.sample_with_cfg(net, (B, 3, 32, 32), y, cfg_scale=2.5)
+        elif kind == "ddim_eta":
+            img = d.sample(net, (B, 3, 32, 32), y)
+        else:
+            img = d.sample(net, (B, 3, 32, 32))
+        assert torch.isfinite(img).all()
+        outs.append((img.clone(), d))
+    assert getattr(outs[1][1], "_graph_cache", None) is not None
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][0], outs[2][0])
