@@ -62,7 +62,25 @@ class ConvDesc(C.Structure):
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("stride", C.c_int32),
                 ("up_phase", C.c_int32), ("weight", vp), ("Cout", C.c_int32), ("Cout_pad", C.c_int32),
                 ("Ktot", C.c_int32), ("bias", vp), ("cond", vp), ("cond_stride", C.c_int32), ("residual", vp),
-                ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("stats_slots", C.c_int32), ("impl", C.c_int32)]
+                ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("stats_slots", C.c_int32), ("impl", C.c_int32),
+                ("act", C.c_int32), ("gate", vp), ("gate_stride", C.c_int32), ("residual_f32", vp), ("out_f32_nhwc", vp),
+                ("unpatch_p", C.c_int32)]
+
+
+class DitCondDesc(C.Structure):
+    _fields_ = [("t", vp), ("y", vp), ("B", C.c_int32), ("uniform_t", C.c_int32), ("num_classes", C.c_int32),
+                ("freq_dim", C.c_int32), ("hidden", C.c_int32), ("ncols", C.c_int32), ("freqs", vp), ("w1", vp), ("b1", vp),
+                ("w2", vp), ("b2", vp), ("emb", vp), ("w_all", vp), ("b_all", vp), ("scratch", vp), ("mod", vp)]
+
+
+class PatchEmbedDesc(C.Structure):
+    _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("patch", C.c_int32), ("hidden", C.c_int32), ("weight", vp), ("bias", vp), ("pos", vp), ("out", vp)]
+
+
+class LnModDesc(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("shift", vp), ("scale", vp),
+                ("mod_stride", C.c_int32), ("eps", C.c_float)]
 
 
 class AttnDesc(C.Structure):
@@ -109,12 +127,16 @@ SYMBOLS = {
     "dmc_plan_add_gn_apply": (C.c_int, [vp, C.POINTER(GnApplyDesc)]),
     "dmc_plan_add_conv": (C.c_int, [vp, C.POINTER(ConvDesc)]),
     "dmc_plan_add_attention": (C.c_int, [vp, C.POINTER(AttnDesc)]),
+    "dmc_plan_add_dit_cond": (C.c_int, [vp, C.POINTER(DitCondDesc)]),
+    "dmc_plan_add_patch_embed": (C.c_int, [vp, C.POINTER(PatchEmbedDesc)]),
+    "dmc_plan_add_ln_modulate": (C.c_int, [vp, C.POINTER(LnModDesc)]),
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
 }
 
-OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm"]
+OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm", "dit_cond",
+            "patch_embed", "ln_modulate"]
 
 _lock = threading.Lock()
 _lib = None

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdmc_b200.so")
 OBJ = os.path.join(PKG, "csrc", "_build")
 
-SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu"]
+SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu", "dit_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

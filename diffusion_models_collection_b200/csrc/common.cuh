@@ -41,6 +41,16 @@ int num_sms();
 // result).  A full-precision division here halves the bandwidth of the GroupNorm-apply pass.
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// GELU, erf form (nn.GELU() default): x * Phi(x) with Phi(x) ~ sigmoid(2 u (a + b u^2 + c u^4)), u = clamp(x, -6, 6).
+// The odd quintic is a minimax fit of the logit of the normal CDF (max abs error of x * Phi 2.5e-5 over all x, 20x
+// below the plain tanh form and far below the bf16 rounding of the result); two SFU ops (ex2, rcp).
+__device__ __forceinline__ float gelu_f(float x) {
+  const float u = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float u2 = u * u;
+  const float arg = u * fmaf(u2, fmaf(u2, -3.51516792e-4f, 3.70056461e-2f), 7.97507884e-1f);
+  return __fdividef(x, 1.0f + __expf(-2.0f * arg));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -52,6 +52,13 @@ struct ConvKParams {
   float* out_nchw;
   float* stats;
   int stats_slots, stats_slot_base;
+  // transformer epilogues (DiT)
+  int act;                    // 1: GELU
+  const float* gate;          // per-image per-channel multiplier
+  int gate_stride;
+  const float* residual_f32;  // fp32 NHWC residual stream
+  float* out_f32;             // fp32 NHWC output
+  int unpatch_p;              // > 0: out_nchw columns are (pi, qi, c) patch entries
 };
 
 struct ConvPrepared {
@@ -349,12 +356,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (p.out_nchw != nullptr) {
             // model head: few real channels, fp32 NCHW, coalesced along W across the warp
             if (valid) {
+              const int up = p.unpatch_p;
+              const int oc = up > 0 ? p.Cout / (up * up) : p.Cout;  // image channels
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int c = cg + j;
                 if (c < p.Cout) {
                   float o = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
-                  p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+                  if (up > 0) {  // DiT.unpatchify: column = (pi * up + qi) * oc + ch
+                    const int ch = c % oc, pq = c / oc;
+                    const int yy = oh * up + pq / up, xx = ow * up + pq % up;
+                    p.out_nchw[((static_cast<size_t>(n) * oc + ch) * (p.out_H * up) + yy) * (p.out_W * up) + xx] = o;
+                  } else {
+                    p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+                  }
                 }
               }
             }
@@ -362,6 +377,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += add[j];
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          }
+          if (p.gate != nullptr && valid) {
+            const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(n) * p.gate_stride + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 gv = __ldg(g4 + j);
+              v[4 * j] *= gv.x; v[4 * j + 1] *= gv.y; v[4 * j + 2] *= gv.z; v[4 * j + 3] *= gv.w;
+            }
+          }
+          if (p.residual_f32 != nullptr && valid) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual_f32 + pix * p.Cout + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rv = r4[j];  // plain load: out_f32 may alias the residual stream
+              v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+            }
+          }
+          if (p.out_f32 != nullptr && valid) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
           if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -479,9 +519,17 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   DMC_REQUIRE(d.up_phase >= -1 && d.up_phase <= 3, "conv: up_phase=%d", d.up_phase);
   DMC_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0, "conv: empty input");
   DMC_REQUIRE(d.Hin % d.stride == 0 && d.Win % d.stride == 0, "conv: odd spatial size with stride 2");
-  DMC_REQUIRE(d.weight && (d.out_bf16 || d.out_f32_nchw), "conv: null weight/output");
+  DMC_REQUIRE(d.weight && (d.out_bf16 || d.out_f32_nchw || d.out_f32_nhwc), "conv: null weight/output");
   DMC_REQUIRE(d.Cout_pad % 32 == 0 && d.Cout <= d.Cout_pad, "conv: Cout_pad=%d must be a multiple of 32", d.Cout_pad);
-  if (d.out_bf16) DMC_REQUIRE(d.Cout % 32 == 0, "conv: bf16 NHWC output needs Cout %% 32 == 0 (got %d)", d.Cout);
+  if (d.out_bf16 || d.out_f32_nhwc)
+    DMC_REQUIRE(d.Cout % 32 == 0, "conv: NHWC output needs Cout %% 32 == 0 (got %d)", d.Cout);
+  DMC_REQUIRE(d.act == 0 || d.act == 1, "conv: act=%d", d.act);
+  DMC_REQUIRE(!(d.residual && d.residual_f32), "conv: bf16 and fp32 residuals are exclusive");
+  DMC_REQUIRE(d.unpatch_p >= 0 && (d.unpatch_p == 0 || (d.out_f32_nchw && d.up_phase < 0 && d.stride == 1 &&
+                                                        d.Cout % (d.unpatch_p * d.unpatch_p) == 0)),
+              "conv: unpatch_p=%d needs an fp32 NCHW output and Cout = p*p*channels", d.unpatch_p);
+  if (d.out_f32_nchw) DMC_REQUIRE(!d.gate && !d.residual_f32 && !d.out_f32_nhwc && d.act == 0,
+                                  "conv: the fp32 NCHW head takes bias only");
   if (d.stats) DMC_REQUIRE(d.out_bf16 != nullptr, "conv: stats need a bf16 output");
 
   ConvPrepared* P = new (std::nothrow) ConvPrepared();
@@ -562,6 +610,10 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   kp.out_nchw = d.out_f32_nchw;
   kp.stats = d.stats;
+  kp.act = d.act;
+  kp.gate = d.gate; kp.gate_stride = d.gate_stride;
+  kp.residual_f32 = d.residual_f32; kp.out_f32 = d.out_f32_nhwc;
+  kp.unpatch_p = d.unpatch_p;
   if (d.stats) {
     const int ppi_img = Hout * Wout;  // iteration pixels per image
     const int base = ppi_img >= 32 ? ppi_img / 32 : 1;

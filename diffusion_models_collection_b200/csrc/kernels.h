@@ -24,6 +24,12 @@ int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st);
 int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st);
 int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
 
+// dit_ops.cu
+int launch_dit_cond(const dmc_dit_cond_desc& d, cudaStream_t st);
+int dit_cond_num_launches(const dmc_dit_cond_desc& d);
+int launch_patch_embed(const dmc_patch_embed_desc& d, cudaStream_t st);
+int launch_ln_modulate(const dmc_ln_mod_desc& d, cudaStream_t st);
+
 // attention.cu : CUDA-core flash kernel (any L; debug / shapes the tensor-core kernel does not cover)
 int launch_attention(const dmc_attn_desc& d, cudaStream_t st);
 // attention_umma.cu : tcgen05 kernel

@@ -25,7 +25,8 @@ static EncodeTiledFn g_encode = nullptr;
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 
-enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM };
+enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM,
+              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD };
 
 struct Op {
   int kind;
@@ -39,6 +40,9 @@ struct Op {
     dmc_attn_desc attn;
     dmc_upsample_desc up;
     dmc_step_desc step;
+    dmc_dit_cond_desc dit_cond;
+    dmc_patch_embed_desc patch;
+    dmc_ln_mod_desc ln_mod;
   };
   ConvPrepared* conv_prep;
   AttnPrepared* attn_prep;
@@ -70,6 +74,9 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_UPSAMPLE: return launch_upsample(op.up, st);
     case OP_DDIM: return launch_step(false, op.step, st);
     case OP_DDPM: return launch_step(true, op.step, st);
+    case OP_DIT_COND: return launch_dit_cond(op.dit_cond, st);
+    case OP_PATCH_EMBED: return launch_patch_embed(op.patch, st);
+    case OP_LN_MOD: return launch_ln_modulate(op.ln_mod, st);
   }
   set_error("plan: unknown op kind %d", op.kind);
   return -1;
@@ -188,7 +195,8 @@ double dmc_plan_op_bytes(const dmc_plan* p, int32_t i) {
 int dmc_plan_num_launches(const dmc_plan* p) {
   if (!p) return -1;
   int n = 0;
-  for (const auto& op : p->ops) n += (op.kind == OP_COND) ? cond_num_launches(op.cond) : 1;
+  for (const auto& op : p->ops)
+    n += (op.kind == OP_COND) ? cond_num_launches(op.cond) : (op.kind == OP_DIT_COND ? dit_cond_num_launches(op.dit_cond) : 1);
   return n;
 }
 
@@ -205,6 +213,9 @@ int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* pt
   if (op.kind == OP_STEM && which == 0) { op.stem.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 0) { op.cond.t = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 1) { op.cond.y = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_PATCH_EMBED && which == 0) { op.patch.x = static_cast<const float*>(ptr); return 0; }
+  if (op.kind == OP_DIT_COND && which == 0) { op.dit_cond.t = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_DIT_COND && which == 1) { op.dit_cond.y = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_CONV && which == 2 && op.conv.out_f32_nchw != nullptr && ptr != nullptr) {
     op.conv.out_f32_nchw = static_cast<float*>(const_cast<void*>(ptr));
     return 0;
@@ -306,7 +317,7 @@ int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d) {
   double in_bytes = 0;
   for (int s = 0; s < d->nsrc; ++s) in_bytes += 2.0 * d->B * d->Hin * d->Win * d->src_c[s];
   op.bytes = in_bytes + 2.0 * static_cast<double>(d->Cout_pad) * d->Ktot + opix * d->Cout * (d->out_bf16 ? 2.0 : 4.0) +
-             (d->residual ? 2.0 * opix * d->Cout : 0.0);
+             (d->residual ? 2.0 * opix * d->Cout : 0.0) + (d->residual_f32 ? 4.0 * opix * d->Cout : 0.0);
   return push(p, op);
 }
 
@@ -322,6 +333,36 @@ int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d) {
   }
   op.flops = 4.0 * d->B * static_cast<double>(d->L) * d->L * d->C;  // QK^T and PV
   op.bytes = 2.0 * d->B * d->L * 4.0 * d->C;
+  return push(p, op);
+}
+
+int dmc_plan_add_dit_cond(dmc_plan* p, const dmc_dit_cond_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_dit_cond: null argument");
+  Op op;
+  op.kind = OP_DIT_COND;
+  op.dit_cond = *d;
+  op.bytes = 4.0 * (static_cast<double>(d->ncols) * d->hidden + 2.0 * d->B * d->ncols);
+  return push(p, op);
+}
+
+int dmc_plan_add_patch_embed(dmc_plan* p, const dmc_patch_embed_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_patch_embed: null argument");
+  DMC_REQUIRE(d->patch > 0, "dmc_plan_add_patch_embed: patch=%d", d->patch);
+  Op op;
+  op.kind = OP_PATCH_EMBED;
+  op.patch = *d;
+  const double tokens = static_cast<double>(d->B) * (d->H / d->patch) * (d->W / d->patch);
+  op.bytes = 4.0 * (static_cast<double>(d->B) * d->Cin * d->H * d->W + tokens * d->hidden);
+  op.flops = 2.0 * tokens * d->hidden * d->Cin * d->patch * d->patch;
+  return push(p, op);
+}
+
+int dmc_plan_add_ln_modulate(dmc_plan* p, const dmc_ln_mod_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_ln_modulate: null argument");
+  Op op;
+  op.kind = OP_LN_MOD;
+  op.ln_mod = *d;
+  op.bytes = 6.0 * d->B * static_cast<double>(d->L) * d->C;  // fp32 in, bf16 out
   return push(p, op);
 }
 

@@ -1,22 +1,36 @@
-"""DiT denoiser drop-in: constructor, attributes and parameter names of /root/reference/models/dit.py:154-295.
+"""DiT denoiser drop-in: constructor, attributes, parameter names/shapes and ``forward(x, t, y=None)`` contract of
+/root/reference/models/dit.py:154-295; the forward is a plan of hand-written sm_100a kernels (C ABI, include/dmc.h):
 
-Parameters are registered with the reference's names/shapes (state_dict contract).  The native
-sm_100a forward (tcgen05 GEMMs with fused bias/GELU/gate-residual epilogues, LN+modulate, patchify/unpatchify)
-is wired in `forward`."""
+  dit_cond      TimestepEmbedder + label lookup + ALL depth+1 adaLN_modulation linears -> one [B, (6*depth+2)*hidden] table
+  patch_embed   p x p patch conv + bias + pos_embed: fp32 NCHW image -> fp32 token stream [B, L, hidden]
+  per block     ln_modulate (LayerNorm + scale/shift -> bf16)  ->  qkv GEMM (+bias)  ->  tcgen05 attention
+                -> out_proj GEMM with "x += gate * (acc + bias)" epilogue on the fp32 stream
+                -> ln_modulate -> fc1 GEMM (+bias, GELU) -> fc2 GEMM with the gate-residual epilogue
+  final         ln_modulate -> linear GEMM whose epilogue un-patchifies straight into the fp32 NCHW eps
+
+The GEMMs are the tcgen05/TMA implicit-GEMM kernel of the UNet (1x1 "convolutions" over the token grid).  The residual
+stream stays fp32 (12 blocks x 2 residual adds); GEMM operands are bf16, accumulation fp32 in TMEM.
+There is no PyTorch / CPU fallback: the forward raises when the CUDA library or device is missing."""
 
 from __future__ import annotations
 
+import contextlib
+import ctypes as C
 import math
+import os
 from typing import Tuple
 
 import torch
 import torch.nn as nn
 
 from .. import _lib
-from .unet import _register
+from .unet import _register, _round_up
 
 
 class DiT(nn.Module):
+    graph_capturable = True  # a forward is a fixed, allocation-free, sync-free launch list (samplers capture it)
+    max_tokens_per_launch = 2048 * 256  # larger batches are processed in chunks
+
     def __init__(self, img_size: Tuple[int, int] = (32, 32), patch_size=2, in_channels=3, hidden_size=768, depth=12,
                  num_heads=12, mlp_ratio=4.0, num_classes=None, dropout=0.1):
         super().__init__()
@@ -33,6 +47,10 @@ class DiT(nn.Module):
         self.dropout = dropout
         self.h_tokens = img_h // patch_size
         self.w_tokens = img_w // patch_size
+        self._uniform_t = False
+        self._plans = {}
+        self._packed = None
+        self._packed_version = None
         self._init_parameters()
 
     def _init_parameters(self):
@@ -71,7 +89,273 @@ class DiT(nn.Module):
         xavier("final_layer.linear", p * p * c, hs, zero=True)
         xavier("final_layer.adaLN_modulation.1", 2 * hs, hs, zero=True)
 
-    def forward(self, x, t, y=None):
+    # ------------------------------------------------------------------------------------------------
+    # weight packing (one-time / on parameter change; plain torch ops -- not on the hot path)
+    # ------------------------------------------------------------------------------------------------
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device):
+        ver = (str(device), self._param_version())
+        if self._packed is not None and self._packed_version == ver:
+            return self._packed
+        sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in self.state_dict().items()}
+        hs, p, c = self.hidden_size, self.patch_size, self.in_channels
+        W, Bv = {}, {}
+        w_all, b_all = [], []
+        for i in range(self.depth):
+            b = f"blocks.{i}"
+            W[b + ".qkv"], Bv[b + ".qkv"] = sd[b + ".attn.in_proj_weight"], sd[b + ".attn.in_proj_bias"]
+            W[b + ".out"], Bv[b + ".out"] = sd[b + ".attn.out_proj.weight"], sd[b + ".attn.out_proj.bias"]
+            W[b + ".fc1"], Bv[b + ".fc1"] = sd[b + ".mlp.0.weight"], sd[b + ".mlp.0.bias"]
+            W[b + ".fc2"], Bv[b + ".fc2"] = sd[b + ".mlp.3.weight"], sd[b + ".mlp.3.bias"]
+            w_all.append(sd[b + ".adaLN_modulation.1.weight"])
+            b_all.append(sd[b + ".adaLN_modulation.1.bias"])
+        w_all.append(sd["final_layer.adaLN_modulation.1.weight"])
+        b_all.append(sd["final_layer.adaLN_modulation.1.bias"])
+        fin = sd["final_layer.linear.weight"]
+        W["final"] = torch.cat([fin, fin.new_zeros(_round_up(fin.shape[0], 32) - fin.shape[0], hs)], dim=0)
+        Bv["final"] = sd["final_layer.linear.bias"]
+        offs, total = {}, 0
+        for k, v in W.items():
+            offs[k] = total
+            total += _round_up(v.numel() * 2)
+        wblob = torch.zeros(total // 2, dtype=torch.bfloat16, device=device)
+        for k, v in W.items():
+            wblob[offs[k] // 2: offs[k] // 2 + v.numel()] = v.reshape(-1).to(torch.bfloat16)
+        half = 128  # frequency_embedding_size 256 (models/dit.py:32)
+        # models/dit.py:44-45, the reference's own expression (divisor `half`, fp32 arange on the CPU, then moved)
+        freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device)
+        self._packed = dict(
+            sd=sd, wblob=wblob, woffs=offs, wshape={k: tuple(v.shape) for k, v in W.items()}, bias=Bv,
+            w_all=torch.cat(w_all, dim=0).contiguous(), b_all=torch.cat(b_all, dim=0).contiguous(), freqs=freqs.contiguous(),
+            patch_wT=sd["x_embedder.proj.weight"].reshape(hs, c * p * p).t().contiguous(),
+            pos=sd["pos_embed"].reshape(-1, hs).contiguous(), ncols=(6 * self.depth + 2) * hs,
+        )
+        self._packed_version = ver
+        for pl in self._plans.values():
+            pl.destroy()
+        self._plans = {}
+        return self._packed
+
+    def _get_plan(self, device, nimg, x_batch, has_y, uniform_t):
+        key = (str(device), nimg, x_batch, has_y, uniform_t)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = _DiTPlan(self, self._ensure_packed(device), device, nimg, x_batch, has_y, uniform_t)
+            self._plans[key] = pl
+        return pl
+
+    @property
+    def max_images_per_launch(self):
+        return max(2, self.max_tokens_per_launch // (self.h_tokens * self.w_tokens))
+
+    def _run(self, x, t, y, cfg):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise _lib.DmcError("DiT.forward: CUDA tensors only -- the B200 hot path has no CPU / PyTorch fallback")
-        raise NotImplementedError("native DiT forward: not wired yet in this round (UNet path first, SURVEY.md section 7.1 step 9)")
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError("the native DiT implements the inference forward only (sampling); "
+                                      "wrap calls in torch.no_grad() / model.eval()")
+        _lib.load()
+        device = x.device
+        self._ensure_packed(device)
+        Hh, Ww = self.img_size
+        if x.dim() != 4 or x.shape[1] != self.in_channels or tuple(x.shape[2:]) != (Hh, Ww):
+            raise ValueError(f"DiT.forward: expected x of shape [B, {self.in_channels}, {Hh}, {Ww}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        if t.shape[0] != B or (y is not None and y.shape[0] != B):
+            raise ValueError("DiT.forward: t / y batch size mismatch")
+        x = x.contiguous().float()
+        t = t.to(device=device, dtype=torch.long).contiguous()  # the reference calls t.float() on integer timesteps
+        has_y = self.num_classes is not None and y is not None
+        if cfg and not has_y:
+            raise ValueError("forward_cfg needs a conditional model and labels")
+        if has_y:
+            y = y.to(device=device, dtype=torch.long).contiguous()
+        mult = 2 if cfg else 1
+        out = torch.empty((mult * B, self.out_channels, Hh, Ww), device=device, dtype=torch.float32)
+        cb = max(1, min(B, self.max_images_per_launch // mult))
+        with torch.cuda.device(device):
+            for s in range(0, B, cb):
+                n = min(cb, B - s)
+                pl = self._get_plan(device, mult * n, n, has_y, bool(self._uniform_t))
+                pl.run(x[s:s + n], t[s:s + n], y[s:s + n] if has_y else None, cfg,
+                       out[s:s + n], out[B + s:B + s + n] if cfg else None)
+        return out
+
+    @contextlib.contextmanager
+    def uniform_timesteps(self):
+        """Promise that every t[n] of the calls inside the block is the same value (what the samplers do): the adaLN
+        table then has only num_classes + 1 distinct rows, computed once per forward."""
+        prev = self._uniform_t
+        self._uniform_t = True
+        try:
+            yield self
+        finally:
+            self._uniform_t = prev
+
+    def forward(self, x, t, y=None):
+        """eps = DiT(x, t, y): x fp32 [B, C, H, W], t int64 [B], y int64 [B] in [0, num_classes] (0 = null) or None."""
+        return self._run(x, t, y, cfg=False)
+
+    def forward_cfg(self, x, t, y):
+        """(eps(x, t, y), eps(x, t, 0)) as ONE batch of 2B images (the reference runs two forwards, ddim.py:300-301)."""
+        B = x.shape[0]
+        out = self._run(x, t, y, cfg=True)
+        return out[:B], out[B:]
+
+    def plan_info(self, batch, cfg=False, device=None):
+        device = torch.device(device or next(self.parameters()).device)
+        _lib.load()
+        mult = 2 if cfg else 1
+        self._ensure_packed(device)
+        return self._get_plan(device, mult * batch, batch, self.num_classes is not None, bool(self._uniform_t))
+
+    def launches_per_forward(self, batch, cfg=False):
+        mult = 2 if cfg else 1
+        cb = max(1, min(batch, self.max_images_per_launch // mult))
+        n = 0
+        for s0 in range(0, batch, cb):
+            n += self.plan_info(min(cb, batch - s0), cfg=cfg).num_launches
+        return n + 1
+
+
+class _DiTPlan:
+    """Owns one dmc_plan (C side) and the activation buffers of one (batch, mode) signature."""
+
+    def __init__(self, net: DiT, pk, device, nimg, x_batch, has_y, uniform_t):
+        lib = _lib.load()
+        self.lib, self.nimg, self.x_batch, self.has_y = lib, nimg, x_batch, has_y
+        hs, depth, heads = net.hidden_size, net.depth, net.num_heads
+        Ht, Wt = net.h_tokens, net.w_tokens
+        L = Ht * Wt
+        Hh, Ww = net.img_size
+        hid = int(hs * net.mlp_ratio)
+        ncols = pk["ncols"]
+        if hs % 128 != 0 or hid % 64 != 0:
+            raise _lib.DmcError(f"native DiT needs hidden_size % 128 == 0 and mlp hidden % 64 == 0 (got {hs}, {hid})")
+        f32, bf16 = torch.float32, torch.bfloat16
+        self.tok = torch.empty((nimg, L, hs), dtype=f32, device=device)
+        self.hb = torch.empty((nimg, L, hs), dtype=bf16, device=device)
+        self.qkv = torch.empty((nimg, L, 3 * hs), dtype=bf16, device=device)
+        self.ao = torch.empty((nimg, L, hs), dtype=bf16, device=device)
+        self.mlp = torch.empty((nimg, L, hid), dtype=bf16, device=device)
+        self.mod = torch.empty((nimg, ncols), dtype=f32, device=device)
+        R = ((net.num_classes + 1) if has_y else 1) if uniform_t else nimg
+        self.scratch = torch.empty((R * (2 * hs + ncols),), dtype=f32, device=device)
+        self.t_stage = torch.zeros((nimg,), dtype=torch.long, device=device)
+        self.y_stage = torch.zeros((nimg,), dtype=torch.long, device=device) if has_y else None
+        self.eps = torch.empty((nimg, net.out_channels, Hh, Ww), dtype=f32, device=device)
+        self.workspace_bytes = sum(t.numel() * t.element_size() for t in (self.tok, self.hb, self.qkv, self.ao, self.mlp, self.mod))
+        handle = C.c_void_p()
+        _lib.check(lib.dmc_plan_create(C.byref(handle)), "dmc_plan_create")
+        self.handle = handle
+        self.op_names = []
+        sd = pk["sd"]
+
+        def add(fn, desc, name):
+            idx = _lib.check(fn(handle, C.byref(desc)), name)
+            self.op_names.append(name)
+            return idx
+
+        d = _lib.DitCondDesc()
+        d.t, d.y = self.t_stage.data_ptr(), (self.y_stage.data_ptr() if has_y else None)
+        d.B, d.uniform_t = nimg, 1 if uniform_t else 0
+        d.num_classes = net.num_classes if net.num_classes is not None else 0
+        d.freq_dim, d.hidden, d.ncols = 256, hs, ncols
+        d.freqs = pk["freqs"].data_ptr()
+        d.w1, d.b1 = sd["t_embedder.mlp.0.weight"].data_ptr(), sd["t_embedder.mlp.0.bias"].data_ptr()
+        d.w2, d.b2 = sd["t_embedder.mlp.2.weight"].data_ptr(), sd["t_embedder.mlp.2.bias"].data_ptr()
+        d.emb = sd["y_embedder.embedding_table.weight"].data_ptr() if has_y else None
+        d.w_all, d.b_all = pk["w_all"].data_ptr(), pk["b_all"].data_ptr()
+        d.scratch, d.mod = self.scratch.data_ptr(), self.mod.data_ptr()
+        self.cond_idx = add(lib.dmc_plan_add_dit_cond, d, "dit_cond")
+
+        d = _lib.PatchEmbedDesc()
+        d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
+        d.Cin, d.H, d.W, d.patch, d.hidden = net.in_channels, Hh, Ww, net.patch_size, hs
+        d.weight, d.bias = pk["patch_wT"].data_ptr(), sd["x_embedder.proj.bias"].data_ptr()
+        d.pos, d.out = pk["pos"].data_ptr(), self.tok.data_ptr()
+        self.patch_idx = add(lib.dmc_plan_add_patch_embed, d, "patch_embed")
+
+        def ln(col_shift, col_scale, name):
+            d = _lib.LnModDesc()
+            d.x, d.out, d.B, d.L, d.C = self.tok.data_ptr(), self.hb.data_ptr(), nimg, L, hs
+            d.shift, d.scale = self.mod.data_ptr() + 4 * col_shift, self.mod.data_ptr() + 4 * col_scale
+            d.mod_stride, d.eps = ncols, 1e-6
+            add(lib.dmc_plan_add_ln_modulate, d, name)
+
+        def gemm(src, cin, wname, cout, name, out_bf16=None, act=0, gate_col=None, head=False):
+            d = _lib.ConvDesc()
+            d.nsrc = 1
+            d.src[0], d.src_c[0], d.src_taps[0] = src.data_ptr(), cin, 1
+            d.B, d.Hin, d.Win, d.stride, d.up_phase = nimg, Ht, Wt, 1, -1
+            rows, K = pk["wshape"][wname]
+            d.weight = pk["wblob"].data_ptr() + pk["woffs"][wname]
+            d.Cout, d.Cout_pad, d.Ktot = cout, rows, K
+            d.bias = pk["bias"][wname].data_ptr()
+            d.act = act
+            if head:
+                d.out_f32_nchw, d.unpatch_p = self.eps.data_ptr(), net.patch_size
+            elif gate_col is not None:  # x += gate * (acc + bias) on the fp32 residual stream, in place
+                d.gate, d.gate_stride = self.mod.data_ptr() + 4 * gate_col, ncols
+                d.residual_f32, d.out_f32_nhwc = self.tok.data_ptr(), self.tok.data_ptr()
+            else:
+                d.out_bf16 = out_bf16.data_ptr()
+            return add(lib.dmc_plan_add_conv, d, name)
+
+        for i in range(depth):
+            b, base = f"blocks.{i}", i * 6 * hs
+            ln(base, base + hs, b + ".norm1")
+            gemm(self.hb, hs, b + ".qkv", 3 * hs, b + ".qkv", out_bf16=self.qkv)
+            a = _lib.AttnDesc()
+            a.qkv, a.out, a.B, a.L, a.heads, a.C = self.qkv.data_ptr(), self.ao.data_ptr(), nimg, L, heads, hs
+            a.impl = int(os.environ.get("DMC_DEBUG_ATTN_IMPL", "0"))
+            add(lib.dmc_plan_add_attention, a, b + ".attention")
+            gemm(self.ao, hs, b + ".out", hs, b + ".out_proj", gate_col=base + 2 * hs)
+            ln(base + 3 * hs, base + 4 * hs, b + ".norm2")
+            gemm(self.hb, hs, b + ".fc1", hid, b + ".fc1", out_bf16=self.mlp, act=1)
+            gemm(self.mlp, hid, b + ".fc2", hs, b + ".fc2", gate_col=base + 5 * hs)
+        base = depth * 6 * hs
+        ln(base, base + hs, "final_layer.norm")
+        self.head_idx = gemm(self.hb, hs, "final", net.patch_size ** 2 * net.out_channels, "final_layer.linear", head=True)
+        self.num_launches = lib.dmc_plan_num_launches(handle)
+        self.gemm_flops = lib.dmc_plan_gemm_flops(handle)
+
+    def run(self, x, t, y, cfg, out_a, out_b):
+        lib, n = self.lib, self.x_batch
+        if cfg:
+            self.t_stage[:n].copy_(t)
+            self.t_stage[n:].copy_(t)
+            self.y_stage[:n].copy_(y)  # second half stays 0 = null label
+        else:
+            self.t_stage.copy_(t)
+            if self.has_y:
+                self.y_stage.copy_(y)
+        _lib.check(lib.dmc_plan_rebind(self.handle, self.patch_idx, 0, x.data_ptr()), "rebind x")
+        _lib.check(lib.dmc_plan_run(self.handle, _lib.stream_ptr()), "dmc_plan_run")
+        if cfg:
+            out_a.copy_(self.eps[:n])
+            out_b.copy_(self.eps[n:])
+        else:
+            out_a.copy_(self.eps)
+
+    def time_ops(self, iters=5):
+        n = self.lib.dmc_plan_num_ops(self.handle)
+        buf = (C.c_float * n)()
+        _lib.check(self.lib.dmc_plan_time_ops(self.handle, _lib.stream_ptr(), iters, buf, n), "dmc_plan_time_ops")
+        kinds = [_lib.OP_KINDS[self.lib.dmc_plan_op_kind(self.handle, i)] for i in range(n)]
+        flops = [self.lib.dmc_plan_op_flops(self.handle, i) for i in range(n)]
+        nbytes = [self.lib.dmc_plan_op_bytes(self.handle, i) for i in range(n)]
+        return [dict(name=self.op_names[i], kind=kinds[i], ms=buf[i], flops=flops[i], bytes=nbytes[i]) for i in range(n)]
+
+    def destroy(self):
+        if getattr(self, "handle", None) is not None:
+            self.lib.dmc_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -120,14 +120,15 @@ DMC_API int dmc_plan_num_launches(const dmc_plan* p);
 /* algorithmic tensor-core FLOPs (2*M*N*K summed over GEMM-shaped ops, real channels only) per run */
 DMC_API double dmc_plan_gemm_flops(const dmc_plan* p);
 /* Re-point one external binding of op `op_index` (returned by dmc_plan_add_*):
- *   which = 0: primary input  (stem: x, cond: t)     which = 1: secondary input (cond: y, may be NULL)
+ *   which = 0: primary input  (stem / patch_embed: x, cond / dit_cond: t)     which = 1: secondary input (cond: y, may be NULL)
  *   which = 2: primary output (conv: out_f32_nchw)                                                     */
 DMC_API int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr);
 /* Per-op device timing: runs every op `iters` times between CUDA events on `stream`, writes the average
  * milliseconds per op into ms_out[num ops].  Debug / profiling aid used by bench.py's roofline leg. */
 DMC_API int dmc_plan_time_ops(dmc_plan* p, void* stream, int32_t iters, float* ms_out, int32_t n_out);
 DMC_API int dmc_plan_num_ops(const dmc_plan* p);
-/* kind of op i: 0 memset, 1 cond, 2 stem, 3 gn_stats, 4 gn_apply, 5 conv, 6 attention, 7 upsample, 8 ddim, 9 ddpm */
+/* kind of op i: 0 memset, 1 cond, 2 stem, 3 gn_stats, 4 gn_apply, 5 conv, 6 attention, 7 upsample, 8 ddim, 9 ddpm,
+ * 10 dit_cond, 11 patch_embed, 12 ln_modulate */
 DMC_API int dmc_plan_op_kind(const dmc_plan* p, int32_t i);
 DMC_API double dmc_plan_op_flops(const dmc_plan* p, int32_t i);
 DMC_API double dmc_plan_op_bytes(const dmc_plan* p, int32_t i);
@@ -230,6 +231,17 @@ typedef struct {
   int32_t stats_slots;    /* must equal max(1, P/32) * (up_phase >= 0 ? 4 : 1), P = iteration pixels per image
                              (Hin/stride * Win/stride): one slot per 32-pixel epilogue warp, per phase */
   int32_t impl;           /* 0: tcgen05/TMA kernel (product path)   1: CUDA-core debug kernel (tests only, no stats) */
+  /* --- transformer (DiT) epilogues: v = acc + bias (+ cond); v = act(v); v *= gate[n, c]; v += residual; store --- */
+  int32_t act;                /* 0 none, 1 GELU (erf form, nn.GELU() default; models/dit.py:97) */
+  const float* gate;          /* per-image per-channel multiplier (adaLN gate, models/dit.py:124,130), row n at
+                                 gate + n * gate_stride; NULL = none */
+  int32_t gate_stride;        /* floats between images */
+  const float* residual_f32;  /* fp32 NHWC residual stream [B, Hout, Wout, Cout] or NULL (exclusive with `residual`) */
+  float* out_f32_nhwc;        /* fp32 NHWC output (may alias residual_f32: each element is read then written by the same
+                                 thread) or NULL */
+  int32_t unpatch_p;          /* > 0 with out_f32_nchw: columns are (pi, qi, c) of a p x p patch and pixel (i, j) of image n
+                                 scatters to out[n, c, i*p + pi, j*p + qi] -- DiT.unpatchify (models/dit.py:249-261);
+                                 Cout = p * p * channels */
 } dmc_conv_desc;
 DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
 
@@ -243,6 +255,60 @@ typedef struct {
                    flash kernel)   1: force the CUDA-core flash kernel (tests / debugging) */
 } dmc_attn_desc;
 DMC_API int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d);
+
+/* ---- DiT (models/dit.py) -------------------------------------------------------------------------------------- */
+
+/* Conditioning of every adaLN layer at once.  Replaces TimestepEmbedder (models/dit.py:42-55), the label lookup
+ * (:278-283) and the depth+1 adaLN_modulation linears (:106-109,115-116,142-147):
+ *   c_n   = W2 . SiLU(W1 . [cos(t_n f) | sin(t_n f)] + b1) + b2  (+ emb[clamp(y_n, 0, num_classes)])
+ *   mod_n = b_all + W_all . SiLU(c_n)              W_all: all adaLN_modulation.1 weights stacked, [ncols, hidden]
+ * With uniform_t (sampling: every t_n equal) only num_classes + 1 distinct rows exist; they are computed once and
+ * gathered per image. */
+typedef struct {
+  const int64_t* t;    /* [B] */
+  const int64_t* y;    /* [B] or NULL */
+  int32_t B, uniform_t, num_classes;
+  int32_t freq_dim;    /* 256 */
+  int32_t hidden, ncols;
+  const float* freqs;  /* [freq_dim / 2], the reference's expression evaluated on the host */
+  const float* w1;     /* [hidden, freq_dim]  t_embedder.mlp.0 */
+  const float* b1;
+  const float* w2;     /* [hidden, hidden]    t_embedder.mlp.2 */
+  const float* b2;
+  const float* emb;    /* [num_classes + 1, hidden] y_embedder.embedding_table.weight, or NULL */
+  const float* w_all;  /* [ncols, hidden] */
+  const float* b_all;  /* [ncols] */
+  float* scratch;      /* [R * (2 * hidden + ncols)], R = uniform_t ? (emb ? num_classes + 1 : 1) : B */
+  float* mod;          /* [B, ncols] */
+} dmc_dit_cond_desc;
+DMC_API int dmc_plan_add_dit_cond(dmc_plan* p, const dmc_dit_cond_desc* d);
+
+/* PatchEmbed + positional embedding (models/dit.py:23-27,265): non-overlapping p x p conv straight from the fp32 NCHW
+ * input to the fp32 token stream tok[n, i*Wt + j, :] = bias + W . patch(i, j) + pos[i*Wt + j, :]. Image n reads
+ * x[n % x_batch] (CFG: both halves of a 2B batch share x). */
+typedef struct {
+  const float* x;      /* [x_batch, Cin, H, W] */
+  int32_t x_batch, B, Cin, H, W, patch, hidden;
+  const float* weight; /* TRANSPOSED x_embedder.proj.weight: [Cin * patch * patch, hidden], k = (ci * patch + pi) * patch + qi */
+  const float* bias;   /* [hidden] */
+  const float* pos;    /* [(H/patch) * (W/patch), hidden] */
+  float* out;          /* fp32 [B, (H/patch) * (W/patch), hidden] */
+} dmc_patch_embed_desc;
+DMC_API int dmc_plan_add_patch_embed(dmc_plan* p, const dmc_patch_embed_desc* d);
+
+/* LayerNorm (no affine, eps) over the channel axis of the fp32 token stream, then adaLN modulation, written as the bf16
+ * GEMM operand: out[n, l, :] = LN(x[n, l, :]) * (1 + scale[n, :]) + shift[n, :]   (models/dit.py:119-120,127-128,148-149).
+ * shift / scale: row n at ptr + n * mod_stride (columns of the dmc_dit_cond table). */
+typedef struct {
+  const float* x;      /* fp32 [B, L, C] */
+  void* out;           /* bf16 [B, L, C] */
+  int32_t B, L, C;
+  const float* shift;
+  const float* scale;
+  int32_t mod_stride;
+  float eps;
+} dmc_ln_mod_desc;
+DMC_API int dmc_plan_add_ln_modulate(dmc_plan* p, const dmc_ln_mod_desc* d);
 
 /* nearest-neighbour 2x upsample of a bf16 NHWC tensor (models/unet.py:119) */
 typedef struct {
