@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="global batch (images per step)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="unet", choices=["unet", "dit"],
+                    help="unet: BASELINE configs[2] (the bench line); dit: configs[3] (DiT patch-2 DDIM-50 uncond, --batch 1024), "
+                         "a side measurement, not the headline")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--ref-sub-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,8 +193,8 @@ def main():
 
     from diffusion_models_collection_b200 import synth
     from diffusion_models_collection_b200.diffusion import DDIM
-    from diffusion_models_collection_b200.models import UNet
-    from diffusion_models_collection_b200.sharding import sharded_sample_with_cfg, shard_bounds
+    from diffusion_models_collection_b200.models import DiT, UNet
+    from diffusion_models_collection_b200.sharding import sharded_sample, sharded_sample_with_cfg, shard_bounds
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -199,8 +202,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    net = UNet(**synth.CIFAR_UNET, num_classes=10)
-    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    is_dit = args.model == "dit"
+    if is_dit:
+        net = DiT(**synth.CIFAR_DIT, num_classes=None)
+        net.load_state_dict(synth.make_dit_state_dict(None, None, seed=42))
+    else:
+        net = UNet(**synth.CIFAR_UNET, num_classes=10)
+        net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
     net = net.to(dev).eval()
     ddim = DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device=dev)
     ddim.progress = False
@@ -215,13 +223,18 @@ def main():
     shape = (B, 3, 32, 32)
 
     def step_resident():
+        if is_dit:
+            return sharded_sample(ddim, net, shape, None, noise=xT_dev, rank=rank, world=world)
         return sharded_sample_with_cfg(ddim, net, shape, y_dev, cfg_scale=3.0, noise=xT_dev, rank=rank, world=world)
 
     def step_e2e():
         # host -> device of this rank's slice of the inputs, device -> host of the gathered images
         yl = y_host[lo:hi].to(dev, non_blocking=True)
         xl = xT_host[lo:hi].to(dev, non_blocking=True)
-        out = sharded_sample_with_cfg(ddim, net, shape, yl, cfg_scale=3.0, noise=xl, rank=rank, world=world, sliced=True)
+        if is_dit:
+            out = sharded_sample(ddim, net, shape, None, noise=xl, rank=rank, world=world, sliced=True)
+        else:
+            out = sharded_sample_with_cfg(ddim, net, shape, yl, cfg_scale=3.0, noise=xl, rank=rank, world=world, sliced=True)
         return out.cpu() if rank == 0 else out[:1].cpu()
 
     def timed(fn, n):
@@ -252,7 +265,7 @@ def main():
     e2e_value = B * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
 
     # launches of OUR kernels in the timed region: per DDIM step, per chunk: one plan run + one fused scheduler kernel
-    launches = net.launches_per_forward(nb, cfg=True) * 50 * args.steps
+    launches = net.launches_per_forward(nb, cfg=not is_dit) * 50 * args.steps
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -261,12 +274,19 @@ def main():
                     "d2h_bytes_per_step": int(B * 3 * 32 * 32 * 4)},
             "gpu_launches": int(launches)}
     pk = peaks()
-    flops_step = 2 * 50 * FLOPS_PER_IMAGE_FORWARD * B  # 2 forwards per DDIM step (cond + uncond)
+    # 2 forwards per DDIM step (cond + uncond) for the CFG UNet workload, 1 for the unconditional DiT one
+    flops_step = (50 * 12.107e9 * B) if is_dit else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B)
     line["model_flops_utilization"] = {"achieved_tflops": flops_step * args.steps / (ms / 1e3) / 1e12 / world,
                                        "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
 
+    if is_dit:
+        line["metric"] = "ddim50_dit_cifar10_images_per_sec"
+        line["config"]["workload"] = ("DiT patch-2 (hidden 384, depth 12, 6 heads) 32x32 unconditional, DDIM-50 "
+                                      "(BASELINE.json configs[3]); side measurement, not the headline metric")
+        line["config"]["cfg_scale"] = None
     if rank == 0 and not args.no_roofline:
-        line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out)
+        line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out, cfg=not is_dit, step_ms=ms / args.steps / 50.0,
+                                        chunks=-(-nb // max(1, net.max_images_per_launch // (1 if is_dit else 2))))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
         line["cpu_baseline"] = cb
@@ -277,12 +297,30 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline_leg(net, dev, nb, pk, ops_out):
+def ncu_traffic(nimg):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/*_ncu_*.json written by
+    tools/summarize_ncu.py), if one exists for this launch size."""
+    import glob
+
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*forward_ncu*.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("images_per_launch") == nimg:
+            best = d
+    return best
+
+
+def roofline_leg(net, dev, nb, pk, ops_out, cfg=True, step_ms=None, chunks=1):
     """Per-op device times of ONE forward (CUDA events on the launching stream, each op timed alone -> burst peak),
-    aggregated per kernel family.  Dominant kernel: the tcgen05 implicit-GEMM convolution."""
-    nimg = min(2 * nb, net.max_images_per_launch)
+    aggregated per kernel family.  Dominant kernel: the tcgen05 implicit-GEMM convolution (all GEMM-shaped launches of
+    one forward, FLOP-weighted: achieved = sum of algorithmic FLOPs / sum of launch durations)."""
+    mult = 2 if cfg else 1
+    nimg = min(mult * nb, net.max_images_per_launch)
     with net.uniform_timesteps():  # what the sampling loop runs
-        plan = net.plan_info(nimg // 2, cfg=True, device=dev)
+        plan = net.plan_info(nimg // mult, cfg=cfg, device=dev)
     ops = plan.time_ops(iters=3)
     fam = {}
     for o in ops:
@@ -308,10 +346,24 @@ def roofline_leg(net, dev, nb, pk, ops_out):
     if ops_out:
         with open(ops_out, "w") as fh:
             json.dump({"images": nimg, "ops": ops, "families": per_family}, fh, indent=1)
-    return {"bound": "tensor", "kernel": "conv_umma_kernel (all conv launches of one forward, FLOP-weighted)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": pk["_source"] + " burst (ops timed alone)", "images_per_launch": nimg,
-            "forward_ms": total_ms, "per_family": per_family}
+    out = {"bound": "tensor", "kernel": "conv_umma_kernel (all conv / GEMM launches of one forward, FLOP-weighted)",
+           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+           "peak_source": pk["_source"] + " burst (ops timed alone)", "images_per_launch": nimg,
+           "launches_per_forward": conv["launches"], "flops_per_launch": conv["flops"] / max(1, conv["launches"]),
+           "forward_ms": total_ms, "per_family": per_family}
+    tr = ncu_traffic(nimg)
+    if tr is not None:
+        out["traffic"] = tr["dram_bytes_per_launch"]
+        out["traffic_algorithmic"] = tr["algorithmic_bytes_per_launch"]
+        out["traffic_source"] = "profiles/" + tr["source"]
+    if step_ms is not None:
+        # the same kernels inside the timed sampling loop (power-capped clocks): time of one denoising step of one chunk,
+        # apportioned by the per-family shares measured above -> fraction of the SUSTAINED peak
+        in_step_ms = step_ms / max(1, chunks) * (conv["ms"] / total_ms)
+        a = conv["flops"] / (in_step_ms / 1e3) / 1e12
+        out["in_step"] = {"achieved": a, "peak": pk["bf16_tflops_sustained"], "frac": a / pk["bf16_tflops_sustained"],
+                          "ms_per_forward": step_ms / max(1, chunks), "note": "step time x conv share of the per-op timing"}
+    return out
 
 
 if __name__ == "__main__":

@@ -59,31 +59,39 @@ struct ConvKParams {
   const float* residual_f32;  // fp32 NHWC residual stream
   float* out_f32;             // fp32 NHWC output
   int unpatch_p;              // > 0: out_nchw columns are (pi, qi, c) patch entries
+  // TMA-store epilogue: every epilogue warp stores its 32 rows x 64 channels as one box {64, qbw, qbh, qbn}
+  int tma_store;
+  int qbw, qbh;               // quarter box: qbw pixels x qbh rows x 32/(qbw*qbh) images
 };
 
 struct ConvPrepared {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
+  CUtensorMap tmOut;
   ConvKParams kp;
   int BN, MT, CG;
   int grid;
   size_t smem;
 };
 
+constexpr int CONV_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4..11 epilogue
+constexpr int EPI_THREADS = 256;
+
 template <int BN, int MT, int CG>
 struct ConvCfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
   static constexpr int B_STAGE_BYTES = (BN / CG) * KB * 2;  // a CTA pair splits the weight tile: N/2 rows each
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
-  static constexpr int NST = (216 * 1024) / STAGE_BYTES > 8 ? 8 : (216 * 1024) / STAGE_BYTES;
+  // epilogue staging for TMA stores: one 32-row x 64-channel bf16 box (4 KB, SWIZZLE_128B) per epilogue warp
+  static constexpr bool TMA_STORE = BN >= 128;
+  static constexpr int STORE_BYTES = TMA_STORE ? (EPI_THREADS / 32) * 4096 : 0;
+  static constexpr int RING_BYTES = 216 * 1024 - STORE_BYTES;
+  static constexpr int NST = RING_BYTES / STAGE_BYTES > 8 ? 8 : RING_BYTES / STAGE_BYTES;
   static constexpr int ACC_COLS = MT * BN;  // TMEM columns of one accumulator stage
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr size_t SMEM = static_cast<size_t>(NST) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = static_cast<size_t>(NST) * STAGE_BYTES + STORE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
 };
-
-constexpr int CONV_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4..11 epilogue
-constexpr int EPI_THREADS = 256;
 
 // Sums each of 8 per-lane values over the 32 lanes of the warp (full) or over each 16-lane half, with 9 (8) shuffles
 // instead of 40: every round halves the number of values a lane carries.  On return `r` is the total of value `idx`.
@@ -144,7 +152,7 @@ template <int BN, int MT, int CG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvKParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BN, MT, CG>;
   constexpr int NST = Cfg::NST;
   constexpr int MTG = MT * CG;  // 128-pixel tiles per CTA-group tile
@@ -152,7 +160,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
+  uint8_t* store_stage = smem + NST * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_BYTES);
   uint64_t* empty_bar = full_bar + NST;
   uint64_t* tfull_bar = empty_bar + NST;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -168,6 +177,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.nseg > 1) tma_prefetch_desc(&tmA1);
     if (p.nseg > 2) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (Cfg::TMA_STORE && p.tma_store) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -306,6 +316,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int ow = (tw * p.BW + wi) * p.oscale + p.ooff_w;
       const bool valid = n < p.B;
       const size_t pix = (static_cast<size_t>(n) * p.out_H + oh) * p.out_W + ow;
+      // TMA store: coordinates (iteration space) of the first row of this warp's 32-row quarter
+      const bool use_tma = Cfg::TMA_STORE && p.tma_store != 0;
+      const int r0 = q * 32;
+      const int sw0 = tw * p.BW + r0 % p.BW, sh0 = th * p.BH + (r0 / p.BW) % p.BH, sn0 = ti * p.BNIMG + r0 / ppi;
+      uint8_t* my_stage = store_stage + (warp - 4) * 4096;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -414,7 +429,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               }
             }
           }
-          if (valid && p.out != nullptr) {
+          if (use_tma) {
+            // stage this 32-column half of a 64-channel box in shared memory (row = lane, 128-byte rows, 16-byte chunks
+            // XOR-swizzled with the row index: conflict-free writes and the layout SWIZZLE_128B tensor maps expect)
+            const int half = (c0 >> 5) & 1;
+            if (half == 0) {  // the previous box of this warp must have been read out of the staging buffer
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+            uint8_t* rowp = my_stage + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = u;
+            }
+            if (half == 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, my_stage, cg - 32, sw0, sh0, sn0);  // clipped at the tensor bounds (n >= B)
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+          } else if (valid && p.out != nullptr) {
             uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -463,6 +504,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         else mbar_arrive(&tempty_bar[acc]);
       }
     }
+    // all TMA stores of this warp have left shared memory and are complete before the CTA exits
+    if (lane == 0 && Cfg::TMA_STORE && p.tma_store != 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -604,6 +647,28 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     cuuint32_t estr[2] = {1, 1};
     if (encode_map(&P->tmB, d.weight, 2, dims, strides, box, estr) != 0) { delete P; return -1; }
   }
+  P->tmOut = P->tmB;
+  kp.tma_store = 0;
+  {
+    const char* e = getenv("DMC_CONV_TMA_STORE");  // "0": per-thread stores everywhere (debug / A-B measurements)
+    const bool allow = !(e && e[0] == '0');
+    if (allow && d.out_bf16 != nullptr && d.Cout % 64 == 0 && BN >= 128) {
+      const int qbw = std::min(BW, 32), qbh = std::min(BH, 32 / qbw), qbn = 32 / (qbw * qbh);
+      const int os = kp.oscale;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.Cout), static_cast<cuuint64_t>(Wout), static_cast<cuuint64_t>(Hout),
+                            static_cast<cuuint64_t>(d.B)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(os) * d.Cout * 2, static_cast<cuuint64_t>(os) * kp.out_W * d.Cout * 2,
+                               static_cast<cuuint64_t>(kp.out_H) * kp.out_W * d.Cout * 2};
+      cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(qbw), static_cast<cuuint32_t>(qbh), static_cast<cuuint32_t>(qbn)};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const char* base = reinterpret_cast<const char*>(d.out_bf16) +
+                         (static_cast<size_t>(kp.ooff_h) * kp.out_W + kp.ooff_w) * d.Cout * 2;
+      if (encode_map(&P->tmOut, base, 4, dims, strides, box, estr) != 0) { delete P; return -1; }
+      kp.tma_store = 1;
+      kp.qbw = qbw;
+      kp.qbh = qbh;
+    }
+  }
   kp.Cout = d.Cout;
   kp.bias = d.bias; kp.cond = d.cond; kp.cond_stride = d.cond_stride;
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
@@ -659,7 +724,7 @@ static int launch_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DMC_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MT, CG>, P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, kp));
+  DMC_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MT, CG>, P->tmA[0], P->tmA[1], P->tmA[2], P->tmB, P->tmOut, kp));
   return 0;
 }
 

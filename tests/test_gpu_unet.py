@@ -181,3 +181,22 @@ def test_cuda_graph_loop_is_bit_identical_to_the_launch_loop(kind, monkeypatch):
     assert getattr(outs[1][1], "_graph_cache", None) is not None
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][0], outs[2][0])
+
+
+def test_full_size_batch_chunking_and_sharding_property():
+    """BASELINE configs[2] scale (thousands of images, several 2048-image launches per step): an image's trajectory does
+    not depend on which chunk / shard it is denoised in -- rows of the big run equal the same rows sampled alone"""
+    from diffusion_models_collection_b200.diffusion import DDIM
+
+    net = build_unet(synth.CIFAR_UNET, 10, 2)
+    B = 2304  # 1024 + 1024 + 256 images per CFG forward
+    g = torch.Generator().manual_seed(7)
+    xT = torch.randn(B, 3, 32, 32, generator=g).cuda()
+    y = (torch.randint(0, 10, (B,), generator=g) + 1).cuda()
+    d = DDIM(1000, 2, device="cuda")
+    d.progress = False
+    big = d.sample_with_cfg(net, (B, 3, 32, 32), y, cfg_scale=3.0, noise=xT)
+    assert torch.isfinite(big).all()
+    for lo, hi in ((0, 8), (1020, 1030), (2296, 2304)):  # inside a chunk, across a chunk boundary, the ragged tail
+        part = d.sample_with_cfg(net, (hi - lo, 3, 32, 32), y[lo:hi], cfg_scale=3.0, noise=xT[lo:hi])
+        assert torch.equal(big[lo:hi], part), (lo, hi)

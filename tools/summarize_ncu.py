@@ -60,6 +60,16 @@ def main(metrics_csv, table_json, out_md, title):
                      f"{f['dram']/max(f['alg'],1):.2f} | {f['dram']/f['ns']:.0f} | {f['flops']/f['ns']/1e3:.0f} | {f['tens']/f['ns']:.1f} |\n")
         fh.write("\n## Per launch\n\n| op | layer | kernel | us | share % | DRAM MB | algorithmic MB | DRAM/alg | DRAM GB/s | TFLOP/s | tensor % | L2 GB/s |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         fh.write("\n".join(lines) + "\n")
+    # machine-readable DRAM traffic per launch of the dominant kernel family (bench.py's roofline.traffic)
+    conv = [f for k, f in fam.items() if k.startswith("conv_umma_kernel")]
+    if conv:
+        n = sum(f["n"] for f in conv)
+        js = dict(images_per_launch=table["images"], kernel="conv_umma_kernel", launches=n,
+                  dram_bytes_per_launch=sum(f["dram"] for f in conv) / n,
+                  algorithmic_bytes_per_launch=sum(f["alg"] for f in conv) / n,
+                  tensor_pipe_active_pct=sum(f["tens"] for f in conv) / sum(f["ns"] for f in conv),
+                  source=out_md.split("/")[-1])
+        json.dump(js, open(out_md.replace(".md", ".json"), "w"), indent=1)
     print("wrote", out_md)
 
 
