@@ -12,7 +12,8 @@ import os
 import threading
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdmc_b200.so")
+# DMC_LIB: an alternative build of the same ABI (A/B measurements of kernel variants only; symbols it lacks are skipped)
+LIB_PATH = os.environ.get("DMC_LIB") or os.path.join(PKG, "libdmc_b200.so")
 
 
 class DmcError(RuntimeError):
@@ -159,6 +160,8 @@ def load(require_device: bool = True):
             for name, (res, args) in SYMBOLS.items():
                 fn = getattr(lib, name, None)
                 if fn is None:
+                    if os.environ.get("DMC_LIB"):
+                        continue
                     raise DmcError(f"{LIB_PATH} does not export {name}")
                 fn.restype, fn.argtypes = res, args
             if lib.dmc_abi_version() != 1:

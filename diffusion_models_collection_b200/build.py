@@ -21,7 +21,9 @@ ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdmc_b200.so")
 OBJ = os.path.join(PKG, "csrc", "_build")
 
-SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu", "dit_ops.cu"]
+SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu", "dit_ops.cu",
+           "conv_inst_256_1_2.cu", "conv_inst_128_2_2.cu", "conv_inst_256_1_1.cu", "conv_inst_128_2_1.cu", "conv_inst_128_1_1.cu",
+           "conv_inst_64_1_1.cu", "conv_inst_32_1_1.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -69,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,8 @@
+// kernel variants of the tcgen05 convolution for the tile configuration BN=128, MT=2, CG=2 (see conv_umma_kernel.cuh)
+#include "conv_umma_kernel.cuh"
+
+namespace dmc {
+int launch_conv_128_2_2(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
+  return launch_tile_cfg<128, 2, 2>(P, kp, st);
+}
+}  // namespace dmc

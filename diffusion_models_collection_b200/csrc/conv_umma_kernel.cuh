@@ -1,0 +1,744 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_umma.cu for the description): parameter block, tile configuration,
+// the kernel template and its launcher.  Included by conv_umma.cu (host side) and by the conv_inst_*.cu translation
+// units, each of which instantiates the kernel variants of ONE tile configuration (parallel, bounded compile times).
+#pragma once
+
+#include "common.cuh"
+#include "kernels.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace dmc {
+
+
+constexpr int TILE_M = 128;
+constexpr int KB = 64;  // K elements per block = 128 bytes of bf16 = one swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * KB * 2;
+
+struct ConvKParams {
+  int nseg;
+  int seg_taps[3];
+  int seg_chunks[3];
+  int seg_kb_end[3];  // cumulative K-block count
+  signed char dh[3][9];
+  signed char dw[3][9];
+  int stride;
+  int BW, BH, BNIMG;
+  int tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles, num_kb;
+  int B, Hout, Wout;     // iteration space (output pixels per image = Hout*Wout)
+  int out_H, out_W;      // stored output tensor spatial dims
+  int oscale, ooff_h, ooff_w;
+  int Cout;
+  const float* bias;
+  const float* cond;
+  int cond_stride;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  float* out_nchw;
+  float* stats;
+  int stats_slots, stats_slot_base;
+  // transformer epilogues (DiT)
+  int act;                    // 1: GELU
+  const float* gate;          // per-image per-channel multiplier
+  int gate_stride;
+  const float* residual_f32;  // fp32 NHWC residual stream
+  float* out_f32;             // fp32 NHWC output
+  int unpatch_p;              // > 0: out_nchw columns are (pi, qi, c) patch entries
+  // TMA-store epilogue: every epilogue warp stores its 32 rows x 64 channels as one box {64, qbw, qbh, qbn}
+  int tma_store;
+  int qbw, qbh;               // quarter box: qbw pixels x qbh rows x 32/(qbw*qbh) images
+  int store_bufs;             // staging buffers per epilogue warp (1 or 2)
+  int res_tma;                // the residual (bf16 or fp32 stream) is fetched as TMA boxes into the staging buffer
+  // shared-memory plan (host computed): [resident weights][ring: nst stages][store staging][barriers]
+  int nst, stage_bytes, a_bytes, b_region_bytes;
+  int bres;                   // weights of the whole K extent stay resident (short-K GEMMs: 1x1 convs, transformer linears)
+  int slab, slab_bytes;       // 3x3 segment 0 is loaded as row slabs shared by the three vertical taps
+};
+
+constexpr int MAX_NST = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+
+struct ConvPrepared {
+  CUtensorMap tmA[3];
+  CUtensorMap tmS;
+  CUtensorMap tmB;
+  CUtensorMap tmOut;
+  CUtensorMap tmRes;
+  ConvKParams kp;
+  int BN, MT, CG;
+  int var;  // kernel variant (VAR_* bits)
+  int grid;
+  size_t smem;
+};
+
+constexpr int CONV_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4..11 epilogue
+constexpr int EPI_THREADS = 256;
+
+template <int BN, int MT, int CG>
+struct ConvCfg {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * KB * 2;  // a CTA pair splits the weight tile: N/2 rows each
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  // epilogue staging for TMA stores: one 32-row x 64-channel bf16 box (4 KB, SWIZZLE_128B) per epilogue warp
+  static constexpr bool TMA_STORE = BN >= 128;
+  static constexpr int STORE_BYTES = (EPI_THREADS / 32) * 4096;
+  static constexpr int ACC_COLS = MT * BN;  // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+};
+
+// Sums each of 8 per-lane values over the 32 lanes of the warp (full) or over each 16-lane half, with 9 (8) shuffles
+// instead of 40: every round halves the number of values a lane carries.  On return `r` is the total of value `idx`.
+__device__ __forceinline__ void reduce8(const float (&v)[8], bool full, int lane, float& r, int& idx) {
+  float w[4];
+  int base;
+  if (full) {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, hi ? v[i] : v[4 + i], 16);
+      w[i] = (hi ? v[4 + i] : v[i]) + recv;
+    }
+    base = hi ? 4 : 0;
+    const bool h8 = (lane & 8) != 0;
+    float u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h8 ? w[i] : w[2 + i], 8);
+      u[i] = (h8 ? w[2 + i] : w[i]) + recv;
+    }
+    base += h8 ? 2 : 0;
+    const bool h4 = (lane & 4) != 0;
+    const float recv = __shfl_xor_sync(0xFFFFFFFFu, h4 ? u[0] : u[1], 4);
+    float t = (h4 ? u[1] : u[0]) + recv;
+    base += h4 ? 1 : 0;
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 2);
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+    r = t;
+    idx = base;
+  } else {
+    const bool h8 = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h8 ? v[i] : v[4 + i], 8);
+      w[i] = (h8 ? v[4 + i] : v[i]) + recv;
+    }
+    base = h8 ? 4 : 0;
+    const bool h4 = (lane & 4) != 0;
+    float u[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, h4 ? w[i] : w[2 + i], 4);
+      u[i] = (h4 ? w[2 + i] : w[i]) + recv;
+    }
+    base += h4 ? 2 : 0;
+    const bool h2 = (lane & 2) != 0;
+    const float recv = __shfl_xor_sync(0xFFFFFFFFu, h2 ? u[0] : u[1], 2);
+    float t = (h2 ? u[1] : u[0]) + recv;
+    base += h2 ? 1 : 0;
+    t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+    r = t;
+    idx = base;
+  }
+}
+
+// VAR (compile-time kernel variant, so that each instantiation carries only the code it runs -- the all-in-one kernel was
+// 107 KB of SASS and lost 8 % to instruction fetch):
+//   bit 0 SLAB   3x3 segment 0 loaded as row slabs shared by the three vertical taps
+//   bit 1 BRES   weights of the whole K extent resident in shared memory (short-K GEMMs)
+//   bit 2 TS     TMA-store epilogue (BN >= 128 only)
+//   bits 3.. EPI 0: UNet convolution (bias, conditioning, bf16 residual, bf16 NHWC out, GroupNorm partial sums)
+//                1: transformer linear, bf16 NHWC out (bias, GELU)
+//                2: model head (bias, fp32 NCHW out, optional unpatchify)
+//                3: transformer linear on the fp32 residual stream (bias, gate, fp32 residual, fp32 NHWC out)
+constexpr int VAR_SLAB = 1, VAR_BRES = 2, VAR_TS = 4, VAR_EPI_SHIFT = 3;
+
+template <int BN, int MT, int CG, int VAR>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BN, MT, CG>;
+  constexpr bool SLAB = (VAR & VAR_SLAB) != 0;
+  constexpr bool BRES = (VAR & VAR_BRES) != 0;
+  constexpr bool TS = (VAR & VAR_TS) != 0 && Cfg::TMA_STORE;
+  constexpr int EPI = VAR >> VAR_EPI_SHIFT;
+  constexpr int MTG = MT * CG;  // 128-pixel tiles per CTA-group tile
+  constexpr int B_TILE = Cfg::B_STAGE_BYTES;
+  const int NST = p.nst;
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  extern __shared__ uint8_t smem_raw[];
+  // [resident weights (bres)] [ring: nst x stage_bytes] [TMA-store staging] [barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = smem + p.b_region_bytes;
+  uint8_t* store_stage = ring + NST * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + (TS ? Cfg::STORE_BYTES * p.store_bufs : 0));
+  uint64_t* empty_bar = full_bar + MAX_NST;
+  uint64_t* tfull_bar = empty_bar + MAX_NST;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bfull_bar = tempty_bar + 2;   // resident weights loaded
+  uint64_t* rbar = bfull_bar + 1;         // residual boxes: [epilogue warp][staging buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * (EPI_THREADS / 32));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_ct = (p.num_m_tiles + MTG - 1) / MTG;  // group tiles along M (MTG consecutive 128-pixel tiles each)
+  const int num_tiles = num_ct * p.num_n_tiles;
+  // Tile schedule: strided over the CTA groups, n fastest -- groups running side by side work on the same pixels, so
+  // the A tile comes from HBM once and from L2 for the other n tiles.  With resident weights a group keeps ONE n tile
+  // for its whole life (n_tile = group % num_n_tiles, loaded once) and strides over the M tiles with the groups that
+  // share its n; the (num_groups % num_n_tiles) left-over groups stay idle.
+  constexpr bool bres = BRES;
+  const int lanes = num_groups / p.num_n_tiles;  // groups per n tile (BRES)
+  const bool bres_idle = bres && group >= lanes * p.num_n_tiles;
+  const int t_begin = bres ? (bres_idle ? num_ct : group / p.num_n_tiles) : group;
+  const int t_end = bres ? num_ct : num_tiles;
+  const int t_step = bres ? lanes : num_groups;
+#define DMC_DECODE_TILE(tile, n_tile, ct)                                   \
+  const int n_tile = bres ? group % p.num_n_tiles : (tile) % p.num_n_tiles; \
+  const int ct = bres ? (tile) : (tile) / p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.nseg > 1) tma_prefetch_desc(&tmA1);
+    if (p.nseg > 2) tma_prefetch_desc(&tmA2);
+    if (SLAB) tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmB);
+    if (TS) tma_prefetch_desc(&tmOut);
+    if (TS && p.res_tma) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], CG * (EPI_THREADS / 32));  // one arrival per epilogue warp (of both CTAs of a pair)
+    }
+    mbar_init(bfull_bar, 1);
+    for (int i = 0; i < 2 * (EPI_THREADS / 32); ++i) mbar_init(&rbar[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // K loop of one tile as "steps" (one ring stage each):
+  //   slab step (3x3 segment 0 when p.slab): ONE box of (MT*BH + 2) image rows x BW pixels x 64 channels shifted by dw
+  //     serves the three vertical taps dh = -1, 0, +1 of MT vertically adjacent sub-tiles (sub-tile mt, tap dh reads rows
+  //     [mt*BH + dh + 1, +BH) of the box: a 1024-byte aligned offset) -> the activations cross L2->SM 3x instead of 9x;
+  //   regular step: MT boxes of 128 pixels x 64 channels for one (tap, chunk) K block.
+  const int slab_steps = SLAB ? 3 * p.seg_chunks[0] : 0;
+  const int reg_kb0 = SLAB ? p.seg_kb_end[0] : 0;            // first K block handled by regular steps
+  const int num_steps = slab_steps + (p.num_kb - reg_kb0);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t phase = 0;
+      int cur_n = -1, stage = 0;
+      const uint32_t bfull_cl = (CG == 2) ? mapa_shared(smem_u32(bfull_bar), 0) : 0;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        DMC_DECODE_TILE(tile, n_tile, ct)
+        if (bres && cur_n < 0) {  // the weight tile of this group: every K block, once
+          if (rank == 0) mbar_expect_tx(bfull_bar, static_cast<uint32_t>(CG) * p.num_kb * B_TILE);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            if (CG == 2) tma_load_2d_cg2(smem + kb * B_TILE, &tmB, bfull_cl, kb * KB, n_tile * BN + rank * (BN / 2));
+            else tma_load_2d(smem + kb * B_TILE, &tmB, bfull_bar, kb * KB, n_tile * BN);
+          }
+          cur_n = n_tile;
+        }
+        int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m_tile = ct * MTG + rank * MT + mt;  // may be past the end: its box is fully out of bounds -> zero fill
+          w0[mt] = (m_tile % p.tiles_w) * p.BW * p.stride;
+          h0[mt] = ((m_tile / p.tiles_w) % p.tiles_h) * p.BH * p.stride;
+          n0[mt] = (m_tile / (p.tiles_w * p.tiles_h)) * p.BNIMG;
+        }
+        int seg = SLAB ? 1 : 0, kb_in_seg = 0;
+        for (int step = 0; step < num_steps; ++step) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = ring + stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          const uint32_t lbar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0;
+          if (SLAB && step < slab_steps) {
+            const int chunk = step / 3, dwi = step % 3;
+            // the leader's barrier counts the bytes of BOTH CTAs of a pair (the MMAs it issues read both)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (p.slab_bytes + (bres ? 0 : 3 * B_TILE)));
+            if (CG == 2) tma_load_4d_cg2(sa, &tmS, lbar, chunk * KB, w0[0] + dwi - 1, h0[0] - 1, n0[0]);
+            else tma_load_4d(sa, &tmS, &full_bar[stage], chunk * KB, w0[0] + dwi - 1, h0[0] - 1, n0[0]);
+            if (!bres) {
+#pragma unroll
+              for (int dhi = 0; dhi < 3; ++dhi) {
+                const int kb = (dhi * 3 + dwi) * p.seg_chunks[0] + chunk;
+                if (CG == 2) tma_load_2d_cg2(sb + dhi * B_TILE, &tmB, lbar, kb * KB, n_tile * BN + rank * (BN / 2));
+                else tma_load_2d(sb + dhi * B_TILE, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+              }
+            }
+          } else {
+            const int kb = reg_kb0 + (step - slab_steps);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (Cfg::A_BYTES + (bres ? 0 : B_TILE)));
+            const int chunks = p.seg_chunks[seg];
+            const int tap = kb_in_seg / chunks, chunk = kb_in_seg % chunks;
+            const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+            if (CG == 2) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                tma_load_4d_cg2(sa + mt * A_STAGE_BYTES, tm, lbar, chunk * KB, w0[mt] + p.dw[seg][tap],
+                                h0[mt] + p.dh[seg][tap], n0[mt]);
+              if (!bres) tma_load_2d_cg2(sb, &tmB, lbar, kb * KB, n_tile * BN + rank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &full_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
+                            h0[mt] + p.dh[seg][tap], n0[mt]);
+              if (!bres) tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+            }
+            if (++kb_in_seg == p.seg_taps[seg] * chunks) {
+              ++seg;
+              kb_in_seg = 0;
+            }
+          }
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M * CG, BN);
+      uint32_t local = 0, phase = 0;
+      int cur_n = -1, stage = 0;
+      const uint32_t bres_addr = smem_u32(smem);
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++local) {
+        DMC_DECODE_TILE(tile, n_tile, ct)
+        (void)ct;
+        const uint32_t acc = local & 1u;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        if (bres && cur_n < 0) {
+          mbar_wait(bfull_bar, 0u);
+          cur_n = n_tile;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        uint32_t accum = 0;
+        for (int step = 0; step < num_steps; ++step) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
+          const uint32_t sb = sa + p.a_bytes;
+          if (SLAB && step < slab_steps) {
+            const int chunk = step / 3, dwi = step % 3;
+#pragma unroll
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const int kb = (dhi * 3 + dwi) * p.seg_chunks[0] + chunk;
+              const uint64_t bdesc = umma_desc_k_sw128(bres ? bres_addr + kb * B_TILE : sb + dhi * B_TILE);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t adesc = umma_desc_k_sw128(sa + ((mt * p.BH + dhi) * p.BW) * 128);
+#pragma unroll
+                for (int k = 0; k < KB / 16; ++k) {
+                  if (CG == 2) umma_bf16_cg2(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | dhi | k) != 0 ? 1u : 0u);
+                  else umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | dhi | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          } else {
+            const int kb = reg_kb0 + (step - slab_steps);
+            const uint64_t bdesc = umma_desc_k_sw128(bres ? bres_addr + kb * B_TILE : sb);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t adesc = umma_desc_k_sw128(sa + mt * A_STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < KB / 16; ++k) {
+                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                if (CG == 2) umma_bf16_cg2(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          accum = 1;
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) umma_commit_cg2(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        // accumulators complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_cg2(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    // warp -> TMEM lane quarter q (= warp % 4, the hardware rule) and group grp: with MT == 2 the group is the
+    // 128-pixel sub-tile, with MT == 1 it is the half of the BN output channels this warp converts.
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row = q * 32 + lane;      // tile row == TMEM lane
+    const int ppi = p.BW * p.BH;        // pixels per image inside one 128-pixel tile
+    constexpr int COLS = (MT == 2) ? BN : (BN >= 64 ? BN / 2 : BN);
+    const int col0 = (MT == 2) ? 0 : (BN >= 64 ? grp * COLS : 0);
+    const bool idle = (MT == 1 && BN < 64 && grp == 1);
+    const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / ppi;
+    constexpr int BOXC = (EPI == 3) ? 32 : 64;  // channels per TMA box: 128-byte rows of fp32 / bf16
+    uint32_t local = 0, boxi = 0, rphase = 0;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++local) {
+      const uint32_t acc = local & 1u;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      DMC_DECODE_TILE(tile, n_tile, ct)
+      const int m_tile = ct * MTG + rank * MT + (MT == 2 ? grp : 0);
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int ti = m_tile / (p.tiles_w * p.tiles_h);
+      const int n = ti * p.BNIMG + ni;
+      const int oh = (th * p.BH + hi) * p.oscale + p.ooff_h;
+      const int ow = (tw * p.BW + wi) * p.oscale + p.ooff_w;
+      const bool valid = n < p.B;
+      const size_t pix = (static_cast<size_t>(n) * p.out_H + oh) * p.out_W + ow;
+      // TMA store: coordinates (iteration space) of the first row of this warp's 32-row quarter
+      const int r0 = q * 32;
+      const int sw0 = tw * p.BW + r0 % p.BW, sh0 = th * p.BH + (r0 / p.BW) % p.BH, sn0 = ti * p.BNIMG + r0 / ppi;
+      uint8_t* my_stage = store_stage + (warp - 4) * 4096 * p.store_bufs;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS +
+                             (MT == 2 ? grp * BN : 0) + col0;
+      if (!idle) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          const int cg = n_tile * BN + col0 + c0;  // first global output channel of this chunk
+          const bool real = cg < p.Cout;           // false only for padded weight rows (warp-uniform)
+          // ---- TMA epilogue I/O: a "box" is this warp's 32 rows x BOXC channels (128-byte rows in shared memory) ----
+          const bool box_start = TS && (c0 % BOXC) == 0;
+          const bool box_end = TS && ((c0 + 32) % BOXC) == 0;
+          const uint32_t bi = (TS && p.store_bufs == 2) ? (boxi & 1u) : 0u;  // staging buffer of this box
+          uint8_t* stg = my_stage + bi * 4096u;
+          uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
+          const bool res_tma = TS && (EPI == 0 || EPI == 3) && p.res_tma != 0;
+          if (box_start && real) {
+            if (lane == 0) {
+              // the staging buffer is free once the TMA store issued from it has read it out of shared memory
+              if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (res_tma) {  // residual box: coalesced, asynchronous, lands in the staging buffer
+                mbar_expect_tx(rb, 4096);
+                tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+              }
+            }
+            __syncwarp();
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          // per-channel addends (warp-uniform addresses -> L1 broadcast), fetched while the TMEM load is in flight
+          float add[32];
+          if (EPI != 2 && real) {
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) add[j] = 0.f;
+            }
+            if (EPI == 0 && p.cond != nullptr && valid) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(c4 + j);
+                add[4 * j] += b.x; add[4 * j + 1] += b.y; add[4 * j + 2] += b.z; add[4 * j + 3] += b.w;
+              }
+            }
+          }
+          uint4 res[4];
+          const bool has_res = EPI == 0 && p.residual != nullptr && valid && real;
+          if (has_res && !res_tma) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = __ldg(r4 + j);
+          }
+          tmem_ld_wait();
+          if (!real) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (EPI == 2) {
+            // model head: few real channels, fp32 NCHW, coalesced along W across the warp
+            if (valid) {
+              const int up = p.unpatch_p;
+              const int oc = up > 0 ? p.Cout / (up * up) : p.Cout;  // image channels
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = cg + j;
+                if (c < p.Cout) {
+                  float o = v[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
+                  if (up > 0) {  // DiT.unpatchify: column = (pi * up + qi) * oc + ch
+                    const int ch = c % oc, pq = c / oc;
+                    const int yy = oh * up + pq / up, xx = ow * up + pq % up;
+                    p.out_nchw[((static_cast<size_t>(n) * oc + ch) * (p.out_H * up) + yy) * (p.out_W * up) + xx] = o;
+                  } else {
+                    p.out_nchw[((static_cast<size_t>(n) * p.Cout + c) * p.out_H + oh) * p.out_W + ow] = o;
+                  }
+                }
+              }
+            }
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += add[j];
+          if (EPI == 1 && p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          }
+          if (EPI == 3 && p.gate != nullptr && valid) {
+            const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(n) * p.gate_stride + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 gv = __ldg(g4 + j);
+              v[4 * j] *= gv.x; v[4 * j + 1] *= gv.y; v[4 * j + 2] *= gv.z; v[4 * j + 3] *= gv.w;
+            }
+          }
+          // ---- residual ----
+          if (res_tma) {
+            if (box_start) {  // (uniform per warp) the residual box of this staging buffer has landed
+              mbar_wait(rb, (rphase >> bi) & 1u);
+              rphase ^= 1u << bi;
+            }
+            const uint8_t* rowp = stg + lane * 128;
+            if (EPI == 3) {  // fp32 row: 8 chunks of 4 floats
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rv = *reinterpret_cast<const float4*>(rowp + ((j ^ (lane & 7)) << 4));
+                v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+              }
+            } else {  // bf16 row: this 32-channel half = 4 chunks of 8
+              const int half = (c0 >> 5) & 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4));
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_bf16x2(w[k]);
+                  v[8 * j + 2 * k] += f.x;
+                  v[8 * j + 2 * k + 1] += f.y;
+                }
+              }
+            }
+          } else {
+            if (EPI == 3 && p.residual_f32 != nullptr && valid) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.residual_f32 + pix * p.Cout + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rv = r4[j];  // plain load: out_f32 may alias the residual stream
+                v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = unpack_bf16x2(w[k]);
+                  v[8 * j + 2 * k] += f.x;
+                  v[8 * j + 2 * k + 1] += f.y;
+                }
+              }
+            }
+          }
+          // ---- output ----
+          if (TS) {
+            // row = lane, 128-byte rows, 16-byte chunks XOR-swizzled with the row index: conflict-free shared-memory
+            // accesses and the layout SWIZZLE_128B tensor maps expect
+            uint8_t* rowp = stg + lane * 128;
+            if (EPI == 3) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              const int half = (c0 >> 5) & 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = u;
+              }
+            }
+            if (box_end) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, stg, cg + 32 - BOXC, sw0, sh0, sn0);  // clipped at the tensor bounds (n >= B)
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++boxi;
+            }
+          } else if (EPI == 3) {
+            if (p.out_f32 != nullptr && valid) {
+              float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else if (valid && p.out != nullptr) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o4[j] = u;
+            }
+          }
+          if (EPI == 0 && p.stats != nullptr) {
+            // GroupNorm partial sums of the OUTPUT per (image, 8-channel block) over the rows of this warp that belong
+            // to one image (all 32 when ppi >= 32, else each 16-lane half), stored in this warp's own slot: plain
+            // stores, no atomics -> deterministic and batch-invariant; the consumer adds the slots in index order.
+            float sv[8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float s = 0.f, ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s += v[8 * b + j];
+                ss = fmaf(v[8 * b + j], v[8 * b + j], ss);
+              }
+              sv[b] = valid ? s : 0.f;
+              sv[4 + b] = valid ? ss : 0.f;
+            }
+            const bool full = ppi >= 32;
+            float tot;
+            int idx;
+            reduce8(sv, full, lane, tot, idx);
+            const bool writer = full ? ((lane & 3) == 0) : ((lane & 1) == 0);
+            if (writer && valid) {
+              const int wpi = ppi >> 5;  // epilogue warps per image inside one tile (0: an image is a half-warp)
+              const int slot = p.stats_slot_base + (full ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
+              float* dst = p.stats + ((static_cast<size_t>(n) * p.stats_slots + slot) * (p.Cout >> 3) + ((cg >> 3) + (idx & 3))) * 2;
+              dst[idx >> 2] = tot;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {  // one arrival per warp, on the leader's barrier (its MMA warp reuses the accumulator stage)
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+    // all TMA stores of this warp have left shared memory and are complete before the CTA exits
+    if (lane == 0 && TS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (warp == 2) {
+    tc_fence_after();
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+#undef DMC_DECODE_TILE
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch: one translation unit per tile configuration (conv_inst_*.cu) instantiates the variants it can run
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MT, int CG, int VAR>
+static int launch_variant(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MT, CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(P->grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = P->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DMC_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MT, CG, VAR>, P->tmA[0], P->tmA[1], P->tmA[2], P->tmS, P->tmB,
+                                 P->tmOut, P->tmRes, kp));
+  return 0;
+}
+
+// The variants conv_prepare() can select (see conv_variant_supported): the TMA store needs BN >= 128; resident weights and
+// slabs are exclusive (slabs are for 3x3 K extents, resident weights for at most 8 K blocks); transformer linears are
+// never 3x3; the head writes fp32 NCHW with per-thread stores.
+template <int BN, int MT, int CG>
+static int launch_tile_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
+  constexpr bool TSOK = ConvCfg<BN, MT, CG>::TMA_STORE;
+  switch (P->var) {
+#define DMC_V(v) case (v): return launch_variant<BN, MT, CG, (v)>(P, kp, st)
+    DMC_V(0);
+    DMC_V(VAR_SLAB);
+    DMC_V(VAR_BRES);
+    DMC_V(1 << VAR_EPI_SHIFT);
+    DMC_V((1 << VAR_EPI_SHIFT) | VAR_BRES);
+    DMC_V(2 << VAR_EPI_SHIFT);
+    DMC_V((2 << VAR_EPI_SHIFT) | VAR_SLAB);
+    DMC_V(3 << VAR_EPI_SHIFT);
+    DMC_V((3 << VAR_EPI_SHIFT) | VAR_BRES);
+#undef DMC_V
+    default: break;
+  }
+  if constexpr (TSOK) {
+    switch (P->var) {
+#define DMC_V(v) case (v): return launch_variant<BN, MT, CG, (v)>(P, kp, st)
+      DMC_V(VAR_TS);
+      DMC_V(VAR_TS | VAR_SLAB);
+      DMC_V(VAR_TS | VAR_BRES);
+      DMC_V((1 << VAR_EPI_SHIFT) | VAR_TS);
+      DMC_V((1 << VAR_EPI_SHIFT) | VAR_TS | VAR_BRES);
+      DMC_V((3 << VAR_EPI_SHIFT) | VAR_TS);
+      DMC_V((3 << VAR_EPI_SHIFT) | VAR_TS | VAR_BRES);
+#undef DMC_V
+      default: break;
+    }
+  }
+  set_error("conv: kernel variant %d is not built for tile configuration (%d, %d, %d)", P->var, BN, MT, CG);
+  return -1;
+}
+
+}  // namespace dmc

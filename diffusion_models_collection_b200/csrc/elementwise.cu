@@ -348,9 +348,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
     const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
     const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
+    const float fold = a.silu ? 0.5f : 1.0f;  // SiLU(y) = h + h tanh(h), h = y / 2: fold the 1/2 into scale and shift
     for (int j = 0; j < 8; ++j) {
-      sc[j] = rstd * gam[j];
-      sh[j] = bet[j] - mean * sc[j];
+      const float s1 = rstd * gam[j];
+      sc[j] = fold * s1;
+      sh[j] = fold * (bet[j] - mean * s1);
     }
   }
   const bool first = cb < a.C0_8;
@@ -379,8 +381,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
           float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
           float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
           if (a.silu) {
-            y0 = silu_f(y0);
-            y1 = silu_f(y1);
+            y0 = silu_from_half(y0);
+            y1 = silu_from_half(y1);
           }
           o[j] = pack_bf16x2(y0, y1);
         }

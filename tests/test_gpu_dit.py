@@ -131,8 +131,16 @@ def _gemm_desc(src, w, bias, cout):
     return d, wq
 
 
+FORCE = [{}, {"DMC_CONV_CG": "2"}, {"DMC_CONV_CG": "2", "DMC_CONV_STORE_BUFS": "1"}, {"DMC_CONV_CG": "2", "DMC_CONV_BRES": "0"},
+         {"DMC_CONV_CG": "2", "DMC_CONV_RES_TMA": "0"}, {"DMC_CONV_CG": "2", "DMC_CONV_TMA_STORE": "0"}]
+FORCE_IDS = ["default", "pairs", "pairs-1buf", "pairs-nobres", "pairs-noresTMA", "pairs-noTS"]
+
+
+@pytest.mark.parametrize("force", FORCE, ids=FORCE_IDS)
 @pytest.mark.parametrize("cin,cout,Ht,B", [(384, 1536, 16, 2), (384, 1152, 16, 1), (128, 256, 4, 3), (768, 3072, 8, 1)])
-def test_gemm_gelu_epilogue(cin, cout, Ht, B):
+def test_gemm_gelu_epilogue(cin, cout, Ht, B, force, monkeypatch):
+    for k, v in force.items():  # small test GEMMs would otherwise run the BN = 32 fallback tile: force the big-tile variants
+        monkeypatch.setenv(k, v)
     x = _rand((B, Ht, Ht, cin), 1).to(torch.bfloat16)
     w, bias = _rand((cout, cin), 2, cin ** -0.5).to(torch.bfloat16).float(), _rand((cout,), 3, 0.2)
     ref = F.gelu(F.linear(x.float(), w, bias))
@@ -147,8 +155,12 @@ def test_gemm_gelu_epilogue(cin, cout, Ht, B):
     assert float((out.float() - ref).abs().max()) < 2e-2
 
 
-@pytest.mark.parametrize("cin,cout,Ht,B,inplace", [(384, 384, 16, 2, True), (1536, 384, 16, 1, True), (128, 128, 4, 3, False)])
-def test_gemm_gate_residual_fp32(cin, cout, Ht, B, inplace):
+@pytest.mark.parametrize("force", FORCE, ids=FORCE_IDS)
+@pytest.mark.parametrize("cin,cout,Ht,B,inplace", [(384, 384, 16, 2, True), (1536, 384, 16, 1, True), (128, 128, 4, 3, False),
+                                                   (384, 384, 16, 3, False)])
+def test_gemm_gate_residual_fp32(cin, cout, Ht, B, inplace, force, monkeypatch):
+    for k, v in force.items():
+        monkeypatch.setenv(k, v)
     x = _rand((B, Ht, Ht, cin), 1).to(torch.bfloat16)
     w, bias = _rand((cout, cin), 2, cin ** -0.5).to(torch.bfloat16).float(), _rand((cout,), 3, 0.2)
     gate = _rand((B, cout + 12), 4, 0.5)

@@ -107,6 +107,71 @@ def test_conv2_with_fused_shortcut(cins, cout, H, B, monkeypatch):
     assert rel_l2(nchw_f32(out), ref) < TOL_BF16
 
 
+VARIANTS = [  # kernel-variant switches of conv_umma.cu, each against its opposite default
+    {"DMC_CONV_SLAB": "0"}, {"DMC_CONV_BRES": "0"}, {"DMC_CONV_TMA_STORE": "0"}, {"DMC_CONV_TMA_STORE": "2"},
+    {"DMC_CONV_SLAB": "0", "DMC_CONV_BRES": "0", "DMC_CONV_TMA_STORE": "0"}, {"DMC_CONV_CG": "1", "DMC_CONV_TMA_STORE": "2"},
+    {"DMC_CONV_CG": "2", "DMC_CONV_TMA_STORE": "2"}, {"DMC_CONV_CG": "2", "DMC_CONV_TMA_STORE": "2", "DMC_CONV_RES_TMA": "0"},
+    {"DMC_CONV_CG": "2", "DMC_CONV_TMA_STORE": "2", "DMC_CONV_STORE_BUFS": "1"},
+]
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k[9:]}={x}" for k, x in v.items()))
+@pytest.mark.parametrize("kind,cins,cout,H,B", [
+    ("3x3", [128], 128, 32, 3), ("3x3", [256], 256, 16, 3), ("3x3", [128], 256, 16, 2), ("3x3+sc", [256, 128], 128, 32, 2),
+    ("3x3+sc", [256, 256], 256, 16, 3), ("1x1", [256], 768, 16, 3), ("1x1", [256], 256, 16, 5), ("1x1", [384], 1152, 16, 2),
+    ("3x3", [64], 64, 64, 1), ("3x3", [256], 256, 8, 4), ("3x3+res", [128], 128, 32, 3), ("3x3+res", [256], 256, 16, 2),
+])
+def test_conv_kernel_variants(kind, cins, cout, H, B, variant, monkeypatch):
+    """row-slab loads (3x3), resident weights (short K), TMA-store epilogue: every switch on and off gives the reference
+    result, bit-identically reproducible, with the GroupNorm partial sums intact; B is odd for some cases so that the last
+    CTA pair works on a tile that is past the end of the tensor"""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    bias = _rand((cout,), 3, 0.1)
+    if kind == "1x1":
+        cin = cins[0]
+        x = _q(_rand((B, cin, H, H), 5))
+        w = _q(_rand((cout, cin, 1, 1), 6, cin ** -0.5))
+        res = _q(_rand((B, cout, H, H), 8))
+        ref = F.conv2d(x, w, bias) + res
+        args = ([nhwc_bf16(x)], [1], w.reshape(cout, cin), cout)
+        kw = dict(bias=bias, residual=nhwc_bf16(res), stats=True)
+    elif kind == "3x3":
+        cin = cins[0]
+        x = _q(_rand((B, cin, H, H), 1))
+        w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
+        cond = _rand((B, cout + 8), 4, 0.2)
+        ref = F.conv2d(x, w, bias, padding=1) + cond[:, :cout, None, None]
+        args = ([nhwc_bf16(x)], [9], pack3(w), cout)
+        kw = dict(bias=bias, cond=cond, stats=True)
+    elif kind == "3x3+res":  # ResidualBlock.conv2 with the identity shortcut (models/unet.py:72)
+        cin = cins[0]
+        x = _q(_rand((B, cin, H, H), 1))
+        w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
+        res = _q(_rand((B, cout, H, H), 8))
+        ref = F.conv2d(x, w, bias, padding=1) + res
+        args = ([nhwc_bf16(x)], [9], pack3(w), cout)
+        kw = dict(bias=bias, residual=nhwc_bf16(res), stats=True)
+    else:
+        a2 = _q(_rand((B, cout, H, H), 9))
+        xs = [_q(_rand((B, c, H, H), 10 + i)) for i, c in enumerate(cins)]
+        w2 = _q(_rand((cout, cout, 3, 3), 20, (cout * 9) ** -0.5))
+        wsc = _q(_rand((cout, sum(cins), 1, 1), 21, sum(cins) ** -0.5))
+        ref = F.conv2d(a2, w2, None, padding=1) + F.conv2d(torch.cat(xs, 1), wsc) + bias[None, :, None, None]
+        args = ([nhwc_bf16(a2)] + [nhwc_bf16(v) for v in xs], [9] + [1] * len(xs),
+                torch.cat([pack3(w2), wsc.reshape(cout, -1)], dim=1), cout)
+        kw = dict(bias=bias, stats=True)
+    out, st = run_conv(*args, **kw)
+    got = nchw_f32(out)
+    assert torch.isfinite(got).all() and torch.isfinite(st).all()
+    assert rel_l2(got, ref) < TOL_BF16
+    tot = st.sum(dim=1)
+    want_ss = (ref * ref).reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
+    assert rel_l2(tot[..., 1], want_ss) < 1e-3
+    out2, st2 = run_conv(*args, **kw)
+    assert torch.equal(out, out2) and torch.equal(st, st2)
+
+
 @pytest.mark.parametrize("B", [1, 3, 8])
 def test_head_conv_fp32_nchw(B):
     x = _q(_rand((B, 128, 32, 32), 30))

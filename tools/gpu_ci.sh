@@ -12,10 +12,11 @@ run() {  # name, pytest args...
   echo "$name exit $? :: $(tail -1 $OUT/$name.log)" >> $OUT/summary.txt
 }
 run sched tests/test_gpu_sched.py
-for k in conv3x3 conv1x1 shortcut head_conv phase stem groupnorm attention conditioning "upsample_nearest or bad_arguments"; do
+for k in conv3x3 conv_kernel_variants conv1x1 shortcut head_conv phase stem groupnorm attention conditioning "upsample_nearest or bad_arguments"; do
   run "ops_${k%% *}" tests/test_gpu_ops.py -k "$k"
 done
 run unet tests/test_gpu_unet.py
+run dit tests/test_gpu_dit.py
 if [ "$1" != "nobench" ]; then
   timeout 900 python bench.py --batch ${BENCH_BATCH:-1024} --steps 1 --warmup 3 --ops-out $OUT/ops.json > $OUT/bench.log 2>&1
   echo "bench exit $? :: $(tail -c 300 $OUT/bench.log)" >> $OUT/summary.txt
