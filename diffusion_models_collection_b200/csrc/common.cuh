@@ -202,6 +202,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrival WITHOUT memory ordering: for hand-shakes whose payload lives in tensor memory and is ordered by
+// tcgen05.fence::before_thread_sync / tcgen05.wait::ld (e.g. "this accumulator stage has been read").  The releasing
+// form costs a cluster-scope MEMBAR + ERRBAR per arrival -- a quarter of the epilogue warps' time in short-K GEMMs.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(

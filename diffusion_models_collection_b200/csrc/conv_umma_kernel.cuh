@@ -656,7 +656,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // one arrival per warp, on the leader's barrier (its MMA warp reuses the accumulator stage)
-        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+        if (CG == 2) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
         else mbar_arrive(&tempty_bar[acc]);
       }
     }
