@@ -162,7 +162,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="global batch (images per step)")
+    ap.add_argument("--batch", type=int, default=None, help="global batch (images per step); default 4096 (256 for ddpm1000)")
+    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50"],
+                    help="ddim50_cfg: BASELINE configs[2], the bench line (default); ddpm1000: configs[1] (uncond UNet, DDPM "
+                         "1000 steps, batch 256); dit_ddim50: configs[3] (same as --model dit).  The last two are side "
+                         "measurements recorded under profiles/, not the headline metric")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="unet", choices=["unet", "dit"],
                     help="unet: BASELINE configs[2] (the bench line); dit: configs[3] (DiT patch-2 DDIM-50 uncond, --batch 1024), "
@@ -173,6 +177,10 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-op timing table (JSON) here")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "dit_ddim50" if args.model == "dit" else "ddim50_cfg"
+    if args.batch is None:
+        args.batch = 256 if args.workload == "ddpm1000" else 4096
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,7 +200,7 @@ def main():
     import torch.distributed as dist
 
     from diffusion_models_collection_b200 import synth
-    from diffusion_models_collection_b200.diffusion import DDIM
+    from diffusion_models_collection_b200.diffusion import DDIM, DDPM
     from diffusion_models_collection_b200.models import DiT, UNet
     from diffusion_models_collection_b200.sharding import sharded_sample, sharded_sample_with_cfg, shard_bounds
 
@@ -202,15 +210,24 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    is_dit = args.model == "dit"
+    is_dit = args.workload == "dit_ddim50"
+    is_ddpm = args.workload == "ddpm1000"
+    uncond = is_dit or is_ddpm
+    sampler_steps = 1000 if is_ddpm else 50
     if is_dit:
         net = DiT(**synth.CIFAR_DIT, num_classes=None)
         net.load_state_dict(synth.make_dit_state_dict(None, None, seed=42))
+    elif is_ddpm:
+        net = UNet(**synth.CIFAR_UNET, num_classes=None)
+        net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42))
     else:
         net = UNet(**synth.CIFAR_UNET, num_classes=10)
         net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
     net = net.to(dev).eval()
-    ddim = DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device=dev)
+    if is_ddpm:
+        ddim = DDPM(1000, 1e-4, 0.02, "linear", device=dev)  # the sampler object of this workload
+    else:
+        ddim = DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device=dev)
     ddim.progress = False
 
     B = args.batch
@@ -223,7 +240,7 @@ def main():
     shape = (B, 3, 32, 32)
 
     def step_resident():
-        if is_dit:
+        if uncond:
             return sharded_sample(ddim, net, shape, None, noise=xT_dev, rank=rank, world=world)
         return sharded_sample_with_cfg(ddim, net, shape, y_dev, cfg_scale=3.0, noise=xT_dev, rank=rank, world=world)
 
@@ -231,7 +248,7 @@ def main():
         # host -> device of this rank's slice of the inputs, device -> host of the gathered images
         yl = y_host[lo:hi].to(dev, non_blocking=True)
         xl = xT_host[lo:hi].to(dev, non_blocking=True)
-        if is_dit:
+        if uncond:
             out = sharded_sample(ddim, net, shape, None, noise=xl, rank=rank, world=world, sliced=True)
         else:
             out = sharded_sample_with_cfg(ddim, net, shape, yl, cfg_scale=3.0, noise=xl, rank=rank, world=world, sliced=True)
@@ -265,7 +282,7 @@ def main():
     e2e_value = B * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
 
     # launches of OUR kernels in the timed region: per DDIM step, per chunk: one plan run + one fused scheduler kernel
-    launches = net.launches_per_forward(nb, cfg=not is_dit) * 50 * args.steps
+    launches = net.launches_per_forward(nb, cfg=not uncond) * sampler_steps * args.steps
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -275,7 +292,7 @@ def main():
             "gpu_launches": int(launches)}
     pk = peaks()
     # 2 forwards per DDIM step (cond + uncond) for the CFG UNet workload, 1 for the unconditional DiT one
-    flops_step = (50 * 12.107e9 * B) if is_dit else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B)
+    flops_step = (50 * 12.107e9 * B) if is_dit else ((1000 * 12.632e9 * B) if is_ddpm else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B))
     line["model_flops_utilization"] = {"achieved_tflops": flops_step * args.steps / (ms / 1e3) / 1e12 / world,
                                        "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
 
@@ -284,9 +301,15 @@ def main():
         line["config"]["workload"] = ("DiT patch-2 (hidden 384, depth 12, 6 heads) 32x32 unconditional, DDIM-50 "
                                       "(BASELINE.json configs[3]); side measurement, not the headline metric")
         line["config"]["cfg_scale"] = None
+    if is_ddpm:
+        line["metric"] = "ddpm1000_unet_cifar10_images_per_sec"
+        line["config"]["workload"] = ("UNet unconditional CIFAR-10 32x32, DDPM 1000 steps, fresh N(0,1) noise every step "
+                                      "(BASELINE.json configs[1]); side measurement, not the headline metric")
+        line["config"]["sampler"] = "ddpm1000"
+        line["config"]["cfg_scale"] = None
     if rank == 0 and not args.no_roofline:
-        line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out, cfg=not is_dit, step_ms=ms / args.steps / 50.0,
-                                        chunks=-(-nb // max(1, net.max_images_per_launch // (1 if is_dit else 2))))
+        line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out, cfg=not uncond, step_ms=ms / args.steps / sampler_steps,
+                                        chunks=-(-nb // max(1, net.max_images_per_launch // (1 if uncond else 2))))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
         line["cpu_baseline"] = cb

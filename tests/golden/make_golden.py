@@ -18,6 +18,8 @@ Fixtures written:
                      and the DDIM timestep subsets
   steps_golden.npz   single p_sample calls (DDIM eta 0 / 0.5, last step, DDPM t>0 / t==0), q_sample
   loops_golden.npz   whole sample() / sample_with_cfg() runs with a toy denoiser and recorded noise
+  samples_golden.npz FINAL images of whole DDIM-50 runs of the REAL CIFAR UNet / DiT through the reference's own
+                     sample() / sample_with_cfg() (fp32 CPU, x_T recorded): the end-to-end pin of BASELINE configs 1 / 3 / 4
 """
 
 from __future__ import annotations
@@ -93,6 +95,44 @@ def gen_unet():
         out[name] = eps.numpy()
         print("unet", name, tuple(eps.shape), float(eps.std()))
     np.savez_compressed(os.path.join(HERE, "unet_golden.npz"), **out)
+
+
+TEACHER_STEPS = [0, 1, 10, 25, 40, 48, 49]  # DDIM-50 steps whose (x_in, x_out) pair is stored for teacher forcing
+
+
+def gen_samples():
+    """whole sampling runs of the real models through the reference's own loops (tqdm bars silenced): the final images and,
+    for a few steps s, the reference's own state before and after step s (teacher-forcing pairs)"""
+    import contextlib
+    import io
+
+    out = {}
+
+    def run(name, net, fn):
+        torch.manual_seed(1234)
+        with NoiseRecorder() as rec, contextlib.redirect_stderr(io.StringIO()), torch.no_grad():
+            traj = fn(net)  # [S, B, C, H, W]: the state after every step (return_all_timesteps=True)
+        xT = rec.draws[0]
+        out[name] = traj[-1].numpy()
+        out[name + ".xT"] = xT.numpy()
+        for s_ in TEACHER_STEPS:
+            out[f"{name}.in{s_}"] = (xT if s_ == 0 else traj[s_ - 1]).numpy()
+            out[f"{name}.out{s_}"] = traj[s_].numpy()
+        print("samples", name, tuple(traj.shape), float(traj[-1].abs().max()), float(traj[-1].std()))
+
+    d50 = ref_ddim.DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
+    net = ref_unet.UNet(**synth.CIFAR_UNET, num_classes=None).eval()
+    net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42), strict=True)
+    run("unet.uncond.ddim50", net, lambda m: d50.sample(m, (2, 3, 32, 32), return_all_timesteps=True))
+    net = ref_unet.UNet(**synth.CIFAR_UNET, num_classes=10).eval()
+    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42), strict=True)
+    y = torch.tensor([3, 10])
+    run("unet.cond.ddim50.cfg3", net, lambda m: d50.sample_with_cfg(m, (2, 3, 32, 32), y, cfg_scale=3.0,
+                                                                    return_all_timesteps=True))
+    net = ref_dit.DiT(**synth.CIFAR_DIT, num_classes=None).eval()
+    net.load_state_dict(synth.make_dit_state_dict(None, None, seed=42), strict=True)
+    run("dit.uncond.ddim50", net, lambda m: d50.sample(m, (2, 3, 32, 32), return_all_timesteps=True))
+    np.savez_compressed(os.path.join(HERE, "samples_golden.npz"), **out)
 
 
 def gen_dit():
@@ -218,6 +258,6 @@ def gen_loops():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["tables", "steps", "loops", "unet", "dit"]
+    which = sys.argv[1:] or ["tables", "steps", "loops", "unet", "dit", "samples"]
     for w in which:
         globals()["gen_" + w]()

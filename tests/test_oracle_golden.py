@@ -147,3 +147,19 @@ def test_sampler_loops(golden):
     eq("ddpm20.cfg3.traj", so.ddpm_sample_cfg(so.toy_model, tb20, nz[0], nz[1:], y, 3.0, trajectory=True))
     nz = n("ddpm20.cfg2.nothr")
     eq("ddpm20.cfg2.nothr", so.ddpm_sample_cfg(so.toy_model, tb20, nz[0], nz[1:], y, 2.0, None))
+
+
+def test_oracle_whole_ddim50_run_matches_reference_samples(golden):
+    """the oracle's UNet restatement + DDIM loop from the recorded x_T reproduce the FINAL images of the reference's own
+    DDIM.sample over 50 steps (fp32 CPU both; the per-forward 2e-6 differences of the restated ops do not grow)"""
+    g = golden["samples"]
+    sd = synth.make_unet_state_dict(None, None, seed=42)
+    tb = so.make_tables()
+    ts = so.ddim_timesteps(1000, 50)
+
+    def model(x, t, y=None):
+        return model_oracle.unet_forward(sd, synth.CIFAR_UNET, x, t, y, num_classes=None)
+
+    img = so.ddim_sample(model, tb, ts, torch.from_numpy(g["unet.uncond.ddim50.xT"]))
+    ref = torch.from_numpy(g["unet.uncond.ddim50"])
+    assert float((img - ref).abs().max()) < 1e-3
