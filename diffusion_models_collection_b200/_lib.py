@@ -45,17 +45,17 @@ class CondDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32),
-                ("W", C.c_int32), ("Cout", C.c_int32), ("weight", vp), ("bias", vp), ("out", vp)]
+                ("W", C.c_int32), ("Cout", C.c_int32), ("weight", vp), ("bias", vp), ("out", vp), ("out_lo", vp)]
 
 
 class GnStatsDesc(C.Structure):
-    _fields_ = [("src", vp), ("B", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32), ("stats", vp)]
+    _fields_ = [("src", vp), ("B", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32), ("stats", vp), ("src_lo", vp)]
 
 
 class GnApplyDesc(C.Structure):
     _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2), ("stats_slots", C.c_int32 * 2),
                 ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
-                ("silu", C.c_int32), ("out", vp)]
+                ("silu", C.c_int32), ("out", vp), ("src_lo", vp * 2), ("out_lo", vp)]
 
 
 class ConvDesc(C.Structure):
@@ -65,7 +65,7 @@ class ConvDesc(C.Structure):
                 ("Ktot", C.c_int32), ("bias", vp), ("cond", vp), ("cond_stride", C.c_int32), ("residual", vp),
                 ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("stats_slots", C.c_int32), ("impl", C.c_int32),
                 ("act", C.c_int32), ("gate", vp), ("gate_stride", C.c_int32), ("residual_f32", vp), ("out_f32_nhwc", vp),
-                ("unpatch_p", C.c_int32)]
+                ("out_lo", vp), ("residual_lo", vp), ("unpatch_p", C.c_int32)]
 
 
 class DitCondDesc(C.Structure):
@@ -86,7 +86,7 @@ class LnModDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [("qkv", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32), ("C", C.c_int32),
-                ("impl", C.c_int32)]
+                ("impl", C.c_int32), ("qkv_lo", vp), ("out_lo", vp)]
 
 
 class UpsampleDesc(C.Structure):

@@ -117,6 +117,84 @@ __global__ void __launch_bounds__(ATT_TQ) attention_kernel(const __nv_bfloat16* 
   }
 }
 
+// Split-bf16 mode: q, k, v are (hi, lo) bf16 pairs, all arithmetic in fp32 on the CUDA cores, the output is a pair again.
+// One thread per query row, K / V tiles as fp32 in shared memory.
+template <int ATT_HD>
+__global__ void __launch_bounds__(ATT_TQ) attention_split_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                 const __nv_bfloat16* __restrict__ qkv_lo,
+                                                                 __nv_bfloat16* __restrict__ out,
+                                                                 __nv_bfloat16* __restrict__ out_lo, int L, int C,
+                                                                 float scale_log2e) {
+  __shared__ float sK[ATT_TK * ATT_HD];
+  __shared__ float sV[ATT_TK * ATT_HD];
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int qi = blockIdx.x * ATT_TQ + threadIdx.x;
+  const bool active = qi < L;
+  const size_t row_stride = static_cast<size_t>(3) * C;
+  const size_t img = static_cast<size_t>(n) * L * row_stride;
+  float q[ATT_HD], acc[ATT_HD];
+#pragma unroll
+  for (int d = 0; d < ATT_HD; ++d) {
+    acc[d] = 0.f;
+    q[d] = 0.f;
+  }
+  if (active) {
+    const size_t o = img + static_cast<size_t>(qi) * row_stride + h * ATT_HD;
+#pragma unroll
+    for (int d = 0; d < ATT_HD; ++d) q[d] = (__bfloat162float(qkv[o + d]) + __bfloat162float(qkv_lo[o + d])) * scale_log2e;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < L; k0 += ATT_TK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < ATT_TK * ATT_HD; e += ATT_TQ) {
+      const int kr = e / ATT_HD, d = e % ATT_HD;
+      float kk = 0.f, vv = 0.f;
+      if (k0 + kr < L) {
+        const size_t o = img + static_cast<size_t>(k0 + kr) * row_stride + h * ATT_HD + d;
+        kk = __bfloat162float(qkv[o + C]) + __bfloat162float(qkv_lo[o + C]);
+        vv = __bfloat162float(qkv[o + 2 * C]) + __bfloat162float(qkv_lo[o + 2 * C]);
+      }
+      sK[e] = kk;
+      sV[e] = vv;
+    }
+    __syncthreads();
+    float s[ATT_TK];
+    float tmax = -INFINITY;
+#pragma unroll 4
+    for (int j = 0; j < ATT_TK; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < ATT_HD; ++d) a = fmaf(q[d], sK[j * ATT_HD + d], a);
+      s[j] = (k0 + j < L) ? a : -INFINITY;
+      tmax = fmaxf(tmax, s[j]);
+    }
+    const float m_new = fmaxf(m, tmax);
+    const float corr = exp2f(m - m_new);
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < ATT_HD; ++d) acc[d] *= corr;
+#pragma unroll 4
+    for (int j = 0; j < ATT_TK; ++j) {
+      const float pj = exp2f(s[j] - m_new);
+      l += pj;
+#pragma unroll
+      for (int d = 0; d < ATT_HD; ++d) acc[d] = fmaf(pj, sV[j * ATT_HD + d], acc[d]);
+    }
+    m = m_new;
+  }
+  if (active) {
+    const float inv = 1.0f / l;
+    const size_t o = (static_cast<size_t>(n) * L + qi) * C + h * ATT_HD;
+#pragma unroll
+    for (int d = 0; d < ATT_HD; ++d) {
+      const float v = acc[d] * inv;
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      out[o + d] = hi;
+      out_lo[o + d] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+  }
+}
+
 int launch_attention(const dmc_attn_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.qkv && d.out && d.B > 0 && d.L > 0 && d.heads > 0, "attention: bad arguments");
   const int hd = d.C / d.heads;
@@ -126,6 +204,15 @@ int launch_attention(const dmc_attn_desc& d, cudaStream_t st) {
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(d.qkv);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  if (d.qkv_lo != nullptr || d.out_lo != nullptr) {
+    DMC_REQUIRE(d.qkv_lo && d.out_lo, "attention: split-bf16 mode needs both qkv_lo and out_lo");
+    const __nv_bfloat16* ql = reinterpret_cast<const __nv_bfloat16*>(d.qkv_lo);
+    __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+    if (hd == 64) attention_split_kernel<64><<<grid, ATT_TQ, 0, st>>>(qkv, ql, out, ol, d.L, d.C, scale_log2e);
+    else attention_split_kernel<32><<<grid, ATT_TQ, 0, st>>>(qkv, ql, out, ol, d.L, d.C, scale_log2e);
+    DMC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (hd == 64) attention_kernel<64><<<grid, ATT_TQ, 0, st>>>(qkv, out, d.L, d.C, scale_log2e);
   else attention_kernel<32><<<grid, ATT_TQ, 0, st>>>(qkv, out, d.L, d.C, scale_log2e);
   DMC_CUDA_OK(cudaGetLastError());

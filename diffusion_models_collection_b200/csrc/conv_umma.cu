@@ -162,7 +162,12 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     if (encode_map(&P->tmB, d.weight, 2, dims, strides, box, estr) != 0) { delete P; return -1; }
   }
   // ---- kernel variant selection (every switch has an environment override for A/B measurements and tests) ----
-  const int epi = d.out_f32_nchw ? 2 : ((d.gate || d.residual_f32 || d.out_f32_nhwc) ? 3 : (d.act ? 1 : 0));
+  const bool split = d.out_lo != nullptr || d.residual_lo != nullptr;  // split-bf16 (hi, lo) output / residual pairs
+  const int epi = d.out_f32_nchw ? 2 : ((d.gate || d.residual_f32 || d.out_f32_nhwc) ? 3 : (d.act ? 1 : (split ? 4 : 0)));
+  if (split && (epi != 4 || !d.out_bf16 || (d.residual_lo && !d.residual))) {
+    delete P;
+    DMC_REQUIRE(false, "conv: out_lo / residual_lo go with a bf16 NHWC output (and residual) of a plain convolution");
+  }
   if ((epi == 1 || epi == 3) && (d.cond || d.residual || d.stats)) {
     delete P;
     DMC_REQUIRE(false, "conv: the transformer epilogues (act / gate / fp32 stream) exclude cond, bf16 residual and stats");
@@ -181,7 +186,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   //     are L2->SM bound; with the whole K extent of one weight tile resident only activations stream.
   kp.bres = 0;
   kp.b_region_bytes = 0;
-  if (env_flag("DMC_CONV_BRES", 1) && epi != 2 && kp.num_kb <= 8 && kp.num_kb * b_tile <= 112 * 1024 &&
+  if (env_flag("DMC_CONV_BRES", 1) && epi != 2 && epi != 4 && kp.num_kb <= 8 && kp.num_kb * b_tile <= 112 * 1024 &&
       kp.num_n_tiles <= 12 && kp.num_n_tiles <= (num_sms() / tc.cg)) {
     kp.bres = 1;
     kp.b_region_bytes = kp.num_kb * b_tile;
@@ -190,7 +195,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.slab = 0;
   kp.slab_bytes = 0;
   P->tmS = P->tmA[0];
-  if (env_flag("DMC_CONV_SLAB", 1) && !kp.bres && (epi == 0 || epi == 2) && d.src_taps[0] == 9 && d.stride == 1 && d.up_phase < 0 && BNIMG == 1 &&
+  if (env_flag("DMC_CONV_SLAB", 1) && !kp.bres && (epi == 0 || epi == 2 || epi == 4) && d.src_taps[0] == 9 && d.stride == 1 && d.up_phase < 0 && BNIMG == 1 &&
       kp.tiles_w == 1 && BW >= 8 && kp.tiles_h % tc.mt == 0) {
     const int rows = tc.mt * BH + 2;
     const int C = d.src_c[0];
@@ -223,7 +228,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     const bool f32 = epi == 3;
     const int boxc = f32 ? 32 : 64;
     void* optr = f32 ? static_cast<void*>(d.out_f32_nhwc) : d.out_bf16;
-    if (want && epi != 2 && optr != nullptr && d.Cout % boxc == 0 && BN >= 128) {
+    if (want && epi != 2 && epi != 4 && optr != nullptr && d.Cout % boxc == 0 && BN >= 128) {
       const int qbw = std::min(BW, 32), qbh = std::min(BH, 32 / qbw), qbn = 32 / (qbw * qbh);
       const int os = kp.oscale;
       const size_t es = f32 ? 4 : 2;
@@ -285,6 +290,8 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.gate = d.gate; kp.gate_stride = d.gate_stride;
   kp.residual_f32 = d.residual_f32; kp.out_f32 = d.out_f32_nhwc;
   kp.unpatch_p = d.unpatch_p;
+  kp.residual_lo = reinterpret_cast<const __nv_bfloat16*>(d.residual_lo);
+  kp.out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
   if (d.stats) {
     const int ppi_img = Hout * Wout;  // iteration pixels per image
     const int base = ppi_img >= 32 ? ppi_img / 32 : 1;

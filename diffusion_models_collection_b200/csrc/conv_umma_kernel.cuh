@@ -46,6 +46,8 @@ struct ConvKParams {
   const float* residual_f32;  // fp32 NHWC residual stream
   float* out_f32;             // fp32 NHWC output
   int unpatch_p;              // > 0: out_nchw columns are (pi, qi, c) patch entries
+  const __nv_bfloat16* residual_lo;  // split-bf16 mode: low parts of the residual and of the output
+  __nv_bfloat16* out_lo;
   // TMA-store epilogue: every epilogue warp stores its 32 rows x 64 channels as one box {64, qbw, qbh, qbn}
   int tma_store;
   int qbw, qbh;               // quarter box: qbw pixels x qbh rows x 32/(qbw*qbh) images
@@ -153,6 +155,7 @@ __device__ __forceinline__ void reduce8(const float (&v)[8], bool full, int lane
 //                1: transformer linear, bf16 NHWC out (bias, GELU)
 //                2: model head (bias, fp32 NCHW out, optional unpatchify)
 //                3: transformer linear on the fp32 residual stream (bias, gate, fp32 residual, fp32 NHWC out)
+//                4: UNet convolution in split-bf16 mode: like 0, the residual and the output are (hi, lo) bf16 pairs
 constexpr int VAR_SLAB = 1, VAR_BRES = 2, VAR_TS = 4, VAR_EPI_SHIFT = 3;
 
 template <int BN, int MT, int CG, int VAR>
@@ -166,6 +169,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   constexpr bool BRES = (VAR & VAR_BRES) != 0;
   constexpr bool TS = (VAR & VAR_TS) != 0 && Cfg::TMA_STORE;
   constexpr int EPI = VAR >> VAR_EPI_SHIFT;
+  constexpr bool UNET = EPI == 0 || EPI == 4;  // bias + conditioning + bf16 residual + GroupNorm partial sums
   constexpr int MTG = MT * CG;  // 128-pixel tiles per CTA-group tile
   constexpr int B_TILE = Cfg::B_STAGE_BYTES;
   const int NST = p.nst;
@@ -468,7 +472,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) add[j] = 0.f;
             }
-            if (EPI == 0 && p.cond != nullptr && valid) {
+            if (UNET && p.cond != nullptr && valid) {
               const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -478,7 +482,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
           uint4 res[4];
-          const bool has_res = EPI == 0 && p.residual != nullptr && valid && real;
+          const bool has_res = UNET && p.residual != nullptr && valid && real;
           if (has_res && !res_tma) {
             const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
 #pragma unroll
@@ -572,6 +576,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   v[8 * j + 2 * k + 1] += f.y;
                 }
               }
+              if (EPI == 4 && p.residual_lo != nullptr) {  // low part of the split-bf16 residual
+                const uint4* r4 = reinterpret_cast<const uint4*>(p.residual_lo + pix * p.Cout + cg);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 rv = r4[j];  // plain load: the output pair may alias the residual pair
+                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack_bf16x2(w[k]);
+                    v[8 * j + 2 * k] += f.x;
+                    v[8 * j + 2 * k + 1] += f.y;
+                  }
+                }
+              }
             }
           }
           // ---- output ----
@@ -613,6 +631,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           } else if (valid && p.out != nullptr) {
             uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
+            uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + cg);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
@@ -621,9 +640,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
               o4[j] = u;
+              if (EPI == 4 && p.out_lo != nullptr) {  // lo = bf16(v - hi): 16 mantissa bits in the pair
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                uint32_t lo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_bf16x2(w[k]);
+                  lo[k] = pack_bf16x2(v[8 * j + 2 * k] - f.x, v[8 * j + 2 * k + 1] - f.y);
+                }
+                l4[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
-          if (EPI == 0 && p.stats != nullptr) {
+          if (UNET && p.stats != nullptr) {
             // GroupNorm partial sums of the OUTPUT per (image, 8-channel block) over the rows of this warp that belong
             // to one image (all 32 when ppi >= 32, else each 16-lane half), stored in this warp's own slot: plain
             // stores, no atomics -> deterministic and batch-invariant; the consumer adds the slots in index order.
@@ -720,6 +749,8 @@ static int launch_tile_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStr
     DMC_V((2 << VAR_EPI_SHIFT) | VAR_SLAB);
     DMC_V(3 << VAR_EPI_SHIFT);
     DMC_V((3 << VAR_EPI_SHIFT) | VAR_BRES);
+    DMC_V(4 << VAR_EPI_SHIFT);
+    DMC_V((4 << VAR_EPI_SHIFT) | VAR_SLAB);
 #undef DMC_V
     default: break;
   }

@@ -134,7 +134,8 @@ int launch_cond(const dmc_cond_desc& d, cudaStream_t st) {
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                   int x_batch, int B, int H, int W, int Cout) {
+                                                   __nv_bfloat16* __restrict__ out_lo, int x_batch, int B, int H, int W,
+                                                   int Cout) {
   constexpr int K = CIN * 9;
   extern __shared__ float sw[];  // [K][Cout] transposed weights, then bias[Cout]
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -197,6 +198,17 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                           pack_bf16x2(acc[u][4], acc[u][5]), pack_bf16x2(acc[u][6], acc[u][7]));
         o[1] = make_uint4(pack_bf16x2(acc[u][8], acc[u][9]), pack_bf16x2(acc[u][10], acc[u][11]),
                           pack_bf16x2(acc[u][12], acc[u][13]), pack_bf16x2(acc[u][14], acc[u][15]));
+        if (out_lo != nullptr) {  // split-bf16 mode: the rounding remainder as a second bf16 tensor
+          uint32_t lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 hi = unpack_bf16x2(pack_bf16x2(acc[u][2 * j], acc[u][2 * j + 1]));
+            lo[j] = pack_bf16x2(acc[u][2 * j] - hi.x, acc[u][2 * j + 1] - hi.y);
+          }
+          uint4* ol = reinterpret_cast<uint4*>(out_lo + pix[u] * Cout + c0);
+          ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
       }
     }
   }
@@ -210,11 +222,12 @@ int launch_stem(const dmc_stem_desc& d, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(d.Cin) * 9 * d.Cout + d.Cout) * sizeof(float);
   DMC_REQUIRE(smem <= 48 * 1024, "stem: Cout=%d too large", d.Cout);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
   switch (d.Cin) {
-    case 1: stem_kernel<1><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
-    case 2: stem_kernel<2><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
-    case 3: stem_kernel<3><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
-    default: stem_kernel<4><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    case 1: stem_kernel<1><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, lo, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    case 2: stem_kernel<2><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, lo, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    case 3: stem_kernel<3><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, lo, d.x_batch, d.B, d.H, d.W, d.Cout); break;
+    default: stem_kernel<4><<<blocks, 256, smem, st>>>(d.x, d.weight, d.bias, out, lo, d.x_batch, d.B, d.H, d.W, d.Cout); break;
   }
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -225,8 +238,9 @@ int launch_stem(const dmc_stem_desc& d, cudaStream_t st) {
 // =============================================================================================
 constexpr int GN_SLAB = 128;  // pixels per CTA
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ src, float* __restrict__ stats, int HW,
-                                                       int C8 /* C/8 */, int rows /* blockDim / C8 */) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ src, const uint4* __restrict__ src_lo,
+                                                       float* __restrict__ stats, int HW, int C8 /* C/8 */,
+                                                       int rows /* blockDim / C8 */) {
   extern __shared__ float red[];  // [rows][C8][2]
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * GN_SLAB;
@@ -237,9 +251,15 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
     for (int p = p0 + r; p < p1; p += rows) {
       uint4 v = src[(static_cast<size_t>(n) * HW + p) * C8 + cb];
       uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      uint4 vl = make_uint4(0, 0, 0, 0);
+      if (src_lo != nullptr) vl = src_lo[(static_cast<size_t>(n) * HW + p) * C8 + cb];
+      const uint32_t ul[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float2 f = unpack_bf16x2(u[j]);
+        const float2 fl = unpack_bf16x2(ul[j]);
+        f.x += fl.x;
+        f.y += fl.y;
         s += f.x + f.y;
         ss = fmaf(f.x, f.x, ss);
         ss = fmaf(f.y, f.y, ss);
@@ -268,7 +288,7 @@ int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st) {
   const int threads = rows * C8;
   dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
   gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads) * 2 * sizeof(float), st>>>(
-      reinterpret_cast<const uint4*>(d.src), d.stats, d.HW, C8, rows);
+      reinterpret_cast<const uint4*>(d.src), reinterpret_cast<const uint4*>(d.src_lo), d.stats, d.HW, C8, rows);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -284,6 +304,9 @@ struct GnApplyArgs {
   const float* gamma;
   const float* beta;
   uint4* out;
+  const uint4* lo0;  // split-bf16 mode: low parts of the sources / of the output (all or none)
+  const uint4* lo1;
+  uint4* out_lo;
   int HW, C0_8, C1_8, groups;
   int slots0, slots1;
   float eps;
@@ -294,6 +317,7 @@ struct GnApplyArgs {
 // sources of a concat) with lane-strided loads and a fixed shuffle tree -> mean / rstd, bit-reproducible.
 // Phase 2: every thread owns ONE 8-channel block (its 8 scales / shifts live in registers) and walks the pixels of the
 // slab: one 128-bit load, 8 FMAs (+ SiLU), one 128-bit store per pixel, four pixels in flight.
+template <bool LO>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C8 = a.C0_8 + a.C1_8;
@@ -360,33 +384,59 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
                            : a.src1 + static_cast<size_t>(n) * a.HW * a.C1_8 + (cb - a.C0_8);
   const int sstride = first ? a.C0_8 : a.C1_8;
   uint4* dst = a.out + static_cast<size_t>(n) * a.HW * C8 + cb;
+  const uint4* src_lo = nullptr;
+  uint4* dst_lo = nullptr;
+  if (LO) {
+    src_lo = first ? a.lo0 + static_cast<size_t>(n) * a.HW * a.C0_8 + cb
+                   : a.lo1 + static_cast<size_t>(n) * a.HW * a.C1_8 + (cb - a.C0_8);
+    dst_lo = a.out_lo + static_cast<size_t>(n) * a.HW * C8 + cb;
+  }
   const int p0 = blockIdx.x * GN_SLAB;
   const int p1 = min(p0 + GN_SLAB, a.HW);
   for (int pb = p0 + r0; pb < p1; pb += 4 * rpi) {
-    uint4 in[4];
+    uint4 in[4], inl[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int p = pb + u * rpi;
-      if (p < p1) in[u] = __ldg(src + static_cast<size_t>(p) * sstride);
+      if (p < p1) {
+        in[u] = __ldg(src + static_cast<size_t>(p) * sstride);
+        if (LO) inl[u] = __ldg(src_lo + static_cast<size_t>(p) * sstride);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int p = pb + u * rpi;
       if (p < p1) {
         const uint32_t w[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
-        uint32_t o[4];
+        const uint32_t wl[4] = {inl[u].x, inl[u].y, inl[u].z, inl[u].w};
+        uint32_t o[4], ol[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
+          float2 f = unpack_bf16x2(w[j]);
+          if (LO) {
+            const float2 fl = unpack_bf16x2(wl[j]);
+            f.x += fl.x;
+            f.y += fl.y;
+          }
           float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
           float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
           if (a.silu) {
-            y0 = silu_from_half(y0);
-            y1 = silu_from_half(y1);
+            if (LO) {  // the accuracy mode keeps the exact-to-fp32 SiLU (ex2 + rcp); y is y/2 here (scale folded)
+              y0 = __fdividef(2.0f * y0, 1.0f + __expf(-2.0f * y0));
+              y1 = __fdividef(2.0f * y1, 1.0f + __expf(-2.0f * y1));
+            } else {
+              y0 = silu_from_half(y0);
+              y1 = silu_from_half(y1);
+            }
           }
           o[j] = pack_bf16x2(y0, y1);
+          if (LO) {
+            const float2 hi = unpack_bf16x2(o[j]);
+            ol[j] = pack_bf16x2(y0 - hi.x, y1 - hi.y);
+          }
         }
         dst[static_cast<size_t>(p) * C8] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (LO) dst_lo[static_cast<size_t>(p) * C8] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
       }
     }
   }
@@ -411,8 +461,14 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.slots0 = d.stats_slots[0];
   a.slots1 = d.nsrc == 2 ? d.stats_slots[1] : 0;
   DMC_REQUIRE(a.slots0 > 0 && (d.nsrc == 1 || a.slots1 > 0), "gn_apply: stats_slots must be positive");
+  const bool lo = d.out_lo != nullptr;
+  if (lo) DMC_REQUIRE(d.src_lo[0] && (d.nsrc == 1 || d.src_lo[1]), "gn_apply: split-bf16 mode needs the low part of every source");
+  a.lo0 = reinterpret_cast<const uint4*>(d.src_lo[0]);
+  a.lo1 = reinterpret_cast<const uint4*>(d.nsrc == 2 ? d.src_lo[1] : d.src_lo[0]);
+  a.out_lo = reinterpret_cast<uint4*>(d.out_lo);
   dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
-  gn_apply_kernel<<<grid, 256, 0, st>>>(a);
+  if (lo) gn_apply_kernel<true><<<grid, 256, 0, st>>>(a);
+  else gn_apply_kernel<false><<<grid, 256, 0, st>>>(a);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

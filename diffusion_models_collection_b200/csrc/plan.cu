@@ -327,7 +327,7 @@ int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d) {
   op.kind = OP_ATTN;
   op.attn = *d;
   DMC_REQUIRE(d->impl == 0 || d->impl == 1, "dmc_plan_add_attention: impl=%d", d->impl);
-  if (d->impl == 0 && attention_umma_supported(*d)) {
+  if (d->impl == 0 && d->qkv_lo == nullptr && d->out_lo == nullptr && attention_umma_supported(*d)) {
     int r = attention_prepare(*d, &op.attn_prep);
     if (r != 0) return r;
   }

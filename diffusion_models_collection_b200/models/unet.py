@@ -101,28 +101,32 @@ class _Arena:
 class _Act:
     """A bf16 NHWC activation [B, H, W, C] living in the plan workspace."""
 
-    __slots__ = ("blk", "C", "H", "W", "stats", "slots")
+    __slots__ = ("blk", "lo", "C", "H", "W", "stats", "slots")
 
-    def __init__(self, blk, Cc, H, W):
-        self.blk, self.C, self.H, self.W = blk, Cc, H, W
+    def __init__(self, blk, Cc, H, W, lo=None):
+        self.blk, self.lo, self.C, self.H, self.W = blk, lo, Cc, H, W  # lo: low parts in split-bf16 mode
         self.stats, self.slots = None, 0  # GroupNorm partial sums [B, slots, C/8, 2] fp32 (workspace block)
 
 
 class _PlanBuilder:
     """Walks the UNet topology once (dry run -> workspace size, then for real) and records the op list."""
 
-    def __init__(self, net: "UNet", nimg, x_batch, has_y, uniform_t, conv_impl):
+    def __init__(self, net: "UNet", nimg, x_batch, has_y, uniform_t, conv_impl, split=False):
         self.net, self.B, self.x_batch = net, nimg, x_batch
         self.has_y, self.uniform_t, self.conv_impl = has_y, uniform_t, conv_impl
+        self.split = split  # split-bf16 ("bf16x3") accuracy mode: every activation is a (hi, lo) pair of bf16 tensors
         self.arena = _Arena()
         self.ops = []  # (kind, dict)
 
     # -- workspace ---------------------------------------------------------------------------------
     def act(self, Cc, H, W):
-        return _Act(self.arena.alloc(self.B * H * W * Cc * 2), Cc, H, W)
+        n = self.B * H * W * Cc * 2
+        return _Act(self.arena.alloc(n), Cc, H, W, self.arena.alloc(n) if self.split else None)
 
     def free(self, a: _Act):
         self.arena.release(a.blk)
+        if a.lo is not None:
+            self.arena.release(a.lo)
         if a.stats is not None:
             self.arena.release(a.stats)
 
@@ -148,7 +152,7 @@ class _PlanBuilder:
         return out
 
     def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
-             up_phase=-1, out=None, want_stats=True):
+             up_phase=-1, out=None, want_stats=True, sc_slice=None):
         Ho, Wo = H // stride, W // stride
         if up_phase >= 0:
             Ho, Wo = 2 * H, 2 * W
@@ -157,9 +161,13 @@ class _PlanBuilder:
         if out is not None and want_stats and self.conv_impl == 0 and out.stats is None:
             ppi = (H // stride) * (W // stride)  # iteration pixels per image: one slot per 32-pixel epilogue warp
             self._alloc_stats(out, max(1, ppi // 32) * (4 if up_phase >= 0 else 1))
-        self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), wname=wname, Cout=Cout, H=H, W=W, stride=stride,
-                                      bias=bias, cond_col=cond_col, residual=residual, out=out, out_nchw=out_nchw,
-                                      up_phase=up_phase, want_stats=want_stats)))
+        parts = ["hi"] * len(srcs)
+        if self.split:  # hi*W_hi + lo*W_hi + hi*W_lo as three K segments (weights packed [W_hi | W_hi | W_lo])
+            assert len(srcs) == 1, "split-bf16 mode: one logical source per launch"
+            srcs, taps, parts = [srcs[0]] * 3, [taps[0]] * 3, ["hi", "lo", "hi"]
+        self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), parts=parts, wname=wname, Cout=Cout, H=H, W=W,
+                                      stride=stride, bias=bias, cond_col=cond_col, residual=residual, out=out,
+                                      out_nchw=out_nchw, up_phase=up_phase, want_stats=want_stats, sc_slice=sc_slice)))
         return out
 
     def resblock(self, srcs, prefix, cout, cond_col):
@@ -170,7 +178,17 @@ class _PlanBuilder:
         self.free(a1)
         a2 = self.gn_apply([h1], prefix + ".conv2.0", 1)
         self.free(h1)
-        if cin != cout:  # 1x1 shortcut fused as extra K columns over the raw (un-normalised) inputs
+        if cin != cout and self.split:
+            # accuracy mode: conv2, then the 1x1 shortcut of every raw source as its own launch chained through the residual
+            out = self.conv([a2], [9], prefix + ".conv2", cout, H, W, bias=prefix + ".conv2+sc", want_stats=False)
+            off = 0
+            for i, s_ in enumerate(srcs):
+                nxt = self.conv([s_], [1], f"{prefix}.sc.{i}", cout, H, W, residual=out, want_stats=(i == len(srcs) - 1),
+                                sc_slice=(off, s_.C))
+                off += s_.C
+                self.free(out)
+                out = nxt
+        elif cin != cout:  # 1x1 shortcut fused as extra K columns over the raw (un-normalised) inputs
             out = self.conv([a2] + list(srcs), [9] + [1] * len(srcs), prefix + ".conv2+sc", cout, H, W,
                             bias=prefix + ".conv2+sc")
         else:
@@ -422,7 +440,16 @@ class UNet(nn.Module):
         half = self.model_channels // 2
         # models/unet.py:20-22 -- exponent divisor (half - 1); computed with the reference's own expression
         freqs = torch.exp(torch.arange(half, device=device) * -(math.log(10000) / (half - 1))).float().contiguous()
+        # split-bf16 mode packs [W_hi | W_hi | W_lo] per logical convolution on demand (see _split_weight)
+        wlog = dict(W)
+        for i_, layers_ in [(f"down_blocks.{i}", l) for i, l in enumerate(down)] + [("middle_block", middle)] + \
+                [(f"up_blocks.{i}", l) for i, l in enumerate(up)]:
+            for j, l in enumerate(layers_):
+                if l[0] == "res" and l[1] != l[2]:
+                    wlog[f"{i_}.{j}.conv2"] = pack3(sd[f"{i_}.{j}.conv2.3.weight"])
+                    wlog[f"{i_}.{j}.sc"] = sd[f"{i_}.{j}.shortcut.weight"].reshape(l[2], l[1])
         self._packed = dict(
+            wlog=wlog, w3={},
             sd=sd, wblob=wblob, woffs=offs, wshape={k: tuple(v.shape) for k, v in W.items()},
             bias={k: v.contiguous() for k, v in Bv.items()}, wt_all=wt_all, bt_all=bt_all, ytab=ytab, freqs=freqs,
             ncols=wt_all.shape[0], temb=temb,
@@ -433,11 +460,31 @@ class UNet(nn.Module):
         self._plans = {}
         return self._packed
 
+    @staticmethod
+    def _split_weight(pk, wname, sc_slice=None):
+        """bf16 [rows, 3K] = [W_hi | W_hi | W_lo] of one logical convolution (split-bf16 mode), cached per packing"""
+        key = (wname, sc_slice)
+        w3 = pk["w3"].get(key)
+        if w3 is None:
+            if sc_slice is not None:  # the columns of one raw source of a 1x1 shortcut
+                w = pk["wlog"][wname.rsplit(".sc.", 1)[0] + ".sc"][:, sc_slice[0]: sc_slice[0] + sc_slice[1]]
+            else:
+                w = pk["wlog"][wname]
+            w = w.float()
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            w3 = pk["w3"][key] = torch.cat([hi, hi, lo], dim=1).contiguous()
+        return w3
+
     # ------------------------------------------------------------------------------------------------
     # plans
     # ------------------------------------------------------------------------------------------------
+    precision = os.environ.get("DMC_PRECISION", "bf16")  # "bf16" (default) or "bf16x3": split-bf16, fp32-level accuracy
+
     def _get_plan(self, device, nimg, x_batch, has_y, uniform_t):
-        key = (str(device), nimg, x_batch, has_y, uniform_t)
+        if self.precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"UNet.precision must be 'bf16' or 'bf16x3', got {self.precision!r}")
+        key = (str(device), nimg, x_batch, has_y, uniform_t, self.precision)
         pl = self._plans.get(key)
         if pl is None:
             pk = self._ensure_packed(device)
@@ -529,7 +576,8 @@ class _UNetPlan:
         self.lib = lib
         self.nimg, self.x_batch, self.has_y = nimg, x_batch, has_y
         conv_impl = int(os.environ.get("DMC_DEBUG_CONV_IMPL", "0"))
-        b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl).build()
+        split = net.precision == "bf16x3"
+        b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl, split=split).build()
         self.workspace_bytes = b.arena.peak
         Hh, Ww = net._hw
         R = 1 if uniform_t else nimg
@@ -551,6 +599,9 @@ class _UNetPlan:
 
         def ap(a):
             return wsp + a.blk[0]
+
+        def ap_lo(a):
+            return (wsp + a.lo[0]) if a.lo is not None else None
 
         def add(fn, desc, name):
             idx = _lib.check(fn(handle, C.byref(desc)), name)
@@ -577,39 +628,47 @@ class _UNetPlan:
                 d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
                 d.Cin, d.H, d.W, d.Cout = net.in_channels, Hh, Ww, net.model_channels
                 d.weight, d.bias = sd["input_conv.weight"].data_ptr(), sd["input_conv.bias"].data_ptr()
-                d.out = ap(o["out"])
+                d.out, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 self.stem_idx = add(lib.dmc_plan_add_stem, d, "input_conv")
             elif kind == "gn_stats":
                 a = o["src"]
                 d = _lib.GnStatsDesc()
                 d.src, d.B, d.HW, d.C, d.stats = ap(a), nimg, a.H * a.W, a.C, wsp + a.stats[0]
+                d.src_lo = ap_lo(a)
                 add(lib.dmc_plan_add_gn_stats, d, "gn_stats")
             elif kind == "gn_apply":
                 d = _lib.GnApplyDesc()
                 d.nsrc = len(o["srcs"])
                 for i, s in enumerate(o["srcs"]):
                     d.src[i], d.src_c[i], d.stats[i], d.stats_slots[i] = ap(s), s.C, wsp + s.stats[0], s.slots
+                    d.src_lo[i] = ap_lo(s)
                 d.B, d.HW, d.groups = nimg, o["srcs"][0].H * o["srcs"][0].W, 8
                 d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
-                d.eps, d.silu, d.out = 1e-5, o["silu"], ap(o["out"])
+                d.eps, d.silu, d.out, d.out_lo = 1e-5, o["silu"], ap(o["out"]), ap_lo(o["out"])
                 add(lib.dmc_plan_add_gn_apply, d, o["prefix"])
             elif kind == "conv":
                 d = _lib.ConvDesc()
                 d.nsrc = len(o["srcs"])
                 for i, s in enumerate(o["srcs"]):
-                    d.src[i], d.src_c[i], d.src_taps[i] = ap(s), s.C, o["taps"][i]
+                    d.src[i], d.src_c[i], d.src_taps[i] = (ap_lo(s) if o["parts"][i] == "lo" else ap(s)), s.C, o["taps"][i]
                 d.B, d.Hin, d.Win, d.stride, d.up_phase = nimg, o["H"], o["W"], o["stride"], o["up_phase"]
-                rows, K = pk["wshape"][o["wname"]]
-                d.weight = pk["wblob"].data_ptr() + pk["woffs"][o["wname"]]
+                if split:
+                    w3 = net._split_weight(pk, o["wname"], o["sc_slice"])
+                    rows, K = w3.shape
+                    d.weight = w3.data_ptr()
+                else:
+                    rows, K = pk["wshape"][o["wname"]]
+                    d.weight = pk["wblob"].data_ptr() + pk["woffs"][o["wname"]]
                 d.Cout, d.Cout_pad, d.Ktot = o["Cout"], rows, K
                 d.bias = pk["bias"][o["bias"]].data_ptr() if o["bias"] is not None else None
                 if o["cond_col"] is not None:
                     d.cond, d.cond_stride = self.cond.data_ptr() + 4 * o["cond_col"], ncols
                 d.residual = ap(o["residual"]) if o["residual"] is not None else None
+                d.residual_lo = ap_lo(o["residual"]) if o["residual"] is not None else None
                 if o["out_nchw"]:
                     d.out_f32_nchw = self.eps.data_ptr()
                 else:
-                    d.out_bf16 = ap(o["out"])
+                    d.out_bf16, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 d.impl = conv_impl
                 if conv_impl == 0 and o["out"] is not None and o["out"].stats is not None and o["want_stats"]:
                     d.stats, d.stats_slots = wsp + o["out"].stats[0], o["out"].slots
@@ -619,6 +678,7 @@ class _UNetPlan:
             elif kind == "attention":
                 d = _lib.AttnDesc()
                 d.qkv, d.out, d.B, d.L, d.heads, d.C = ap(o["qkv"]), ap(o["out"]), nimg, o["L"], 4, o["C"]
+                d.qkv_lo, d.out_lo = ap_lo(o["qkv"]), ap_lo(o["out"])
                 d.impl = int(os.environ.get("DMC_DEBUG_ATTN_IMPL", "0"))
                 add(lib.dmc_plan_add_attention, d, "attention")
             elif kind == "upsample":

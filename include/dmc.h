@@ -170,10 +170,17 @@ typedef struct {
   const float* weight; /* [Cout, Cin, 3, 3] fp32 */
   const float* bias;   /* [Cout] */
   void* out;           /* bf16 [B, H, W, Cout] */
+  void* out_lo;        /* optional: bf16 rounding remainder (value - bf16(value)), see "split-bf16 mode" below */
 } dmc_stem_desc;
 DMC_API int dmc_plan_add_stem(dmc_plan* p, const dmc_stem_desc* d);
 
-/* GroupNorm statistics as deterministic partial sums.  A statistics buffer is fp32 [B, slots, C/8, 2]: (sum, sumsq)
+/* Split-bf16 mode ("bf16x3", the fp32-accuracy mode of the UNet): every activation is the SUM of two bf16 tensors, hi =
+ * bf16(v) and lo = bf16(v - hi) (16 mantissa bits together), and every convolution is three bf16 tensor-core products
+ * hi*W_hi + lo*W_hi + hi*W_lo accumulated in fp32 -- expressed with the ordinary multi-source convolution below as the
+ * K-concatenation of the sources (hi, lo, hi) against the weight columns [W_hi | W_hi | W_lo].  The `*_lo` members of the
+ * descriptors carry the low parts; they are NULL in the bf16 mode.
+ *
+ * GroupNorm statistics as deterministic partial sums.  A statistics buffer is fp32 [B, slots, C/8, 2]: (sum, sumsq)
  * of one image over one 8-channel block and one slice ("slot") of its pixels.  Every (image, slot, block) entry is
  * written exactly once with a plain store (no atomics, no pre-zeroing), and the consumer adds the slots in index
  * order -- so results are bit-reproducible and independent of what else is in the batch.
@@ -182,6 +189,7 @@ typedef struct {
   const void* src; /* bf16 [B, HW, C] */
   int32_t B, HW, C;
   float* stats;    /* [B, ceil(HW/128), C/8, 2] */
+  const void* src_lo; /* optional low part: the tensor value is src + src_lo */
 } dmc_gn_stats_desc;
 DMC_API int dmc_plan_add_gn_stats(dmc_plan* p, const dmc_gn_stats_desc* d);
 
@@ -199,6 +207,8 @@ typedef struct {
   float eps;
   int32_t silu;
   void* out;              /* bf16 [B, HW, C] */
+  const void* src_lo[2];  /* optional low parts of the sources (value = src + src_lo) */
+  void* out_lo;           /* optional low part of the output */
 } dmc_gn_apply_desc;
 DMC_API int dmc_plan_add_gn_apply(dmc_plan* p, const dmc_gn_apply_desc* d);
 
@@ -239,6 +249,8 @@ typedef struct {
   const float* residual_f32;  /* fp32 NHWC residual stream [B, Hout, Wout, Cout] or NULL (exclusive with `residual`) */
   float* out_f32_nhwc;        /* fp32 NHWC output (may alias residual_f32: each element is read then written by the same
                                  thread) or NULL */
+  void* out_lo;               /* optional low part of out_bf16 (split-bf16 mode; per-thread stores, no TMA epilogue) */
+  const void* residual_lo;    /* optional low part of `residual` */
   int32_t unpatch_p;          /* > 0 with out_f32_nchw: columns are (pi, qi, c) of a p x p patch and pixel (i, j) of image n
                                  scatters to out[n, c, i*p + pi, j*p + qi] -- DiT.unpatchify (models/dit.py:249-261);
                                  Cout = p * p * channels */
@@ -253,6 +265,8 @@ typedef struct {
   int32_t B, L, heads, C;
   int32_t impl; /* 0: tcgen05/TMA kernel (head dim 64, L in {16, 32, 64, 128, 256}; other shapes run the CUDA-core
                    flash kernel)   1: force the CUDA-core flash kernel (tests / debugging) */
+  const void* qkv_lo; /* optional low parts (split-bf16 mode): fp32 CUDA-core kernel on qkv + qkv_lo, writes out + out_lo */
+  void* out_lo;
 } dmc_attn_desc;
 DMC_API int dmc_plan_add_attention(dmc_plan* p, const dmc_attn_desc* d);
 

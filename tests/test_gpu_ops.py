@@ -349,3 +349,46 @@ def test_bad_arguments_are_reported_not_crashed():
     with pytest.raises(_lib.DmcError):
         p.add("conv", d)
     assert b"conv" in lib.dmc_last_error()
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("cin,cout,H,B,k", [(128, 128, 32, 2, 3), (256, 256, 16, 3, 3), (256, 256, 8, 2, 3), (256, 768, 16, 2, 1),
+                                            (64, 64, 32, 1, 3)])
+def test_conv_split_bf16_three_products(cin, cout, H, B, k):
+    """split-bf16 mode of one convolution: sources (hi, lo, hi) against [W_hi | W_hi | W_lo], residual and output as
+    (hi, lo) pairs -> fp32-level accuracy (relative L2 < 2e-5 vs the fp32 convolution of the fp32 operands)"""
+    x = _rand((B, cin, H, H), 1)
+    w = _rand((cout, cin, k, k), 2, (cin * k * k) ** -0.5)
+    bias = _rand((cout,), 3, 0.1)
+    res = _rand((B, cout, H, H), 4)
+    ref = F.conv2d(x, w, bias, padding=k // 2) + res
+    xh, xl = _split(x.permute(0, 2, 3, 1).contiguous())
+    rh, rl = _split(res.permute(0, 2, 3, 1).contiguous())
+    wm = pack3(w) if k == 3 else w.reshape(cout, cin)
+    wh = wm.to(torch.bfloat16)
+    wl = (wm - wh.float()).to(torch.bfloat16)
+    w3 = torch.cat([wh, wh, wl], dim=1).contiguous()
+    from diffusion_models_collection_b200 import _lib
+    d = _lib.ConvDesc()
+    d.nsrc = 3
+    for i, s in enumerate((xh, xl, xh)):
+        d.src[i], d.src_c[i], d.src_taps[i] = s.data_ptr(), cin, k * k
+    d.B, d.Hin, d.Win, d.stride, d.up_phase = B, H, H, 1, -1
+    d.weight, d.Cout, d.Cout_pad, d.Ktot = w3.data_ptr(), cout, cout, w3.shape[1]
+    d.bias, d.residual, d.residual_lo = bias.data_ptr(), rh.data_ptr(), rl.data_ptr()
+    oh = torch.full((B, H, H, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ol = torch.full_like(oh, float("nan"))
+    st = torch.full((B, max(1, H * H // 32), cout // 8, 2), float("nan"), device="cuda")
+    d.out_bf16, d.out_lo, d.stats, d.stats_slots = oh.data_ptr(), ol.data_ptr(), st.data_ptr(), st.shape[1]
+    p = Plan()
+    p.add("conv", d)
+    p.run()
+    got = nchw_f32(oh) + nchw_f32(ol)
+    assert torch.isfinite(got).all() and torch.isfinite(st).all()
+    assert rel_l2(got, ref) < 2e-5
+    want_ss = (ref * ref).reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
+    assert rel_l2(st.sum(dim=1)[..., 1], want_ss) < 1e-4
