@@ -81,7 +81,7 @@ class PatchEmbedDesc(C.Structure):
 
 class LnModDesc(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("shift", vp), ("scale", vp),
-                ("mod_stride", C.c_int32), ("eps", C.c_float)]
+                ("mod_stride", C.c_int32), ("eps", C.c_float), ("out_lo", vp)]
 
 
 class AttnDesc(C.Structure):

@@ -164,9 +164,9 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   // ---- kernel variant selection (every switch has an environment override for A/B measurements and tests) ----
   const bool split = d.out_lo != nullptr || d.residual_lo != nullptr;  // split-bf16 (hi, lo) output / residual pairs
   const int epi = d.out_f32_nchw ? 2 : ((d.gate || d.residual_f32 || d.out_f32_nhwc) ? 3 : (d.act ? 1 : (split ? 4 : 0)));
-  if (split && (epi != 4 || !d.out_bf16 || (d.residual_lo && !d.residual))) {
+  if (split && !((epi == 4 || (epi == 1 && !d.residual_lo)) && d.out_bf16 && (!d.residual_lo || d.residual))) {
     delete P;
-    DMC_REQUIRE(false, "conv: out_lo / residual_lo go with a bf16 NHWC output (and residual) of a plain convolution");
+    DMC_REQUIRE(false, "conv: out_lo / residual_lo go with a bf16 NHWC output (and residual) of a plain convolution or linear");
   }
   if ((epi == 1 || epi == 3) && (d.cond || d.residual || d.stats)) {
     delete P;
@@ -228,7 +228,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     const bool f32 = epi == 3;
     const int boxc = f32 ? 32 : 64;
     void* optr = f32 ? static_cast<void*>(d.out_f32_nhwc) : d.out_bf16;
-    if (want && epi != 2 && epi != 4 && optr != nullptr && d.Cout % boxc == 0 && BN >= 128) {
+    if (want && epi != 2 && epi != 4 && !split && optr != nullptr && d.Cout % boxc == 0 && BN >= 128) {
       const int qbw = std::min(BW, 32), qbh = std::min(BH, 32 / qbw), qbn = 32 / (qbw * qbh);
       const int os = kp.oscale;
       const size_t es = f32 ? 4 : 2;

@@ -640,7 +640,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
               o4[j] = u;
-              if (EPI == 4 && p.out_lo != nullptr) {  // lo = bf16(v - hi): 16 mantissa bits in the pair
+              if ((EPI == 4 || EPI == 1) && p.out_lo != nullptr) {  // lo = bf16(v - hi): 16 mantissa bits in the pair
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
                 uint32_t lo[4];
 #pragma unroll

@@ -230,6 +230,7 @@ int launch_patch_embed(const dmc_patch_embed_desc& d, cudaStream_t st) {
 // =============================================================================================
 template <int V4>  // float4 per lane: C = 128 * V4
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          __nv_bfloat16* __restrict__ out_lo,
                                                           const float* __restrict__ shift, const float* __restrict__ scale,
                                                           int mod_stride, size_t tokens, int L, float eps) {
   constexpr int C = 128 * V4;
@@ -267,7 +268,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
     const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + sc.y, sh.y);
     const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + sc.z, sh.z);
     const float y3 = fmaf((v[i].w - mean) * rstd, 1.0f + sc.w, sh.w);
-    o2[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    const uint2 hi = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    o2[lane + 32 * i] = hi;
+    if (out_lo != nullptr) {  // split-bf16 mode: the rounding remainder
+      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+      reinterpret_cast<uint2*>(out_lo + tok * C)[lane + 32 * i] =
+          make_uint2(pack_bf16x2(y0 - h0.x, y1 - h0.y), pack_bf16x2(y2 - h1.x, y3 - h1.y));
+    }
   }
 }
 
@@ -278,7 +285,8 @@ int launch_ln_modulate(const dmc_ln_mod_desc& d, cudaStream_t st) {
   const size_t tokens = static_cast<size_t>(d.B) * d.L;
   const int blocks = static_cast<int>((tokens + 7) / 8);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
-#define LNM(V) ln_modulate_kernel<V><<<blocks, 256, 0, st>>>(d.x, out, d.shift, d.scale, d.mod_stride, tokens, d.L, d.eps)
+  __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+#define LNM(V) ln_modulate_kernel<V><<<blocks, 256, 0, st>>>(d.x, out, out_lo, d.shift, d.scale, d.mod_stride, tokens, d.L, d.eps)
   switch (d.C / 128) {
     case 1: LNM(1); break;
     case 2: LNM(2); break;

@@ -30,6 +30,7 @@ from .unet import _register, _round_up
 class DiT(nn.Module):
     graph_capturable = True  # a forward is a fixed, allocation-free, sync-free launch list (samplers capture it)
     max_tokens_per_launch = 2048 * 256  # larger batches are processed in chunks
+    precision = os.environ.get("DMC_PRECISION", "bf16")  # "bf16" or "bf16x3" (split-bf16, fp32-level accuracy; see UNet)
 
     def __init__(self, img_size: Tuple[int, int] = (32, 32), patch_size=2, in_channels=3, hidden_size=768, depth=12,
                  num_heads=12, mlp_ratio=4.0, num_classes=None, dropout=0.1):
@@ -127,6 +128,7 @@ class DiT(nn.Module):
         # models/dit.py:44-45, the reference's own expression (divisor `half`, fp32 arange on the CPU, then moved)
         freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device)
         self._packed = dict(
+            wlog=dict(W), w3={},
             sd=sd, wblob=wblob, woffs=offs, wshape={k: tuple(v.shape) for k, v in W.items()}, bias=Bv,
             w_all=torch.cat(w_all, dim=0).contiguous(), b_all=torch.cat(b_all, dim=0).contiguous(), freqs=freqs.contiguous(),
             patch_wT=sd["x_embedder.proj.weight"].reshape(hs, c * p * p).t().contiguous(),
@@ -139,7 +141,9 @@ class DiT(nn.Module):
         return self._packed
 
     def _get_plan(self, device, nimg, x_batch, has_y, uniform_t):
-        key = (str(device), nimg, x_batch, has_y, uniform_t)
+        if self.precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"DiT.precision must be 'bf16' or 'bf16x3', got {self.precision!r}")
+        key = (str(device), nimg, x_batch, has_y, uniform_t, self.precision)
         pl = self._plans.get(key)
         if pl is None:
             pl = _DiTPlan(self, self._ensure_packed(device), device, nimg, x_batch, has_y, uniform_t)
@@ -235,11 +239,14 @@ class _DiTPlan:
         if hs % 128 != 0 or hid % 64 != 0:
             raise _lib.DmcError(f"native DiT needs hidden_size % 128 == 0 and mlp hidden % 64 == 0 (got {hs}, {hid})")
         f32, bf16 = torch.float32, torch.bfloat16
+        split = net.precision == "bf16x3"
         self.tok = torch.empty((nimg, L, hs), dtype=f32, device=device)
         self.hb = torch.empty((nimg, L, hs), dtype=bf16, device=device)
         self.qkv = torch.empty((nimg, L, 3 * hs), dtype=bf16, device=device)
         self.ao = torch.empty((nimg, L, hs), dtype=bf16, device=device)
         self.mlp = torch.empty((nimg, L, hid), dtype=bf16, device=device)
+        # split-bf16 mode: the low parts of every bf16 GEMM operand
+        self.lo = {id(t): torch.empty_like(t) for t in (self.hb, self.qkv, self.ao, self.mlp)} if split else {}
         self.mod = torch.empty((nimg, ncols), dtype=f32, device=device)
         R = ((net.num_classes + 1) if has_y else 1) if uniform_t else nimg
         self.scratch = torch.empty((R * (2 * hs + ncols),), dtype=f32, device=device)
@@ -283,15 +290,26 @@ class _DiTPlan:
             d.x, d.out, d.B, d.L, d.C = self.tok.data_ptr(), self.hb.data_ptr(), nimg, L, hs
             d.shift, d.scale = self.mod.data_ptr() + 4 * col_shift, self.mod.data_ptr() + 4 * col_scale
             d.mod_stride, d.eps = ncols, 1e-6
+            if split:
+                d.out_lo = self.lo[id(self.hb)].data_ptr()
             add(lib.dmc_plan_add_ln_modulate, d, name)
 
         def gemm(src, cin, wname, cout, name, out_bf16=None, act=0, gate_col=None, head=False):
             d = _lib.ConvDesc()
-            d.nsrc = 1
-            d.src[0], d.src_c[0], d.src_taps[0] = src.data_ptr(), cin, 1
             d.B, d.Hin, d.Win, d.stride, d.up_phase = nimg, Ht, Wt, 1, -1
-            rows, K = pk["wshape"][wname]
-            d.weight = pk["wblob"].data_ptr() + pk["woffs"][wname]
+            if split:  # hi*W_hi + lo*W_hi + hi*W_lo as three K segments
+                from .unet import UNet
+                w3 = UNet._split_weight(pk, wname)
+                d.nsrc = 3
+                for i_, t_ in enumerate((src, self.lo[id(src)], src)):
+                    d.src[i_], d.src_c[i_], d.src_taps[i_] = t_.data_ptr(), cin, 1
+                rows, K = w3.shape
+                d.weight = w3.data_ptr()
+            else:
+                d.nsrc = 1
+                d.src[0], d.src_c[0], d.src_taps[0] = src.data_ptr(), cin, 1
+                rows, K = pk["wshape"][wname]
+                d.weight = pk["wblob"].data_ptr() + pk["woffs"][wname]
             d.Cout, d.Cout_pad, d.Ktot = cout, rows, K
             d.bias = pk["bias"][wname].data_ptr()
             d.act = act
@@ -302,6 +320,8 @@ class _DiTPlan:
                 d.residual_f32, d.out_f32_nhwc = self.tok.data_ptr(), self.tok.data_ptr()
             else:
                 d.out_bf16 = out_bf16.data_ptr()
+                if split:
+                    d.out_lo = self.lo[id(out_bf16)].data_ptr()
             return add(lib.dmc_plan_add_conv, d, name)
 
         for i in range(depth):
@@ -310,6 +330,8 @@ class _DiTPlan:
             gemm(self.hb, hs, b + ".qkv", 3 * hs, b + ".qkv", out_bf16=self.qkv)
             a = _lib.AttnDesc()
             a.qkv, a.out, a.B, a.L, a.heads, a.C = self.qkv.data_ptr(), self.ao.data_ptr(), nimg, L, heads, hs
+            if split:
+                a.qkv_lo, a.out_lo = self.lo[id(self.qkv)].data_ptr(), self.lo[id(self.ao)].data_ptr()
             a.impl = int(os.environ.get("DMC_DEBUG_ATTN_IMPL", "0"))
             add(lib.dmc_plan_add_attention, a, b + ".attention")
             gemm(self.ao, hs, b + ".out", hs, b + ".out_proj", gate_col=base + 2 * hs)

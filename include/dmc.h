@@ -321,6 +321,7 @@ typedef struct {
   const float* scale;
   int32_t mod_stride;
   float eps;
+  void* out_lo;        /* optional low part of the output (split-bf16 mode) */
 } dmc_ln_mod_desc;
 DMC_API int dmc_plan_add_ln_modulate(dmc_plan* p, const dmc_ln_mod_desc* d);
 

@@ -343,3 +343,22 @@ def test_dit_ddim50_teacher_forced_along_reference_trajectory(golden):
         with open("gpurun_out/eps_errors.txt", "a") as fh:
             fh.write(f"ddim50_{name} teacher_forced_step_maxabs {worst:.4e} free_running_final_maxabs {mx:.4e}\n")
     assert mx <= 2.0
+
+
+@pytest.mark.parametrize("name", list(DIT_CASES))
+def test_dit_eps_split_bf16_mode_vs_reference_golden(golden, name):
+    """the fp32-accuracy mode (DiT.precision = "bf16x3": (hi, lo) bf16 operand pairs, three tensor-core products per
+    linear, fp32 attention) against the reference's fp32 eps: relative L2 <= 1e-3 (BASELINE.json north_star)"""
+    c = DIT_CASES[name]
+    net = build_dit(c["num_classes"], c["wseed"])
+    net.precision = "bf16x3"
+    x, t, y = case_inputs(c)
+    with torch.no_grad():
+        eps = net(x.cuda(), t.cuda(), None if y is None else y.cuda())
+    err = rel_l2(eps, torch.from_numpy(golden["dit"][name]))
+    print(f"dit {name}: split-bf16 eps rel-L2 vs reference = {err:.3e}")
+    import os
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/eps_errors.txt", "a") as fh:
+            fh.write(f"split_bf16_dit_{name} {err:.4e}\n")
+    assert torch.isfinite(eps).all() and err < 1e-3
