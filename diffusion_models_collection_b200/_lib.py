@@ -79,6 +79,12 @@ class PatchEmbedDesc(C.Structure):
                 ("patch", C.c_int32), ("hidden", C.c_int32), ("weight", vp), ("bias", vp), ("pos", vp), ("out", vp)]
 
 
+class HeadDesc(C.Structure):
+    _fields_ = [("src", vp), ("stats", vp), ("stats_slots", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("C", C.c_int32), ("Cout", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
+                ("weight", vp), ("bias", vp), ("out", vp), ("wfrag", vp)]
+
+
 class LnModDesc(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("shift", vp), ("scale", vp),
                 ("mod_stride", C.c_int32), ("eps", C.c_float), ("out_lo", vp)]
@@ -131,13 +137,15 @@ SYMBOLS = {
     "dmc_plan_add_dit_cond": (C.c_int, [vp, C.POINTER(DitCondDesc)]),
     "dmc_plan_add_patch_embed": (C.c_int, [vp, C.POINTER(PatchEmbedDesc)]),
     "dmc_plan_add_ln_modulate": (C.c_int, [vp, C.POINTER(LnModDesc)]),
+    "dmc_plan_add_head": (C.c_int, [vp, C.POINTER(HeadDesc)]),
+    "dmc_head_supported": (C.c_int, [C.POINTER(HeadDesc)]),
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
 }
 
 OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm", "dit_cond",
-            "patch_embed", "ln_modulate"]
+            "patch_embed", "ln_modulate", "head"]
 
 _lock = threading.Lock()
 _lib = None

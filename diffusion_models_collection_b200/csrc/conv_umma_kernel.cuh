@@ -518,8 +518,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += add[j];
           if (EPI == 1 && p.act == 1) {
+            if (p.out_lo != nullptr) {  // accuracy mode: the two-SFU-op form (max abs error 2.5e-5)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            }
           }
           if (EPI == 3 && p.gate != nullptr && valid) {
             const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(n) * p.gate_stride + cg);

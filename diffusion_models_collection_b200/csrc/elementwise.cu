@@ -501,3 +501,212 @@ int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st) {
 }
 
 }  // namespace dmc
+
+namespace dmc {
+
+// =============================================================================================
+// Output head, fused: GroupNorm apply + SiLU + 3x3 convolution C -> Cout <= 8 (+bias) -> fp32 NCHW
+// (/root/reference/models/unet.py:237-241, 287-292).  With 3 output channels the layer is memory-bound (read the
+// activation once: 256 B per pixel): on the tcgen05 path it needs N padded to 32 and a separate GroupNorm pass
+// (0.55 + 0.20 ms per 2048 images); here one CTA normalises a (TH+2) x (W+2) halo tile into shared memory once and
+// each warp runs mma.sync m16n8k16 (N = 8 covers the 3 channels) over the 9 taps -- the tensor work is negligible,
+// the kernel runs at the speed of its single read of the input.
+// =============================================================================================
+constexpr int HEAD_TH = 8;        // output rows per CTA (one per warp)
+constexpr int HEAD_THREADS = 256;
+
+struct HeadArgs {
+  const uint4* src;      // bf16 [B, H, W, C]
+  const float* stats;    // [B, slots, C/8, 2]
+  const float* gamma;
+  const float* beta;
+  const float* weight;   // fp32 [Cout, C, 3, 3]
+  const float* bias;     // [Cout]
+  uint2* wfrag;          // [9 * C/16][32]: the weights as mma.m16n8k16 B fragments (written by head_pack_kernel)
+  float* out;            // fp32 [B, Cout, H, W]
+  int H, W, C, Cout, groups, slots;
+  float eps;
+};
+
+// weight fragments of mma.m16n8k16 (B col-major 16 x 8): lane holds k = 2 (lane % 4) + {0, 1} (+8), n = lane / 4
+__global__ void __launch_bounds__(256) head_pack_kernel(HeadArgs a) {
+  const int CB = a.C / 16;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * CB * 32) return;
+  const int ks = e >> 5, l = e & 31;
+  const int tap = ks / CB, cb = ks % CB;
+  const int nn = l >> 2, k0 = cb * 16 + (l & 3) * 2;
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nn < a.Cout) {
+    const float* wp = a.weight + (static_cast<size_t>(nn) * a.C) * 9 + tap;
+    w[0] = __ldg(wp + static_cast<size_t>(k0) * 9);
+    w[1] = __ldg(wp + static_cast<size_t>(k0 + 1) * 9);
+    w[2] = __ldg(wp + static_cast<size_t>(k0 + 8) * 9);
+    w[3] = __ldg(wp + static_cast<size_t>(k0 + 9) * 9);
+  }
+  a.wfrag[e] = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+}
+
+template <int C, int W>  // compile-time geometry: the index arithmetic below is shifts and constant divisions
+__global__ void __launch_bounds__(HEAD_THREADS) head_fused_kernel(HeadArgs a) {
+  extern __shared__ __align__(16) uint8_t hsm[];
+  constexpr int C8 = C / 8, CB = C / 16;
+  constexpr int pitch = C * 2 + 16;                // bytes per halo pixel: +16 keeps ldmatrix rows on distinct banks
+  uint8_t* tile = hsm;                             // (TH+2) x (W+2) pixels
+  uint2* bfrag = reinterpret_cast<uint2*>(tile + (HEAD_TH + 2) * (W + 2) * pitch);  // [9 * CB][32]
+  float* s_sc = reinterpret_cast<float*>(bfrag + 9 * CB * 32);                      // [C] scale / 2, shift / 2
+  float* s_sh = s_sc + C;
+  __shared__ float s_mean[32], s_rstd[32];
+  const int n = blockIdx.y, y0 = blockIdx.x * HEAD_TH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // phase 0: group statistics of image n from the partial sums (fixed order -> bit-reproducible); weight fragments
+  const int gs8 = C8 / a.groups;
+  for (int g = warp; g < a.groups; g += HEAD_THREADS / 32) {
+    const float2* base = reinterpret_cast<const float2*>(a.stats) + static_cast<size_t>(n) * a.slots * C8;
+    float s = 0.f, ss = 0.f;
+    for (int e = lane; e < gs8 * a.slots; e += 32) {
+      const float2 v = __ldg(base + static_cast<size_t>(e / gs8) * C8 + g * gs8 + e % gs8);
+      s += v.x;
+      ss += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    }
+    if (lane == 0) {
+      const float inv_cnt = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.H * a.W));
+      const float mean = s * inv_cnt;
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + a.eps);
+    }
+  }
+  for (int e = threadIdx.x; e < 9 * CB * 32; e += HEAD_THREADS) bfrag[e] = __ldg(a.wfrag + e);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += HEAD_THREADS) {
+    const int g = (c / 8) / gs8;
+    const float s1 = s_rstd[g] * __ldg(a.gamma + c);
+    s_sc[c] = 0.5f * s1;                                   // SiLU(y) = h + h tanh(h), h = y / 2
+    s_sh[c] = 0.5f * (__ldg(a.beta + c) - s_mean[g] * s1);
+  }
+  __syncthreads();
+  // phase 1: halo tile, normalised + SiLU, bf16; pixels outside the image are the convolution's zero padding.
+  // Four independent 128-bit loads in flight per thread.
+  constexpr int HP = HEAD_TH + 2, WP = W + 2;
+  constexpr int total = HP * WP * C8;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * HEAD_THREADS) {
+    uint4 v[4];
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * HEAD_THREADS;
+      const int cb = e % C8, px = e / C8;
+      const int iy = y0 + px / WP - 1, ix = px % WP - 1;
+      in[u] = e < total && iy >= 0 && iy < a.H && ix >= 0 && ix < W;
+      if (in[u]) v[u] = __ldg(a.src + ((static_cast<size_t>(n) * a.H + iy) * W + ix) * C8 + cb);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * HEAD_THREADS;
+      if (e >= total) continue;
+      const int cb = e % C8, px = e / C8;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (in[u]) {
+        const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(wv[j]);
+          const int c = cb * 8 + 2 * j;
+          r[j] = pack_bf16x2(silu_from_half(fmaf(f.x, s_sc[c], s_sh[c])), silu_from_half(fmaf(f.y, s_sc[c + 1], s_sh[c + 1])));
+        }
+        o = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+      *reinterpret_cast<uint4*>(tile + px * pitch + cb * 16) = o;
+    }
+  }
+  __syncthreads();
+  // phase 2: warp = output row, W / 16 m16 tiles per row
+  const int y = y0 + warp;
+  if (y >= a.H) return;
+  const uint32_t tile_s = smem_u32(tile);
+  for (int mt = 0; mt < W / 16; ++mt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+      const uint32_t rowaddr = tile_s + ((warp + dy) * WP + mt * 16 + (lane & 15) + dx) * pitch + (lane >> 4) * 16;
+#pragma unroll 4
+      for (int cb = 0; cb < CB; ++cb) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(rowaddr + cb * 32));
+        const uint2 b = bfrag[(tap * CB + cb) * 32 + lane];
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+            "{%0, %1, %2, %3};"
+            : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+      }
+    }
+    // D fragment: rows lane / 4 (+8), columns 2 (lane % 4) + {0, 1}
+    const int c0 = (lane & 3) * 2;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int x = mt * 16 + (lane >> 2) + half * 8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = c0 + j;
+        if (c < a.Cout)
+          a.out[((static_cast<size_t>(n) * a.Cout + c) * a.H + y) * W + x] = acc[half * 2 + j] + __ldg(a.bias + c);
+      }
+    }
+  }
+}
+
+static size_t head_smem(int C, int W) {
+  return static_cast<size_t>(HEAD_TH + 2) * (W + 2) * (C * 2 + 16) + static_cast<size_t>(9) * (C / 16) * 32 * 8 +
+         static_cast<size_t>(2) * C * 4;
+}
+
+// instantiated geometries: the UNet heads of the reference's configs (model_channels 64 / 128, 16..64-pixel rows)
+bool head_fused_supported(const dmc_head_desc& d) {
+  return (d.C == 64 || d.C == 128) && (d.W == 16 || d.W == 32 || d.W == 64) && d.Cout >= 1 && d.Cout <= 8 && d.groups > 0 &&
+         d.groups <= 32 && (d.C / 8) % d.groups == 0 && head_smem(d.C, d.W) <= 200 * 1024;
+}
+
+template <int C, int W>
+static int launch_head_t(const HeadArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMC_CUDA_OK(cudaFuncSetAttribute(head_fused_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  head_fused_kernel<C, W><<<grid, HEAD_THREADS, smem, st>>>(a);
+  return 0;
+}
+
+int launch_head_fused(const dmc_head_desc& d, cudaStream_t st) {
+  DMC_REQUIRE(d.src && d.stats && d.gamma && d.beta && d.weight && d.bias && d.out && d.wfrag, "head: null pointer argument");
+  DMC_REQUIRE(head_fused_supported(d), "head: unsupported shape (C=%d W=%d Cout=%d groups=%d)", d.C, d.W, d.Cout, d.groups);
+  DMC_REQUIRE(d.B > 0 && d.H > 0 && d.stats_slots > 0, "head: empty input");
+  HeadArgs a;
+  a.src = reinterpret_cast<const uint4*>(d.src);
+  a.stats = d.stats; a.gamma = d.gamma; a.beta = d.beta; a.weight = d.weight; a.bias = d.bias; a.out = d.out;
+  a.wfrag = reinterpret_cast<uint2*>(d.wfrag);
+  a.H = d.H; a.W = d.W; a.C = d.C; a.Cout = d.Cout; a.groups = d.groups; a.slots = d.stats_slots; a.eps = d.eps;
+  const size_t smem = head_smem(d.C, d.W);
+  const int nfrag = 9 * (d.C / 16) * 32;
+  head_pack_kernel<<<(nfrag + 255) / 256, 256, 0, st>>>(a);  // weights -> B fragments (the caller may have updated them)
+  dim3 grid((d.H + HEAD_TH - 1) / HEAD_TH, d.B);
+  int rc = -1;
+#define DMC_HEAD(CC, WW) if (d.C == CC && d.W == WW) rc = launch_head_t<CC, WW>(a, grid, smem, st)
+  DMC_HEAD(64, 16); DMC_HEAD(64, 32); DMC_HEAD(64, 64); DMC_HEAD(128, 16); DMC_HEAD(128, 32); DMC_HEAD(128, 64);
+#undef DMC_HEAD
+  if (rc != 0) return rc;
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dmc

@@ -23,6 +23,8 @@ int launch_stem(const dmc_stem_desc& d, cudaStream_t st);
 int launch_gn_stats(const dmc_gn_stats_desc& d, cudaStream_t st);
 int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st);
 int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
+int launch_head_fused(const dmc_head_desc& d, cudaStream_t st);
+bool head_fused_supported(const dmc_head_desc& d);
 
 // dit_ops.cu
 int launch_dit_cond(const dmc_dit_cond_desc& d, cudaStream_t st);

@@ -26,7 +26,7 @@ int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 
 enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM,
-              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD };
+              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD };
 
 struct Op {
   int kind;
@@ -43,6 +43,7 @@ struct Op {
     dmc_dit_cond_desc dit_cond;
     dmc_patch_embed_desc patch;
     dmc_ln_mod_desc ln_mod;
+    dmc_head_desc head;
   };
   ConvPrepared* conv_prep;
   AttnPrepared* attn_prep;
@@ -77,6 +78,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_DIT_COND: return launch_dit_cond(op.dit_cond, st);
     case OP_PATCH_EMBED: return launch_patch_embed(op.patch, st);
     case OP_LN_MOD: return launch_ln_modulate(op.ln_mod, st);
+    case OP_HEAD: return launch_head_fused(op.head, st);
   }
   set_error("plan: unknown op kind %d", op.kind);
   return -1;
@@ -196,7 +198,7 @@ int dmc_plan_num_launches(const dmc_plan* p) {
   if (!p) return -1;
   int n = 0;
   for (const auto& op : p->ops)
-    n += (op.kind == OP_COND) ? cond_num_launches(op.cond) : (op.kind == OP_DIT_COND ? dit_cond_num_launches(op.dit_cond) : 1);
+    n += (op.kind == OP_HEAD) ? 2 : (op.kind == OP_COND) ? cond_num_launches(op.cond) : (op.kind == OP_DIT_COND ? dit_cond_num_launches(op.dit_cond) : 1);
   return n;
 }
 
@@ -213,6 +215,7 @@ int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* pt
   if (op.kind == OP_STEM && which == 0) { op.stem.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 0) { op.cond.t = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 1) { op.cond.y = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_HEAD && which == 2 && ptr != nullptr) { op.head.out = static_cast<float*>(const_cast<void*>(ptr)); return 0; }
   if (op.kind == OP_PATCH_EMBED && which == 0) { op.patch.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_DIT_COND && which == 0) { op.dit_cond.t = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_DIT_COND && which == 1) { op.dit_cond.y = static_cast<const int64_t*>(ptr); return 0; }
@@ -363,6 +366,20 @@ int dmc_plan_add_ln_modulate(dmc_plan* p, const dmc_ln_mod_desc* d) {
   op.kind = OP_LN_MOD;
   op.ln_mod = *d;
   op.bytes = 6.0 * d->B * static_cast<double>(d->L) * d->C;  // fp32 in, bf16 out
+  return push(p, op);
+}
+
+int dmc_head_supported(const dmc_head_desc* d) { return (d != nullptr && head_fused_supported(*d)) ? 1 : 0; }
+
+int dmc_plan_add_head(dmc_plan* p, const dmc_head_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_head: null argument");
+  DMC_REQUIRE(head_fused_supported(*d), "dmc_plan_add_head: unsupported shape (C=%d W=%d Cout=%d)", d->C, d->W, d->Cout);
+  Op op;
+  op.kind = OP_HEAD;
+  op.head = *d;
+  const double pix = static_cast<double>(d->B) * d->H * d->W;
+  op.bytes = pix * (2.0 * d->C + 4.0 * d->Cout);
+  op.flops = 2.0 * pix * d->Cout * d->C * 9;
   return push(p, op);
 }
 

@@ -121,14 +121,14 @@ DMC_API int dmc_plan_num_launches(const dmc_plan* p);
 DMC_API double dmc_plan_gemm_flops(const dmc_plan* p);
 /* Re-point one external binding of op `op_index` (returned by dmc_plan_add_*):
  *   which = 0: primary input  (stem / patch_embed: x, cond / dit_cond: t)     which = 1: secondary input (cond: y, may be NULL)
- *   which = 2: primary output (conv: out_f32_nchw)                                                     */
+ *   which = 2: primary output (conv: out_f32_nchw, head: out)                                                     */
 DMC_API int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr);
 /* Per-op device timing: runs every op `iters` times between CUDA events on `stream`, writes the average
  * milliseconds per op into ms_out[num ops].  Debug / profiling aid used by bench.py's roofline leg. */
 DMC_API int dmc_plan_time_ops(dmc_plan* p, void* stream, int32_t iters, float* ms_out, int32_t n_out);
 DMC_API int dmc_plan_num_ops(const dmc_plan* p);
 /* kind of op i: 0 memset, 1 cond, 2 stem, 3 gn_stats, 4 gn_apply, 5 conv, 6 attention, 7 upsample, 8 ddim, 9 ddpm,
- * 10 dit_cond, 11 patch_embed, 12 ln_modulate */
+ * 10 dit_cond, 11 patch_embed, 12 ln_modulate, 13 head */
 DMC_API int dmc_plan_op_kind(const dmc_plan* p, int32_t i);
 DMC_API double dmc_plan_op_flops(const dmc_plan* p, int32_t i);
 DMC_API double dmc_plan_op_bytes(const dmc_plan* p, int32_t i);
@@ -256,6 +256,25 @@ typedef struct {
                                  Cout = p * p * channels */
 } dmc_conv_desc;
 DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
+
+/* Output head, fused: GroupNorm(groups, C) + SiLU + 3x3 convolution C -> Cout (<= 8) + bias, written as the fp32 NCHW
+ * model output (models/unet.py:237-241,287-292).  One read of the activation; replaces a gn_apply + a padded-N conv. */
+typedef struct {
+  const void* src;      /* bf16 [B, H, W, C] (raw, un-normalised) */
+  const float* stats;   /* [B, stats_slots, C/8, 2] partial sums of src */
+  int32_t stats_slots;
+  int32_t B, H, W, C, Cout, groups;
+  const float* gamma;   /* [C] */
+  const float* beta;    /* [C] */
+  float eps;
+  const float* weight;  /* fp32 [Cout, C, 3, 3] (the reference's layout) */
+  const float* bias;    /* [Cout] */
+  float* out;           /* fp32 [B, Cout, H, W] */
+  void* wfrag;          /* caller-owned scratch, 9 * (C/16) * 256 bytes: the weights re-packed as tensor-core fragments */
+} dmc_head_desc;
+DMC_API int dmc_plan_add_head(dmc_plan* p, const dmc_head_desc* d);
+/* 1 when the fused head kernel covers this shape (C % 16 == 0, C <= 256, W % 16 == 0, W <= 64, Cout <= 8) */
+DMC_API int dmc_head_supported(const dmc_head_desc* d);
 
 /* Multi-head self-attention core softmax(Q K^T / sqrt(hd)) V over L tokens (models/unet.py:88-96;
  * models/dit.py:94,123).  qkv: bf16 [B, L, 3*C], channel order [q|k|v][head][hd]; out: bf16 [B, L, C]. */

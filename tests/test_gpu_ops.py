@@ -392,3 +392,38 @@ def test_conv_split_bf16_three_products(cin, cout, H, B, k):
     assert rel_l2(got, ref) < 2e-5
     want_ss = (ref * ref).reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
     assert rel_l2(st.sum(dim=1)[..., 1], want_ss) < 1e-4
+
+
+@pytest.mark.parametrize("C_,H,B,cout", [(128, 32, 3, 3), (64, 32, 2, 3), (128, 16, 2, 1), (64, 64, 1, 8), (128, 32, 1, 4), (128, 64, 1, 3)])
+def test_fused_output_head(C_, H, B, cout):
+    """GroupNorm(8) + SiLU + conv3x3 C -> cout + bias -> fp32 NCHW in one kernel vs PyTorch fp32 on the bf16-rounded input"""
+    from diffusion_models_collection_b200 import _lib
+    x = _q(_rand((B, C_, H, H), 1, 1.5) + 0.3)
+    gamma, beta = _rand((C_,), 2, 0.3) + 1.0, _rand((C_,), 3, 0.2)
+    w, bias = _rand((cout, C_, 3, 3), 4, (C_ * 9) ** -0.5), _rand((cout,), 5, 0.1)
+    ref = F.conv2d(F.silu(F.group_norm(x, 8, gamma, beta, eps=1e-5)), w, bias, padding=1)
+    src = nhwc_bf16(x)
+    slots = (H * H + 127) // 128
+    stats = torch.empty((B, slots, C_ // 8, 2), device="cuda")
+    gs = _lib.GnStatsDesc()
+    gs.src, gs.B, gs.HW, gs.C, gs.stats = src.data_ptr(), B, H * H, C_, stats.data_ptr()
+    out = torch.full((B, cout, H, H), float("nan"), device="cuda")
+    d = _lib.HeadDesc()
+    d.src, d.stats, d.stats_slots, d.B, d.H, d.W, d.C, d.Cout, d.groups = src.data_ptr(), stats.data_ptr(), slots, B, H, H, C_, cout, 8
+    d.gamma, d.beta, d.eps, d.weight, d.bias, d.out = gamma.data_ptr(), beta.data_ptr(), 1e-5, w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    wfrag = torch.empty(9 * (C_ // 16) * 256, dtype=torch.uint8, device="cuda")
+    d.wfrag = wfrag.data_ptr()
+    assert _lib.load().dmc_head_supported(d) == 1
+    p = Plan()
+    p.add("gn_stats", gs)
+    p.add("head", d)
+    p.run()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < TOL_BF16  # normalised activations and weights are rounded to bf16 for the tensor cores
+    out2 = torch.empty_like(out)
+    d.out = out2.data_ptr()
+    p2 = Plan()
+    p2.add("gn_stats", gs)
+    p2.add("head", d)
+    p2.run()
+    assert torch.equal(out, out2)

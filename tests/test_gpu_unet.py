@@ -317,3 +317,19 @@ def test_split_bf16_mode_cfg_sampling_and_batch_invariance():
     torch.manual_seed(3)
     b = d.sample_with_cfg(net, (5, 3, 32, 32), y, cfg_scale=2.0)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_fused_head_path_matches_two_kernel_path(monkeypatch):
+    """the opt-in fused output head (GroupNorm + SiLU + conv3x3 in one kernel) vs the default gn_apply + conv path"""
+    from diffusion_models_collection_b200.models import UNet
+
+    x, t, y = case_inputs(UNET_CASES["cond_labels"])
+    net = build_unet(synth.CIFAR_UNET, 10, 2)
+    with torch.no_grad():
+        a = net(x.cuda(), t.cuda(), y.cuda())
+    monkeypatch.setattr(UNet, "fuse_head", True)
+    net2 = build_unet(synth.CIFAR_UNET, 10, 2)
+    with torch.no_grad():
+        b = net2(x.cuda(), t.cuda(), y.cuda())
+    assert "output.head" in net2.plan_info(4).op_names and "output.head" not in net.plan_info(4).op_names
+    assert rel_l2(a, b) < 3e-3

@@ -12,7 +12,7 @@ run() {  # name, pytest args...
   echo "$name exit $? :: $(tail -1 $OUT/$name.log)" >> $OUT/summary.txt
 }
 run sched tests/test_gpu_sched.py
-for k in conv3x3 conv_kernel_variants conv1x1 shortcut head_conv phase stem groupnorm attention conditioning "upsample_nearest or bad_arguments"; do
+for k in conv3x3 conv_kernel_variants conv_split fused_output_head conv1x1 shortcut head_conv phase stem groupnorm attention conditioning "upsample_nearest or bad_arguments"; do
   run "ops_${k%% *}" tests/test_gpu_ops.py -k "$k"
 done
 run unet tests/test_gpu_unet.py

@@ -27,7 +27,7 @@ def main(metrics_csv, table_json, out_md, title):
     # expand ops to launches: the conditioning ops are 4 launches, everything else 1
     exp = []
     for o in ops:
-        n = 4 if o["kind"] in ("cond", "dit_cond") else 1
+        n = 4 if o["kind"] in ("cond", "dit_cond") else (2 if o["kind"] == "head" else 1)
         for i in range(n):
             exp.append(dict(o, part=i, parts=n))
     assert len(exp) == len(launches), (len(exp), len(launches))
