@@ -227,28 +227,71 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tile_coords(p, t, h, q_row0, key_row0);
       mbar_wait(&s_full[slot], ph);
       tc_fence_after();
+      float m = -INFINITY, sum = 0.f;
+      float ms;
+      if (!SMALL) {
+        // L = 128 / 256: every chunk is live.  TMEM loads are software-pipelined -- the load of chunk c+1 is in flight
+        // while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads, so exactly one is kept in
+        // flight); with two warps per scheduler the ~150-clock load latency of 18 chunks per tile was mostly exposed.
+        uint32_t ra[32], rb[32];
+        // pass 1: row max
+        tmem_ld_32x32(lane_addr, ra);
+#pragma unroll 1
+        for (int c0 = 0; c0 < keys; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld_32x32(lane_addr + c0 + 32, rb);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+          tmem_ld_wait();
+          tmem_ld_32x32(lane_addr + ((c0 + 64 < keys) ? c0 + 64 : 0), ra);  // last iteration: chunk 0 again, for pass 2
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        }
+        ms = m * p.scale_log2e;
+        // pass 2: p = 2^(s * scale - max * scale), row sum, bf16 P into the K-major SWIZZLE_128B operand layout
+        auto emit = [&](const uint32_t (&r)[32], int c0) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms));
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          uint8_t* sub = sPs + (c0 >> 6) * (AT_M * 128) + row * 128;
+          const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk of these 32 keys inside the 128-byte row
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (chunk0 + q4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        };
+#pragma unroll 1
+        for (int c0 = 0; c0 < keys; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld_32x32(lane_addr + c0 + 32, rb);
+          emit(ra, c0);
+          tmem_ld_wait();
+          if (c0 + 64 < keys) tmem_ld_32x32(lane_addr + c0 + 64, ra);
+          emit(rb, c0 + 32);
+        }
+      } else {
       // pass 1: row max
-      float m = -INFINITY;
       for (int c0 = w_lo & ~31; c0 < w_hi; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(lane_addr + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (SMALL) {
-            const int c = c0 + j;
-            if (c >= c_lo && c < c_hi) m = fmaxf(m, __uint_as_float(r[j]));
-          } else {
-            m = fmaxf(m, __uint_as_float(r[j]));
-          }
+          const int c = c0 + j;
+          if (c >= c_lo && c < c_hi) m = fmaxf(m, __uint_as_float(r[j]));
         }
       }
-      const float ms = m * p.scale_log2e;
+      ms = m * p.scale_log2e;
       // pass 2: p = 2^(s * scale - max * scale), row sum, bf16 P into the K-major SWIZZLE_128B operand layout
-      float sum = 0.f;
       for (int c0 = 0; c0 < keys; c0 += 32) {
         uint32_t pk[16];
-        if (SMALL && (c0 + 32 <= w_lo || c0 >= w_hi)) {  // chunk outside every row's block: probabilities are zero
+        if (c0 + 32 <= w_lo || c0 >= w_hi) {  // chunk outside every row's block: probabilities are zero
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = 0u;
         } else {
@@ -259,11 +302,9 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int j = 0; j < 32; j += 2) {
             float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms));
             float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms));
-            if (SMALL) {
-              const int c = c0 + j;
-              e0 = (c >= c_lo && c < c_hi) ? e0 : 0.f;
-              e1 = (c + 1 >= c_lo && c + 1 < c_hi) ? e1 : 0.f;
-            }
+            const int c = c0 + j;
+            e0 = (c >= c_lo && c < c_hi) ? e0 : 0.f;
+            e1 = (c + 1 >= c_lo && c + 1 < c_hi) ? e1 : 0.f;
             sum += e0 + e1;
             pk[j >> 1] = pack_bf16x2(e0, e1);
           }
@@ -276,6 +317,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
       }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[slot]);
@@ -285,11 +327,13 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const float inv = 1.0f / sum;
       const int grow = q_row0 + row;
       __nv_bfloat16* op = p.out + static_cast<size_t>(grow) * p.C + h * AT_HD;
+      uint32_t ro[2][32];
+      tmem_ld_32x32(lane_addr, ro[0]);
+      tmem_ld_32x32(lane_addr + 32, ro[1]);
+      tmem_ld_wait();
 #pragma unroll
       for (int c0 = 0; c0 < AT_HD; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_addr + c0, r);
-        tmem_ld_wait();
+        const uint32_t (&r)[32] = ro[c0 >> 5];
         if (grow < p.total_rows) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
