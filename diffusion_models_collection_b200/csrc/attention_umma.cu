@@ -168,40 +168,56 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
+    // Issue order (software-pipelined so that the two slots run HALF A PERIOD APART: while one slot's warpgroup runs its
+    // exponentials the tensor core works for the other slot -- issued in lock-step, both warpgroups computed at the same
+    // time and the tensor core idled meanwhile, then the warpgroups idled during the MMAs):
+    //   S0(0);  for every item i:  S1(i);  PV0(i);  S0(i+1);  PV1(i)
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_M, keys);
       const uint32_t idesc_o = umma_idesc_bf16(AT_M, AT_HD, /*b_mn_major=*/1);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1u;
-        const int ns = (2 * item + 1 < p.tiles) ? 2 : 1;
-        mbar_wait(k_full, ph);
-        for (int s = 0; s < ns; ++s) {
-          mbar_wait(&q_full[s], ph);
-          mbar_wait(&s_empty[s], ph ^ 1u);
-          tc_fence_after();
-          const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + s * AT_Q_BYTES));
-          const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + s * kv_slot_bytes));
+      auto issue_s = [&](int s, uint32_t ph) {  // S[s] = Q[s] K^T of the item whose phase is ph
+        mbar_wait(&q_full[s], ph);
+        mbar_wait(&s_empty[s], ph ^ 1u);
+        tc_fence_after();
+        const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + s * AT_Q_BYTES));
+        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + s * kv_slot_bytes));
 #pragma unroll
-          for (int k = 0; k < AT_HD / 16; ++k)
-            umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&q_empty[s]);
-          umma_commit(&s_full[s]);
+        for (int k = 0; k < AT_HD / 16; ++k)
+          umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&q_empty[s]);
+        umma_commit(&s_full[s]);
+      };
+      auto issue_pv = [&](int s, uint32_t ph) {  // O[s] = P[s] V
+        mbar_wait(&p_full[s], ph);
+        tc_fence_after();
+        const uint32_t pbase = smem_u32(sP + s * AT_P_BYTES);
+        const uint32_t vbase = smem_u32(sV + s * kv_slot_bytes);
+        for (int j = 0; j < keys / 16; ++j) {
+          const uint64_t pdesc = umma_desc_k_sw128(pbase + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
+          const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
+          umma_bf16(tmem_base + s * 256, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
         }
-        umma_commit(k_empty);
+        umma_commit(&o_full[s]);
+      };
+      uint32_t it = 0;
+      int item = blockIdx.x;
+      if (item < p.items) {
+        mbar_wait(k_full, 0u);
+        issue_s(0, 0u);
+      }
+      for (; item < p.items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        const bool two = 2 * item + 1 < p.tiles;
+        const int next = item + gridDim.x;
+        if (two) issue_s(1, ph);
+        umma_commit(k_empty);  // K(i) has been consumed by S0(i) and S1(i): the producer may load K(i+1)
         mbar_wait(v_full, ph);
-        for (int s = 0; s < ns; ++s) {
-          mbar_wait(&p_full[s], ph);
-          tc_fence_after();
-          const uint32_t pbase = smem_u32(sP + s * AT_P_BYTES);
-          const uint32_t vbase = smem_u32(sV + s * kv_slot_bytes);
-          for (int j = 0; j < keys / 16; ++j) {
-            const uint64_t pdesc = umma_desc_k_sw128(pbase + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
-            const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
-            umma_bf16(tmem_base + s * 256, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
-          }
-          umma_commit(&o_full[s]);
+        issue_pv(0, ph);
+        if (next < p.items) {
+          mbar_wait(k_full, ph ^ 1u);
+          issue_s(0, ph ^ 1u);
         }
+        if (two) issue_pv(1, ph);
         umma_commit(v_empty);
       }
     }
