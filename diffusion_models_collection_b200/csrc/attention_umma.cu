@@ -375,6 +375,222 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long sequences (L a multiple of 256, L > 256: the shipped DiT config has 64 x 64 images = 1024 tokens): the same
+// roles and buffers, flash-style over 256-key tiles.  A work item is the pair of 128-query tiles (slot 0 / 1) of one
+// (image, head); for every key tile:  S = Q K_t^T  ->  running max m, P = 2^(S - m), l = l a + rowsum(P)  ->
+// O_t = P V_t on the tensor core  ->  the thread that owns the row keeps the running output in REGISTERS,
+// O = O a + O_t  (a = 2^(m_old - m_new); no TMEM read-modify-write).  Q stays in shared memory for the whole item.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                      const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * AT_Q_BYTES;
+  uint8_t* sV = sK + AT_KV_BYTES;
+  uint8_t* sP = sV + AT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
+  uint64_t* k_full = bars + 0;
+  uint64_t* k_empty = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_empty = bars + 3;
+  uint64_t* q_full = bars + 4;    // [2]
+  uint64_t* q_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;    // [2]
+  uint64_t* s_empty = bars + 10;  // [2]
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* o_full = bars + 14;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int KT = AT_MAXKEYS;  // keys per tile
+  const int nkt = p.L / KT;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t itq = 0, u = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itq) {
+        int h, qr, kr;
+        tile_coords(p, 2 * item, h, qr, kr);  // both q-tiles of the item belong to the same (image, head)
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&q_empty[s], (itq & 1u) ^ 1u);
+          mbar_expect_tx(&q_full[s], AT_Q_BYTES);
+          tma_load_2d(sQ + s * AT_Q_BYTES, &tmQ, &q_full[s], h * AT_HD, qr + s * AT_M);
+        }
+        for (int kt = 0; kt < nkt; ++kt, ++u) {
+          const uint32_t ph = u & 1u;
+          mbar_wait(k_empty, ph ^ 1u);
+          mbar_expect_tx(k_full, AT_KV_BYTES);
+          tma_load_2d(sK, &tmKV, k_full, p.C + h * AT_HD, kr + kt * KT);
+          mbar_wait(v_empty, ph ^ 1u);
+          mbar_expect_tx(v_full, AT_KV_BYTES);
+          tma_load_2d(sV, &tmKV, v_full, 2 * p.C + h * AT_HD, kr + kt * KT);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_M, KT);
+      const uint32_t idesc_o = umma_idesc_bf16(AT_M, AT_HD, /*b_mn_major=*/1);
+      uint32_t itq = 0, u = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itq) {
+        for (int kt = 0; kt < nkt; ++kt, ++u) {
+          const uint32_t ph = u & 1u;
+          mbar_wait(k_full, ph);
+          for (int s = 0; s < 2; ++s) {
+            if (kt == 0) mbar_wait(&q_full[s], itq & 1u);
+            mbar_wait(&s_empty[s], ph ^ 1u);
+            tc_fence_after();
+            const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + s * AT_Q_BYTES));
+            const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK));
+#pragma unroll
+            for (int k = 0; k < AT_HD / 16; ++k)
+              umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            if (kt == nkt - 1) umma_commit(&q_empty[s]);  // Q is free once its last S product has been read
+            umma_commit(&s_full[s]);
+          }
+          umma_commit(k_empty);
+          mbar_wait(v_full, ph);
+          for (int s = 0; s < 2; ++s) {
+            mbar_wait(&p_full[s], ph);
+            tc_fence_after();
+            const uint32_t pbase = smem_u32(sP + s * AT_P_BYTES);
+            const uint32_t vbase = smem_u32(sV);
+            for (int j = 0; j < KT / 16; ++j) {
+              const uint64_t pdesc = umma_desc_k_sw128(pbase + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
+              const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
+              umma_bf16(tmem_base + s * 256, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
+            }
+            umma_commit(&o_full[s]);
+          }
+          umma_commit(v_empty);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax + running output: warpgroup = slot, thread = query row =====================
+    const int slot = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256;
+    uint8_t* sPs = sP + slot * AT_P_BYTES;
+    uint32_t u = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int h, q_row0, key_row0;
+      tile_coords(p, 2 * item + slot, h, q_row0, key_row0);
+      float m = -INFINITY, l = 0.f;
+      float o[AT_HD];
+#pragma unroll
+      for (int d = 0; d < AT_HD; ++d) o[d] = 0.f;
+      for (int kt = 0; kt < nkt; ++kt, ++u) {
+        const uint32_t ph = u & 1u;
+        mbar_wait(&s_full[slot], ph);
+        tc_fence_after();
+        float mt = -INFINITY;
+        for (int c0 = 0; c0 < KT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mt = fmaxf(mt, __uint_as_float(r[j]));
+        }
+        const float m_new = fmaxf(m, mt);
+        const float alpha = ex2_approx((m - m_new) * p.scale_log2e);  // first tile: 2^(-inf) = 0
+        const float ms = m_new * p.scale_log2e;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < KT; c0 += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld_32x32(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms));
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          uint8_t* sub = sPs + (c0 >> 6) * (AT_M * 128) + row * 128;
+          const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (chunk0 + q4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        }
+        l = fmaf(l, alpha, sum);
+        m = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[slot]);
+        // O_t = P V_t done: fold it into the running output
+        mbar_wait(&o_full[slot], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < AT_HD; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], alpha, __uint_as_float(r[j]));
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[slot]);
+      }
+      const float inv = 1.0f / l;
+      const int grow = q_row0 + row;
+      if (grow < p.total_rows) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(grow) * p.C + h * AT_HD);
+#pragma unroll
+        for (int v = 0; v < AT_HD / 8; ++v) {
+          uint4 w;
+          w.x = pack_bf16x2(o[8 * v] * inv, o[8 * v + 1] * inv);
+          w.y = pack_bf16x2(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
+          w.z = pack_bf16x2(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
+          w.w = pack_bf16x2(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
+          op[v] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   DMC_REQUIRE(fn != nullptr, "attention: cuTensorMapEncodeTiled unavailable -- call dmc_init()");
@@ -392,7 +608,7 @@ static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 bool attention_umma_supported(const dmc_attn_desc& d) {
   if (d.heads <= 0 || d.C != d.heads * AT_HD) return false;
   const int L = d.L;
-  if (L >= AT_M) return L == 128 || L == 256;
+  if (L >= AT_M) return L == 128 || L == 256 || (L > AT_MAXKEYS && L % AT_MAXKEYS == 0);
   return L >= 1 && (AT_M % L) == 0 && L >= 16;  // L in {16, 32, 64}
 }
 
@@ -404,7 +620,7 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
   DMC_REQUIRE(P != nullptr, "attention: out of host memory");
   AttnParams& p = P->p;
   p.L = d.L; p.heads = d.heads; p.C = d.C;
-  p.keys = d.L < AT_M ? AT_M : d.L;
+  p.keys = d.L < AT_M ? AT_M : (d.L > AT_MAXKEYS ? AT_MAXKEYS : d.L);
   p.total_rows = d.B * d.L;
   p.tiles = ((p.total_rows + AT_M - 1) / AT_M) * d.heads;
   p.items = (p.tiles + 1) / 2;
@@ -429,7 +645,14 @@ int launch_attention_umma(const AttnPrepared* P, cudaStream_t st) {
                                      static_cast<int>(AT_SMEM)));
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(AT_SMEM)));
     attr_set = true;
+  }
+  if (P->p.L > AT_MAXKEYS) {
+    attention_long_kernel<<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
+    DMC_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   if (P->p.L < AT_M) attention_umma_kernel<true><<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
   else attention_umma_kernel<false><<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
