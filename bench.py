@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="global batch (images per step); default 4096 (256 for ddpm1000)")
-    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50"],
+    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50", "dit64_ddim50"],
                     help="ddim50_cfg: BASELINE configs[2], the bench line (default); ddpm1000: configs[1] (uncond UNet, DDPM "
                          "1000 steps, batch 256); dit_ddim50: configs[3] (same as --model dit).  The last two are side "
                          "measurements recorded under profiles/, not the headline metric")
@@ -180,7 +180,7 @@ def main():
     if args.workload is None:
         args.workload = "dit_ddim50" if args.model == "dit" else "ddim50_cfg"
     if args.batch is None:
-        args.batch = 256 if args.workload == "ddpm1000" else 4096
+        args.batch = 256 if args.workload in ("ddpm1000", "dit64_ddim50") else 4096
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,13 +210,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    is_dit = args.workload == "dit_ddim50"
+    is_dit = args.workload in ("dit_ddim50", "dit64_ddim50")
+    dit64 = args.workload == "dit64_ddim50"
+    img = 64 if dit64 else 32
     is_ddpm = args.workload == "ddpm1000"
     uncond = is_dit or is_ddpm
     sampler_steps = 1000 if is_ddpm else 50
     if is_dit:
-        net = DiT(**synth.CIFAR_DIT, num_classes=None)
-        net.load_state_dict(synth.make_dit_state_dict(None, None, seed=42))
+        dcfg = dict(synth.CIFAR_DIT, img_size=(img, img))
+        net = DiT(**dcfg, num_classes=None)
+        net.load_state_dict(synth.make_dit_state_dict(dcfg, None, seed=42))
     elif is_ddpm:
         net = UNet(**synth.CIFAR_UNET, num_classes=None)
         net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42))
@@ -235,9 +238,9 @@ def main():
     nb = hi - lo
     g = torch.Generator().manual_seed(42)
     y_host = (torch.randint(0, 10, (B,), generator=g) + 1).pin_memory()
-    xT_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    xT_host = torch.randn(B, 3, img, img, generator=g).pin_memory()
     y_dev, xT_dev = y_host.to(dev), xT_host.to(dev)
-    shape = (B, 3, 32, 32)
+    shape = (B, 3, img, img)
 
     def step_resident():
         if uncond:
@@ -287,19 +290,20 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, nb), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)),
-                    "d2h_bytes_per_step": int(B * 3 * 32 * 32 * 4)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * img * img * 4 + 8)),
+                    "d2h_bytes_per_step": int(B * 3 * img * img * 4)},
             "gpu_launches": int(launches)}
     pk = peaks()
     # 2 forwards per DDIM step (cond + uncond) for the CFG UNet workload, 1 for the unconditional DiT one
-    flops_step = (50 * 12.107e9 * B) if is_dit else ((1000 * 12.632e9 * B) if is_ddpm else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B))
+    flops_step = (50 * (62.855e9 if dit64 else 12.107e9) * B) if is_dit else ((1000 * 12.632e9 * B) if is_ddpm else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B))
     line["model_flops_utilization"] = {"achieved_tflops": flops_step * args.steps / (ms / 1e3) / 1e12 / world,
                                        "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
 
     if is_dit:
         line["metric"] = "ddim50_dit_cifar10_images_per_sec"
-        line["config"]["workload"] = ("DiT patch-2 (hidden 384, depth 12, 6 heads) 32x32 unconditional, DDIM-50 "
-                                      "(BASELINE.json configs[3]); side measurement, not the headline metric")
+        line["config"]["workload"] = (f"DiT patch-2 (hidden 384, depth 12, 6 heads) {img}x{img} unconditional, DDIM-50 "
+                                      "(BASELINE.json configs[3]" + (", the shipped 64x64 image size" if dit64 else "") +
+                                      "); side measurement, not the headline metric")
         line["config"]["cfg_scale"] = None
     if is_ddpm:
         line["metric"] = "ddpm1000_unet_cifar10_images_per_sec"
