@@ -109,6 +109,19 @@ class DiffusionBase:
 
         return tqdm(it, desc=desc, total=total)
 
+    # ---- per-step noise ---------------------------------------------------------------------------
+    _noise_shard = None  # (global batch, lo, hi) when this process samples one shard of a larger batch (sharding.py)
+
+    def _draw_like(self, img):
+        """The per-step N(0,1) draw (DDPM every step, DDIM when eta > 0; ddpm.py:216, ddim.py:205).  On a shard of a
+        larger batch every rank draws the GLOBAL tensor and keeps its own rows: the generator advances exactly as in the
+        single-process run, so an N-rank run reproduces it image for image."""
+        sh = self._noise_shard
+        if sh is None:
+            return torch.randn_like(img)
+        total, lo, hi = sh
+        return torch.randn((total,) + tuple(img.shape[1:]), device=img.device, dtype=img.dtype)[lo:hi]
+
     # ---- whole-loop CUDA graph ------------------------------------------------------------------
     def _graph_ok(self, model, return_all_timesteps, step_noise):
         return (self.use_cuda_graph and not return_all_timesteps and step_noise is None
@@ -125,7 +138,8 @@ class DiffusionBase:
         S = int(t_seq.numel())
         packed = getattr(model, "_packed", None)
         key = (id(model), bool(ddpm), bool(cfg), tuple(img.shape), y is not None, float(g.cfg_scale), int(g.clip_mode),
-               int(g.q_lo), int(g.q_hi), float(g.q_weight), bool(draw_noise), S, id(coef_seq), id(t_seq), str(img.device))
+               int(g.q_lo), int(g.q_hi), float(g.q_weight), bool(draw_noise), S, id(coef_seq), id(t_seq), str(img.device),
+               self._noise_shard)
         ent = getattr(self, "_graph_cache", None)
         if ent is not None and (ent["key"] != key or ent["packed"] is not getattr(model, "_packed", None)):
             ent = self._graph_cache = None
@@ -147,7 +161,7 @@ class DiffusionBase:
                 _lib.check(lib.dmc_advance(counter.data_ptr(), t_seq.data_ptr(), t_batch.data_ptr(), B,
                                            _lib.stream_ptr()), "dmc_advance")
                 eps_c, eps_u = model_call()
-                z = torch.randn_like(x) if draw_noise else None
+                z = self._draw_like(x) if draw_noise else None
                 _lib.check(step_at(x.data_ptr(), eps_c.data_ptr(), _lib.ptr(eps_u), _lib.ptr(z), x.data_ptr(), B, n,
                                    coef_seq.data_ptr(), counter.data_ptr() + 4, g, _lib.stream_ptr()), "dmc_step_at")
 

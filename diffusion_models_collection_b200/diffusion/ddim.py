@@ -121,7 +121,7 @@ class DDIM(DiffusionBase):
                 eps = model(img, t_batch, y)
                 z = None
                 if self.eta > 0:
-                    z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
+                    z = self._draw_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
                 self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
                 img, nxt = nxt, img
                 if return_all_timesteps:
@@ -163,7 +163,7 @@ class DDIM(DiffusionBase):
                 eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
                 z = None
                 if self.eta > 0:
-                    z = torch.randn_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
+                    z = self._draw_like(img) if step_noise is None else step_noise[i].to(img.device).float().contiguous()
                 self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
                 img, nxt = nxt, img
                 if return_all_timesteps:

@@ -114,7 +114,7 @@ class DDPM(DiffusionBase):
             for k, i in enumerate(self._bar(reversed(range(0, self.num_timesteps)), "Sampling", self.num_timesteps)):
                 t_batch.fill_(i)
                 eps = model(img, t_batch, y)
-                z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
+                z = self._draw_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
                 self._step(lib, img, eps.contiguous(), None, z, nxt, coefs.data_ptr() + 20 * i, g)
                 img, nxt = nxt, img
                 if return_all_timesteps:
@@ -154,7 +154,7 @@ class DDPM(DiffusionBase):
                                             f"DDPM Sampling with CFG scale {cfg_scale}", self.num_timesteps)):
                 t_batch.fill_(i)
                 eps_c, eps_u = self._eps_pair(model, img, t_batch, y, y_uncond)
-                z = torch.randn_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
+                z = self._draw_like(img) if step_noise is None else step_noise[k].to(img.device).float().contiguous()
                 self._step(lib, img, eps_c.contiguous(), eps_u.contiguous(), z, nxt, coefs.data_ptr() + 20 * i, g)
                 img, nxt = nxt, img
                 if return_all_timesteps:

@@ -10,6 +10,8 @@ all-gathered (NCCL over NVLink / NVSwitch; gloo on CPU in the tests).  The refer
 
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -39,7 +41,7 @@ def gather_shards(local: torch.Tensor, total: int, rank: int, world: int, group=
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
-def sharded_call(fn, shape, y=None, noise=None, rank=None, world=None, sliced=False, group=None):
+def sharded_call(fn, shape, y=None, noise=None, rank=None, world=None, sliced=False, group=None, diffusion=None):
     """Runs fn(local_shape, y_local, noise_local) -> [n_local, ...] on this rank's slice and gathers the result.
     y / noise are GLOBAL tensors (sliced here) unless sliced=True."""
     if world is None:
@@ -53,7 +55,8 @@ def sharded_call(fn, shape, y=None, noise=None, rank=None, world=None, sliced=Fa
         noise = None if noise is None else noise[lo:hi]
     local_shape = (hi - lo,) + tuple(shape[1:])
     if hi > lo:
-        local = fn(local_shape, y, noise)
+        with _noise_shard(diffusion, (total, lo, hi) if world > 1 else None):
+            local = fn(local_shape, y, noise)
     else:  # more ranks than samples: nothing to do here, but still take part in the gather
         ref = noise if noise is not None else torch.empty(0)
         local = torch.empty((0,) + tuple(shape[1:]), dtype=torch.float32, device=ref.device)
@@ -66,6 +69,23 @@ def _resolve(rank, world, group):
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     return rank, world
+
+
+@contextlib.contextmanager
+def _noise_shard(diffusion, shard):
+    """per-step draws (DDPM, DDIM eta > 0) of a shard = this rank's rows of the GLOBAL per-step draw (seed parity with the
+    single-process run); a no-op for samplers without the hook"""
+    if diffusion is None:
+        yield
+        return
+    prev = getattr(diffusion, "_noise_shard", None)
+    if hasattr(diffusion, "_draw_like"):
+        diffusion._noise_shard = shard
+    try:
+        yield
+    finally:
+        if hasattr(diffusion, "_draw_like"):
+            diffusion._noise_shard = prev
 
 
 def _global_noise(diffusion, shape, noise, rank, world, sliced):
@@ -90,7 +110,7 @@ def sharded_sample_with_cfg(diffusion, model, shape, y, cfg_scale=3.0, p_thresho
     def fn(local_shape, yl, nl):
         return diffusion.sample_with_cfg(model, local_shape, yl, cfg_scale=cfg_scale, p_threshold=p_threshold, noise=nl)
 
-    return sharded_call(fn, shape, y, noise, rank, world, sliced, group)
+    return sharded_call(fn, shape, y, noise, rank, world, sliced, group, diffusion=diffusion)
 
 
 def sharded_sample(diffusion, model, shape, y=None, noise=None, rank=None, world=None, sliced=False, group=None):
@@ -101,4 +121,4 @@ def sharded_sample(diffusion, model, shape, y=None, noise=None, rank=None, world
     def fn(local_shape, yl, nl):
         return diffusion.sample(model, local_shape, yl, noise=nl)
 
-    return sharded_call(fn, shape, y, noise, rank, world, sliced, group)
+    return sharded_call(fn, shape, y, noise, rank, world, sliced, group, diffusion=diffusion)

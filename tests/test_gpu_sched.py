@@ -247,3 +247,33 @@ def test_api_errors():
     with pytest.raises(ValueError):
         DDPM(10, device="cuda").p_losses(_cpu_toy, torch.zeros(1, 3, 8, 8).cuda(), torch.zeros(1, dtype=torch.long).cuda(),
                                          loss_type="l3")
+
+
+@pytest.mark.parametrize("kind", ["ddpm", "ddim_eta"])
+def test_sharded_sampling_with_per_step_noise_reproduces_the_single_process_run(kind):
+    """DDPM (and DDIM with eta > 0) draw N(0,1) at every step: a rank that samples rows [lo, hi) of a global batch draws the
+    GLOBAL per-step tensor and keeps its rows, so the shards of a 3-rank run (emulated one after the other on this GPU,
+    each from the same seed like separate processes) concatenate to exactly the 1-rank run."""
+    from diffusion_models_collection_b200.diffusion import DDIM, DDPM
+    from diffusion_models_collection_b200.sharding import sharded_sample, shard_bounds
+
+    B, shape = 7, (7, 3, 8, 8)
+    mk = (lambda: DDPM(12, device="cuda")) if kind == "ddpm" else (lambda: DDIM(1000, 6, eta=0.5, device="cuda"))
+
+    def model(x, t, y=None):  # a per-sample denoiser stand-in on the GPU
+        return torch.tanh(x * 0.7 + (t.view(-1, 1, 1, 1).float() / 1000.0))
+
+    d = mk()
+    d.progress = False
+    torch.manual_seed(11)
+    whole = sharded_sample(d, model, shape, rank=0, world=1)
+    parts = []
+    for r in range(3):
+        d = mk()
+        d.progress = False
+        torch.manual_seed(11)
+        lo, hi = shard_bounds(B, r, 3)
+        x_T = torch.randn(shape, device="cuda")  # what _global_noise draws on every rank
+        d._noise_shard = (B, lo, hi)
+        parts.append(d.sample(model, (hi - lo,) + shape[1:], noise=x_T[lo:hi]))
+    assert torch.equal(torch.cat(parts, dim=0), whole)

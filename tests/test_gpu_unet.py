@@ -333,3 +333,28 @@ def test_fused_head_path_matches_two_kernel_path(monkeypatch):
         b = net2(x.cuda(), t.cuda(), y.cuda())
     assert "output.head" in net2.plan_info(4).op_names and "output.head" not in net.plan_info(4).op_names
     assert rel_l2(a, b) < 3e-3
+
+
+def test_sharded_ddpm_with_native_unet_graph_loop_reproduces_single_process_run():
+    """per-step noise of a shard = this rank's rows of the global draw, inside the captured step graph too"""
+    from diffusion_models_collection_b200.diffusion import DDPM
+    from diffusion_models_collection_b200.sharding import shard_bounds
+
+    net = build_unet(SMALL_UNET, None, 5)
+    B, shape = 6, (6, 3, 32, 32)
+    d = DDPM(8, device="cuda")
+    d.progress = False
+    torch.manual_seed(21)
+    x_T = torch.randn(shape, device="cuda")
+    whole = d.sample(net, shape, noise=x_T)
+    parts = []
+    for r in range(2):
+        d2 = DDPM(8, device="cuda")
+        d2.progress = False
+        torch.manual_seed(21)
+        x_T2 = torch.randn(shape, device="cuda")
+        lo, hi = shard_bounds(B, r, 2)
+        d2._noise_shard = (B, lo, hi)
+        parts.append(d2.sample(net, (hi - lo,) + shape[1:], noise=x_T2[lo:hi]))
+        assert getattr(d2, "_graph_cache", None) is not None
+    assert torch.equal(torch.cat(parts, dim=0), whole)
