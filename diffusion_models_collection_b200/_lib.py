@@ -79,6 +79,12 @@ class PatchEmbedDesc(C.Structure):
                 ("patch", C.c_int32), ("hidden", C.c_int32), ("weight", vp), ("bias", vp), ("pos", vp), ("out", vp)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [("x", vp), ("dy", vp), ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin", C.c_int32),
+                ("Cout", C.c_int32), ("stride", C.c_int32), ("taps", C.c_int32), ("splits", C.c_int32), ("partial", vp),
+                ("dw", vp), ("accumulate", C.c_int32)]
+
+
 class HeadDesc(C.Structure):
     _fields_ = [("src", vp), ("stats", vp), ("stats_slots", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("C", C.c_int32), ("Cout", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
@@ -115,6 +121,8 @@ SYMBOLS = {
     "dmc_ddpm_step_at": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(Guidance), vp]),
     "dmc_advance": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "dmc_q_sample": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]),
+    "dmc_conv_wgrad_splits": (C.c_int, [C.POINTER(WgradDesc)]),
+    "dmc_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
     "dmc_plan_create": (C.c_int, [C.POINTER(vp)]),
     "dmc_plan_destroy": (C.c_int, [vp]),
     "dmc_plan_run": (C.c_int, [vp, vp]),

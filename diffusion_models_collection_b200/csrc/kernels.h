@@ -46,6 +46,9 @@ struct ConvPrepared;
 int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out);
 void conv_release(ConvPrepared* p);
 int launch_conv(const dmc_conv_desc& d, const ConvPrepared* p, cudaStream_t st);
+// conv_wgrad.cu : weight gradient on tcgen05 (training)
+int conv_wgrad_splits(const dmc_wgrad_desc& d);
+int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st);
 // conv_ref.cu : CUDA-core debug implementation of the same contract (tests only)
 int launch_conv_ref(const dmc_conv_desc& d, cudaStream_t st);
 

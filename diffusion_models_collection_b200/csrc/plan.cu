@@ -150,6 +150,16 @@ int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, const fl
   return launch_q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, x_t, B, n_per_sample, static_cast<cudaStream_t>(stream));
 }
 
+int dmc_conv_wgrad_splits(const dmc_wgrad_desc* d) {
+  DMC_REQUIRE(d != nullptr && d->stride >= 1 && d->Cout >= 128 && d->Cin >= 64, "dmc_conv_wgrad_splits: bad descriptor");
+  return conv_wgrad_splits(*d);
+}
+
+int dmc_conv_wgrad(const dmc_wgrad_desc* d, void* stream) {
+  DMC_REQUIRE(d != nullptr, "dmc_conv_wgrad: null descriptor");
+  return launch_conv_wgrad(*d, static_cast<cudaStream_t>(stream));
+}
+
 int dmc_plan_create(dmc_plan** out) {
   DMC_REQUIRE(out != nullptr, "dmc_plan_create: null out");
   *out = new (std::nothrow) dmc_plan();

@@ -104,6 +104,31 @@ DMC_API int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, 
                  const float* sqrt_1m_acp, float* x_t, int32_t B, int32_t n_per_sample, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training step building blocks (the full step is not wired yet)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Weight gradient of a 3x3 (padding 1) or 1x1 convolution, the backward of nn.Conv2d w.r.t. its weight
+ * (models/unet.py:37,54,58,81,82,106,116 under autograd):
+ *   dw[co, ci, r, s] (+)= sum_{n,h,w} dy[n, h, w, co] * x[n, h*stride + r - pad, w*stride + s - pad, ci]
+ * tcgen05 GEMM over K = output pixels with both operands MN-major straight from the NHWC tensors; the pixels are cut into
+ * `splits` slices whose partial sums are added in index order (deterministic).
+ * (The input gradient needs no new kernel: it is dmc_plan_add_conv over dy with the weights packed transposed and
+ * tap-flipped.) */
+typedef struct {
+  const void* x;    /* bf16 NHWC [B, Hin, Win, Cin], the convolution's input */
+  const void* dy;   /* bf16 NHWC [B, Hin/stride, Win/stride, Cout], gradient of its output */
+  int32_t B, Hin, Win, Cin, Cout; /* Cin % 64 == 0, Cout % 128 == 0 */
+  int32_t stride;   /* 1 or 2 */
+  int32_t taps;     /* 9: 3x3 with padding 1;  1: 1x1 */
+  int32_t splits;   /* must equal dmc_conv_wgrad_splits() */
+  float* partial;   /* scratch, fp32 [splits, Cout, taps, Cin] */
+  float* dw;        /* fp32 [Cout, Cin, kh, kw] (the reference's parameter layout) */
+  int32_t accumulate; /* 1: dw += ..., 0: dw = ... */
+} dmc_wgrad_desc;
+DMC_API int dmc_conv_wgrad_splits(const dmc_wgrad_desc* d);
+DMC_API int dmc_conv_wgrad(const dmc_wgrad_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Denoiser forward as a "plan": an ordered list of kernel launches with all pointers, shapes and TMA
  * descriptors resolved once per (model, batch size, workspace).  One dmc_plan_run() == one
  * model(x, t, y) call of the reference (models/unet.py:243-292, models/dit.py:263-295).
