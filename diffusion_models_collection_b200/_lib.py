@@ -55,7 +55,8 @@ class GnStatsDesc(C.Structure):
 class GnApplyDesc(C.Structure):
     _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2), ("stats_slots", C.c_int32 * 2),
                 ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
-                ("silu", C.c_int32), ("out", vp), ("src_lo", vp * 2), ("out_lo", vp)]
+                ("silu", C.c_int32), ("out", vp), ("src_lo", vp * 2), ("out_lo", vp), ("drop_p", C.c_float),
+                ("seed", C.c_uint32)]
 
 
 class ConvDesc(C.Structure):
@@ -77,6 +78,19 @@ class DitCondDesc(C.Structure):
 class PatchEmbedDesc(C.Structure):
     _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("patch", C.c_int32), ("hidden", C.c_int32), ("weight", vp), ("bias", vp), ("pos", vp), ("out", vp)]
+
+
+class GnBwdDesc(C.Structure):
+    _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2),
+                ("stats_slots", C.c_int32 * 2), ("dout", vp), ("dsrc", vp * 2), ("accumulate", C.c_int32 * 2),
+                ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
+                ("silu", C.c_int32), ("drop_p", C.c_float), ("seed", C.c_uint32), ("dgamma", vp), ("dbeta", vp),
+                ("scratch", vp)]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [("qkv", vp), ("out", vp), ("dout", vp), ("dqkv", vp), ("B", C.c_int32), ("L", C.c_int32),
+                ("heads", C.c_int32), ("C", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -123,6 +137,13 @@ SYMBOLS = {
     "dmc_q_sample": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]),
     "dmc_conv_wgrad_splits": (C.c_int, [C.POINTER(WgradDesc)]),
     "dmc_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
+    "dmc_gn_backward": (C.c_int, [C.POINTER(GnBwdDesc), vp]),
+    "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
+    "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_block_sum2x2": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_conv_dgrad_strided": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, vp]),
     "dmc_plan_create": (C.c_int, [C.POINTER(vp)]),
     "dmc_plan_destroy": (C.c_int, [vp]),
     "dmc_plan_run": (C.c_int, [vp, vp]),

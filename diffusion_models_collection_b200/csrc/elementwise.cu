@@ -311,7 +311,16 @@ struct GnApplyArgs {
   int slots0, slots1;
   float eps;
   int silu;
+  float drop_scale;       // training: 1 / (1 - p) for kept elements
+  uint32_t drop_thresh, seed;
 };
+
+// counter-based dropout mask (the same function as in train_ops.cu: forward and backward regenerate the same mask)
+__device__ __forceinline__ bool gn_dropout_keep(uint32_t seed, uint64_t idx, uint32_t thresh) {
+  uint32_t h = static_cast<uint32_t>(idx) * 0x9E3779B1u ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u) ^ seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= thresh;
+}
 
 // Phase 1 (per CTA, cheap): warp g reduces the partial sums of group g (slots x 8-channel blocks, possibly from both
 // sources of a concat) with lane-strided loads and a fixed shuffle tree -> mean / rstd, bit-reproducible.
@@ -429,6 +438,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
               y1 = silu_from_half(y1);
             }
           }
+          if (a.drop_thresh != 0u) {  // dropout after SiLU (ResidualBlock.conv2, models/unet.py:53), training only
+            const uint64_t idx = ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8 + 2 * j;
+            y0 = gn_dropout_keep(a.seed, idx, a.drop_thresh) ? y0 * a.drop_scale : 0.f;
+            y1 = gn_dropout_keep(a.seed, idx + 1, a.drop_thresh) ? y1 * a.drop_scale : 0.f;
+          }
           o[j] = pack_bf16x2(y0, y1);
           if (LO) {
             const float2 hi = unpack_bf16x2(o[j]);
@@ -458,6 +472,10 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.stats1 = d.nsrc == 2 ? d.stats[1] : d.stats[0];
   a.gamma = d.gamma; a.beta = d.beta; a.out = reinterpret_cast<uint4*>(d.out);
   a.HW = d.HW; a.C0_8 = C0 / 8; a.C1_8 = C1 / 8; a.groups = d.groups; a.eps = d.eps; a.silu = d.silu;
+  DMC_REQUIRE(d.drop_p >= 0.f && d.drop_p < 1.f, "gn_apply: drop_p=%f", d.drop_p);
+  a.drop_thresh = dropout_threshold(d.drop_p);
+  a.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
+  a.seed = d.seed;
   a.slots0 = d.stats_slots[0];
   a.slots1 = d.nsrc == 2 ? d.stats_slots[1] : 0;
   DMC_REQUIRE(a.slots0 > 0 && (d.nsrc == 1 || a.slots1 > 0), "gn_apply: stats_slots must be positive");

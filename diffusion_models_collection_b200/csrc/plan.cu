@@ -160,6 +160,29 @@ int dmc_conv_wgrad(const dmc_wgrad_desc* d, void* stream) {
   return launch_conv_wgrad(*d, static_cast<cudaStream_t>(stream));
 }
 
+int dmc_gn_backward(const dmc_gn_bwd_desc* d, void* stream) {
+  DMC_REQUIRE(d != nullptr, "dmc_gn_backward: null descriptor");
+  return launch_gn_backward(*d, static_cast<cudaStream_t>(stream));
+}
+int dmc_attention_backward(const dmc_attn_bwd_desc* d, void* stream) {
+  DMC_REQUIRE(d != nullptr, "dmc_attention_backward: null descriptor");
+  return launch_attention_backward(*d, static_cast<cudaStream_t>(stream));
+}
+int dmc_channel_sum(const void* src, float* out, int32_t B, int32_t HW, int32_t C, int32_t per_image, int32_t accumulate,
+                    void* stream) {
+  return launch_channel_sum(src, out, B, HW, C, per_image, accumulate, static_cast<cudaStream_t>(stream));
+}
+int dmc_block_sum2x2(const void* dhigh, void* dlow, int32_t B, int32_t H, int32_t W, int32_t C, int32_t accumulate, void* stream) {
+  return launch_block_sum2x2(dhigh, dlow, B, H, W, C, accumulate, static_cast<cudaStream_t>(stream));
+}
+int dmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t Csrc, int32_t HW, int32_t Cdst, void* stream) {
+  return launch_nchw_to_nhwc_pad(src, dst, B, Csrc, HW, Cdst, static_cast<cudaStream_t>(stream));
+}
+int dmc_conv_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t Hin, int32_t Win, int32_t Cin,
+                           int32_t Cout, int32_t stride, int32_t accumulate, void* stream) {
+  return launch_conv_dgrad_strided(dy, w, dx, B, Hin, Win, Cin, Cout, stride, accumulate, static_cast<cudaStream_t>(stream));
+}
+
 int dmc_plan_create(dmc_plan** out) {
   DMC_REQUIRE(out != nullptr, "dmc_plan_create: null out");
   *out = new (std::nothrow) dmc_plan();

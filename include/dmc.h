@@ -128,6 +128,56 @@ typedef struct {
 DMC_API int dmc_conv_wgrad_splits(const dmc_wgrad_desc* d);
 DMC_API int dmc_conv_wgrad(const dmc_wgrad_desc* d, void* stream);
 
+/* GroupNorm(groups) (+ SiLU) (+ dropout) backward over the concatenation of up to two sources: the backward of the
+ * dmc_gn_apply pass (models/unet.py:35-36,51-53,80).  Recomputes the normalised value from src and the forward partial
+ * sums; writes (or accumulates into) the gradients of the sources and writes dgamma / dbeta. */
+typedef struct {
+  int32_t nsrc;
+  const void* src[2];      /* bf16 [B, HW, c_i]: the un-normalised inputs of the forward pass */
+  int32_t src_c[2];
+  const float* stats[2];   /* their forward partial sums */
+  int32_t stats_slots[2];
+  const void* dout;        /* bf16 [B, HW, C]: gradient of the pass's output */
+  void* dsrc[2];           /* bf16 [B, HW, c_i]: gradients of the sources */
+  int32_t accumulate[2];   /* 1: dsrc += ..., 0: dsrc = ... */
+  int32_t B, HW, groups;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t silu;
+  float drop_p;            /* dropout probability applied after SiLU in the forward pass (0: none) */
+  uint32_t seed;           /* the forward pass's dropout seed */
+  float* dgamma;           /* fp32 [C] */
+  float* dbeta;            /* fp32 [C] */
+  float* scratch;          /* fp32 [B * ceil(HW/128) * (2*C + C/4)] */
+} dmc_gn_bwd_desc;
+DMC_API int dmc_gn_backward(const dmc_gn_bwd_desc* d, void* stream);
+
+/* Attention backward (models/unet.py:88-96 under autograd): dqkv from qkv, the forward output and its gradient.
+ * CUDA-core fp32 kernel, head dim 64, L <= 256 (first version: the tensor-core form is future work). */
+typedef struct {
+  const void* qkv;  /* bf16 [B, L, 3C] */
+  const void* out;  /* bf16 [B, L, C] forward output */
+  const void* dout; /* bf16 [B, L, C] */
+  void* dqkv;       /* bf16 [B, L, 3C] */
+  int32_t B, L, heads, C;
+} dmc_attn_bwd_desc;
+DMC_API int dmc_attention_backward(const dmc_attn_bwd_desc* d, void* stream);
+
+/* out[n or 0][c] (+)= sum over pixels (and images unless per_image) of src[n, p, c]: bias and conditioning-row gradients */
+DMC_API int dmc_channel_sum(const void* src_bf16, float* out, int32_t B, int32_t HW, int32_t C, int32_t per_image,
+                    int32_t accumulate, void* stream);
+/* dlow[n, i, j, :] (+)= the 2x2 block sum of dhigh (backward of the nearest 2x upsample, models/unet.py:119) */
+DMC_API int dmc_block_sum2x2(const void* dhigh_bf16, void* dlow_bf16, int32_t B, int32_t H, int32_t W, int32_t C,
+                     int32_t accumulate, void* stream);
+/* fp32 NCHW [B, Csrc, H*W] -> bf16 NHWC [B, H*W, Cdst >= Csrc] with zero-padded channels */
+DMC_API int dmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t Csrc, int32_t HW, int32_t Cdst,
+                              void* stream);
+/* input gradient of a strided 3x3 / padding-1 convolution (Downsample layers), CUDA cores:
+ * dx bf16 [B, Hin, Win, Cin] (+)= ..., dy bf16 [B, Hin/stride, Win/stride, Cout], w fp32 [Cout, Cin, 3, 3] */
+DMC_API int dmc_conv_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t Hin, int32_t Win,
+                           int32_t Cin, int32_t Cout, int32_t stride, int32_t accumulate, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Denoiser forward as a "plan": an ordered list of kernel launches with all pointers, shapes and TMA
  * descriptors resolved once per (model, batch size, workspace).  One dmc_plan_run() == one
@@ -234,6 +284,8 @@ typedef struct {
   void* out;              /* bf16 [B, HW, C] */
   const void* src_lo[2];  /* optional low parts of the sources (value = src + src_lo) */
   void* out_lo;           /* optional low part of the output */
+  float drop_p;           /* training: dropout after SiLU (models/unet.py:53), counter-based mask from `seed`; 0 = none */
+  uint32_t seed;
 } dmc_gn_apply_desc;
 DMC_API int dmc_plan_add_gn_apply(dmc_plan* p, const dmc_gn_apply_desc* d);
 

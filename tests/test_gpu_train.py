@@ -74,3 +74,169 @@ def test_conv_input_gradient_is_a_forward_conv_with_flipped_transposed_weights(c
     out, _ = run_conv([nhwc_bf16(dy)], [k * k], wmat, cin)
     got = out.float().permute(0, 3, 1, 2)
     assert rel_l2(got, ref) < 4e-3  # the result is stored in bf16
+
+
+def _gn_forward(xs, gamma, beta, silu, drop_p=0.0, seed=0):
+    """runs the forward gn_stats + gn_apply kernels; returns (out bf16 NHWC, stats list, slots)"""
+    from tests.gpu_util import Plan
+    B, H, W, _ = xs[0].shape
+    HW = H * W
+    slots = (HW + 127) // 128
+    stats = []
+    p = Plan()
+    for x in xs:
+        st = torch.empty((B, slots, x.shape[3] // 8, 2), device="cuda")
+        g = _lib.GnStatsDesc()
+        g.src, g.B, g.HW, g.C, g.stats = x.data_ptr(), B, HW, x.shape[3], st.data_ptr()
+        p.add("gn_stats", g)
+        stats.append(st)
+    Ctot = sum(x.shape[3] for x in xs)
+    out = torch.full((B, H, W, Ctot), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = _lib.GnApplyDesc()
+    d.nsrc = len(xs)
+    for i, x in enumerate(xs):
+        d.src[i], d.src_c[i], d.stats[i], d.stats_slots[i] = x.data_ptr(), x.shape[3], stats[i].data_ptr(), slots
+    d.B, d.HW, d.groups, d.gamma, d.beta, d.eps, d.silu, d.out = B, HW, 8, gamma.data_ptr(), beta.data_ptr(), 1e-5, silu, out.data_ptr()
+    d.drop_p, d.seed = drop_p, seed
+    p.add("gn_apply", d)
+    p.run()
+    return out, stats, slots
+
+
+@pytest.mark.parametrize("cs,H,B,silu", [([128], 32, 2, 1), ([256], 16, 3, 0), ([256, 256], 4, 5, 1), ([256, 128], 16, 2, 1),
+                                         ([64], 8, 3, 1), ([128, 128], 32, 1, 1)])
+def test_groupnorm_silu_backward(cs, H, B, silu):
+    lib = _lib.load()
+    C_ = sum(cs)
+    xs = [_q(_rand((B, c, H, H), 10 + i, 1.5) + 0.3) for i, c in enumerate(cs)]
+    gamma = (_rand((C_,), 2, 0.3) + 1.0).requires_grad_(True)
+    beta = _rand((C_,), 3, 0.2).requires_grad_(True)
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    y = F.group_norm(torch.cat(xr, 1), 8, gamma, beta, eps=1e-5)
+    if silu:
+        y = F.silu(y)
+    dy = _q(_rand(tuple(y.shape), 4))
+    refs = torch.autograd.grad(y, xr + [gamma, beta], dy)
+    xn = [nhwc_bf16(x) for x in xs]
+    _, stats, slots = _gn_forward(xn, gamma.detach(), beta.detach(), silu)
+    dout = nhwc_bf16(dy)
+    dsrc = [torch.full_like(x, float("nan")) for x in xn]
+    dgamma, dbeta = torch.full((C_,), float("nan"), device="cuda"), torch.full((C_,), float("nan"), device="cuda")
+    nslab = (H * H + 127) // 128
+    scratch = torch.empty(B * nslab * (2 * C_ + C_ // 4), device="cuda")
+    d = _lib.GnBwdDesc()
+    d.nsrc = len(cs)
+    for i in range(len(cs)):
+        d.src[i], d.src_c[i], d.stats[i], d.stats_slots[i] = xn[i].data_ptr(), cs[i], stats[i].data_ptr(), slots
+        d.dsrc[i], d.accumulate[i] = dsrc[i].data_ptr(), 0
+    d.dout, d.B, d.HW, d.groups = dout.data_ptr(), B, H * H, 8
+    d.gamma, d.beta, d.eps, d.silu = gamma.detach().data_ptr(), beta.detach().data_ptr(), 1e-5, silu
+    d.dgamma, d.dbeta, d.scratch = dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr()
+    _lib.check(lib.dmc_gn_backward(C.byref(d), _lib.stream_ptr()), "gn_backward")
+    torch.cuda.synchronize()
+    for i in range(len(cs)):
+        got = dsrc[i].float().permute(0, 3, 1, 2)
+        assert rel_l2(got, refs[i]) < 5e-3, i  # bf16 gradient storage
+    assert rel_l2(dgamma, refs[-2]) < 1e-4 and rel_l2(dbeta, refs[-1]) < 1e-4
+    # accumulate mode adds on top
+    for i in range(len(cs)):
+        d.accumulate[i] = 1
+    before = [t.clone() for t in dsrc]
+    _lib.check(lib.dmc_gn_backward(C.byref(d), _lib.stream_ptr()), "gn_backward acc")
+    torch.cuda.synchronize()
+    for i in range(len(cs)):
+        assert rel_l2(dsrc[i].float(), 2 * before[i].float()) < 5e-3
+
+
+def test_dropout_mask_is_the_same_in_forward_and_backward():
+    """the forward pass scales kept activations by 1/(1-p) and zeroes the rest; the backward pass regenerates the same
+    counter-based mask: its gradients equal autograd's through  silu(gn(x)) * mask / (1-p)  with the mask read off the
+    forward output"""
+    lib = _lib.load()
+    B, C_, H, p, seed = 2, 128, 16, 0.25, 1234
+    xf = _q(_rand((B, C_, H, H), 1, 1.5))
+    x = nhwc_bf16(xf)
+    gamma, beta = _rand((C_,), 2, 0.3) + 1.0, _rand((C_,), 3, 0.2)
+    out0, stats, slots = _gn_forward([x], gamma, beta, 1)
+    out1, _, _ = _gn_forward([x], gamma, beta, 1, drop_p=p, seed=seed)
+    kept = out1 != 0
+    assert abs(float(kept.float().mean()) - (1 - p)) < 0.02
+    assert rel_l2(out1.float()[kept], out0.float()[kept] / (1 - p)) < 5e-3
+    mask = kept.float().permute(0, 3, 1, 2)
+    xr = xf.clone().requires_grad_(True)
+    g_, b_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.silu(F.group_norm(xr, 8, g_, b_, eps=1e-5)) * mask / (1 - p)
+    dy = _q(_rand((B, C_, H, H), 4))
+    rx, rg, rb = torch.autograd.grad(y, [xr, g_, b_], dy)
+    dout = nhwc_bf16(dy)
+    dsrc = torch.empty_like(x)
+    dg, db = torch.empty(C_, device="cuda"), torch.empty(C_, device="cuda")
+    scratch = torch.empty(B * 2 * (2 * C_ + C_ // 4), device="cuda")
+    d = _lib.GnBwdDesc()
+    d.nsrc = 1
+    d.src[0], d.src_c[0], d.stats[0], d.stats_slots[0], d.dsrc[0] = x.data_ptr(), C_, stats[0].data_ptr(), slots, dsrc.data_ptr()
+    d.dout, d.B, d.HW, d.groups = dout.data_ptr(), B, H * H, 8
+    d.gamma, d.beta, d.eps, d.silu, d.drop_p, d.seed = gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, p, seed
+    d.dgamma, d.dbeta, d.scratch = dg.data_ptr(), db.data_ptr(), scratch.data_ptr()
+    _lib.check(lib.dmc_gn_backward(C.byref(d), _lib.stream_ptr()), "gn_backward")
+    torch.cuda.synchronize()
+    assert rel_l2(dsrc.float().permute(0, 3, 1, 2), rx) < 5e-3
+    assert rel_l2(dg, rg) < 1e-4 and rel_l2(db, rb) < 1e-4
+
+
+@pytest.mark.parametrize("L,heads,B", [(256, 4, 2), (64, 4, 3), (16, 4, 2), (128, 2, 1)])
+def test_attention_backward(L, heads, B):
+    lib = _lib.load()
+    hd, C_ = 64, heads * 64
+    qkv = _q(_rand((B, L, 3 * C_), 80)).requires_grad_(True)
+    q, k, v = (qkv[..., i * C_:(i + 1) * C_].reshape(B, L, heads, hd).transpose(1, 2) for i in range(3))
+    a = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    out = (a @ v).transpose(1, 2).reshape(B, L, C_)
+    dout = _q(_rand((B, L, C_), 81))
+    (ref,) = torch.autograd.grad(out, qkv, dout)
+    qb, ob, db = qkv.detach().to(torch.bfloat16).contiguous(), out.detach().to(torch.bfloat16).contiguous(), dout.to(torch.bfloat16).contiguous()
+    dqkv = torch.full_like(qb, float("nan"))
+    d = _lib.AttnBwdDesc()
+    d.qkv, d.out, d.dout, d.dqkv, d.B, d.L, d.heads, d.C = qb.data_ptr(), ob.data_ptr(), db.data_ptr(), dqkv.data_ptr(), B, L, heads, C_
+    _lib.check(lib.dmc_attention_backward(C.byref(d), _lib.stream_ptr()), "attention_backward")
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv).all()
+    assert rel_l2(dqkv.float(), ref) < 8e-3  # o is read in bf16 for D = do . o; outputs stored in bf16
+
+
+def test_small_training_kernels():
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    B, H, C_ = 3, 8, 128
+    t = _rand((B, H * H, C_), 1).to(torch.bfloat16)
+    out = torch.zeros(C_, device="cuda")
+    _lib.check(lib.dmc_channel_sum(t.data_ptr(), out.data_ptr(), B, H * H, C_, 0, 0, st), "channel_sum")
+    per = torch.zeros(B, C_, device="cuda")
+    _lib.check(lib.dmc_channel_sum(t.data_ptr(), per.data_ptr(), B, H * H, C_, 1, 0, st), "channel_sum per image")
+    hi = _rand((B, 2 * H, 2 * H, C_), 2).to(torch.bfloat16)
+    lo = torch.zeros((B, H, H, C_), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dmc_block_sum2x2(hi.data_ptr(), lo.data_ptr(), B, H, H, C_, 0, st), "block_sum")
+    src = _rand((B, 3, H, H), 3)
+    dst = torch.full((B, H, H, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dmc_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.data_ptr(), B, 3, H * H, 64, st), "pack")
+    torch.cuda.synchronize()
+    assert rel_l2(out, t.float().sum(dim=(0, 1))) < 1e-5
+    assert rel_l2(per, t.float().sum(dim=1)) < 1e-5
+    want = hi.float().reshape(B, H, 2, H, 2, C_).sum(dim=(2, 4))
+    assert rel_l2(lo.float(), want) < 5e-3
+    assert torch.equal(dst[..., :3].float(), src.permute(0, 2, 3, 1).to(torch.bfloat16).float()) and float(dst[..., 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,H,B", [(128, 128, 32, 2), (256, 256, 16, 1)])
+def test_strided_conv_input_gradient(cin, cout, H, B):
+    lib = _lib.load()
+    x = _q(_rand((B, cin, H, H), 1)).requires_grad_(True)
+    w = _rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5)
+    y = F.conv2d(x, w, None, stride=2, padding=1)
+    dy = _q(_rand(tuple(y.shape), 3))
+    (ref,) = torch.autograd.grad(y, x, dy)
+    dx = torch.full((B, H, H, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dyn = nhwc_bf16(dy)
+    _lib.check(lib.dmc_conv_dgrad_strided(dyn.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, cin, cout, 2, 0, _lib.stream_ptr()), "dgrad")
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float().permute(0, 3, 1, 2), ref) < 4e-3
