@@ -140,6 +140,7 @@ SYMBOLS = {
     "dmc_gn_backward": (C.c_int, [C.POINTER(GnBwdDesc), vp]),
     "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
     "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_add_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp]),
     "dmc_block_sum2x2": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_conv_dgrad_strided": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -150,6 +151,7 @@ SYMBOLS = {
     "dmc_plan_run_op": (C.c_int, [vp, C.c_int32, vp]),
     "dmc_plan_num_launches": (C.c_int, [vp]),
     "dmc_plan_gemm_flops": (C.c_double, [vp]),
+    "dmc_plan_set_seed": (C.c_int, [vp, C.c_int32, C.c_uint32]),
     "dmc_plan_rebind": (C.c_int, [vp, C.c_int32, C.c_int32, vp]),
     "dmc_plan_time_ops": (C.c_int, [vp, vp, C.c_int32, c_f32p, C.c_int32]),
     "dmc_plan_num_ops": (C.c_int, [vp]),

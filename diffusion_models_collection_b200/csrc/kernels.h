@@ -51,6 +51,7 @@ uint32_t dropout_threshold(float p);
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st);
 int launch_attention_backward(const dmc_attn_bwd_desc& d, cudaStream_t st);
 int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int per_image, int accumulate, cudaStream_t st);
+int launch_add_bf16(void* dst, const void* src, size_t n, int accumulate, cudaStream_t st);
 int launch_block_sum2x2(const void* dhigh, void* dlow, int B, int H, int W, int C, int accumulate, cudaStream_t st);
 int launch_nchw_to_nhwc_pad(const float* src, void* dst, int B, int Cs, int HW, int Cd, cudaStream_t st);
 int launch_conv_dgrad_strided(const void* dy, const float* w, void* dx, int B, int Hin, int Win, int Cin, int Cout, int stride,

@@ -172,6 +172,10 @@ int dmc_channel_sum(const void* src, float* out, int32_t B, int32_t HW, int32_t 
                     void* stream) {
   return launch_channel_sum(src, out, B, HW, C, per_image, accumulate, static_cast<cudaStream_t>(stream));
 }
+int dmc_add_bf16(void* dst, const void* src, int64_t n, int32_t accumulate, void* stream) {
+  DMC_REQUIRE(n > 0, "dmc_add_bf16: n=%lld", static_cast<long long>(n));
+  return launch_add_bf16(dst, src, static_cast<size_t>(n), accumulate, static_cast<cudaStream_t>(stream));
+}
 int dmc_block_sum2x2(const void* dhigh, void* dlow, int32_t B, int32_t H, int32_t W, int32_t C, int32_t accumulate, void* stream) {
   return launch_block_sum2x2(dhigh, dlow, B, H, W, C, accumulate, static_cast<cudaStream_t>(stream));
 }
@@ -240,6 +244,14 @@ double dmc_plan_gemm_flops(const dmc_plan* p) {
   if (p)
     for (const auto& op : p->ops) f += op.flops;
   return f;
+}
+
+int dmc_plan_set_seed(dmc_plan* p, int32_t op_index, uint32_t seed) {
+  DMC_REQUIRE(p && op_index >= 0 && op_index < static_cast<int>(p->ops.size()), "dmc_plan_set_seed: bad op index");
+  Op& op = p->ops[op_index];
+  DMC_REQUIRE(op.kind == OP_GN_APPLY, "dmc_plan_set_seed: op %d is not a GroupNorm pass", op_index);
+  op.gn_apply.seed = seed;
+  return 0;
 }
 
 int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr) {

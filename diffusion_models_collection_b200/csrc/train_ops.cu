@@ -497,6 +497,35 @@ int launch_block_sum2x2(const void* dhigh, void* dlow, int B, int H, int W, int 
   return 0;
 }
 
+// dst (+)= src over n bf16 elements (n % 8 == 0): gradient of an identity residual branch / fan-out accumulation
+__global__ void __launch_bounds__(256) add_bf16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n8,
+                                                       int accumulate) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint4 s = src[i];
+    if (accumulate) {
+      uint4 d = dst[i];
+      const __nv_bfloat162* sp = reinterpret_cast<const __nv_bfloat162*>(&s);
+      __nv_bfloat162* dp = reinterpret_cast<__nv_bfloat162*>(&d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __bfloat1622float2(sp[j]), b = __bfloat1622float2(dp[j]);
+        dp[j] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+      }
+      s = d;
+    }
+    dst[i] = s;
+  }
+}
+
+int launch_add_bf16(void* dst, const void* src, size_t n, int accumulate, cudaStream_t st) {
+  DMC_REQUIRE(dst && src && n > 0 && n % 8 == 0, "add_bf16: bad arguments");
+  const size_t n8 = n / 8;
+  const int blocks = static_cast<int>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  add_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n8, accumulate);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // fp32 NCHW [B, Csrc, H, W] -> bf16 NHWC [B, H, W, Cdst] with zero-padded channels (head gradient, stem input)
 __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                int B, int Cs, int HW, int Cd) {

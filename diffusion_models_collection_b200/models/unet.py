@@ -111,10 +111,13 @@ class _Act:
 class _PlanBuilder:
     """Walks the UNet topology once (dry run -> workspace size, then for real) and records the op list."""
 
-    def __init__(self, net: "UNet", nimg, x_batch, has_y, uniform_t, conv_impl, split=False):
+    def __init__(self, net: "UNet", nimg, x_batch, has_y, uniform_t, conv_impl, split=False, keep=False, drop_p=0.0):
         self.net, self.B, self.x_batch = net, nimg, x_batch
         self.has_y, self.uniform_t, self.conv_impl = has_y, uniform_t, conv_impl
         self.split = split  # split-bf16 ("bf16x3") accuracy mode: every activation is a (hi, lo) pair of bf16 tensors
+        # training forward: every activation stays alive for the backward pass (no workspace reuse), Upsample materialises the
+        # upsampled tensor (its weight gradient reads it), ResidualBlock dropout (models/unet.py:53) runs in the conv2 GroupNorm pass
+        self.keep, self.drop_p = keep, drop_p
         self.arena = _Arena()
         self.ops = []  # (kind, dict)
 
@@ -124,6 +127,8 @@ class _PlanBuilder:
         return _Act(self.arena.alloc(n), Cc, H, W, self.arena.alloc(n) if self.split else None)
 
     def free(self, a: _Act):
+        if self.keep:
+            return
         self.arena.release(a.blk)
         if a.lo is not None:
             self.arena.release(a.lo)
@@ -148,7 +153,8 @@ class _PlanBuilder:
         out = self.act(sum(s.C for s in srcs), H, W)
         for s in srcs:
             self.stats_of(s)
-        self.ops.append(("gn_apply", dict(srcs=list(srcs), prefix=prefix, silu=silu, out=out)))
+        drop = self.drop_p if prefix.endswith(".conv2.0") else 0.0
+        self.ops.append(("gn_apply", dict(srcs=list(srcs), prefix=prefix, silu=silu, out=out, drop_p=drop)))
         return out
 
     def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
@@ -172,7 +178,7 @@ class _PlanBuilder:
 
     def fused_head(self, h):
         """the fused output-head kernel covers this geometry (and we are not in the split-bf16 / debug modes)"""
-        if self.split or self.conv_impl != 0 or not self.net.fuse_head:
+        if self.split or self.keep or self.conv_impl != 0 or not self.net.fuse_head:
             return False
         return h.C in (64, 128) and h.W in (16, 32, 64) and self.net.out_channels <= 8 and (h.C // 8) % 8 == 0
 
@@ -238,7 +244,7 @@ class _PlanBuilder:
                     new = self.attnblock(cur, p)
                 elif l[0] == "down":
                     new = self.conv([cur], [9], p + ".conv", l[1], cur.H, cur.W, stride=2, bias=p + ".conv")
-                elif l[0] == "up" and self.net.upsample_phases:
+                elif l[0] == "up" and self.net.upsample_phases and not self.keep:
                     # four 2x2 phase convolutions on the low-res tensor, scattered into one output (no upsampled copy)
                     new = self.act(l[1], 2 * cur.H, 2 * cur.W)
                     for ph in range(4):
@@ -307,8 +313,9 @@ class UNet(nn.Module):
         self._hw = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
         self._uniform_t = False
         self._plans = {}
+        self._train_engines = {}
         self._packed = None
-        self._packed_version = None
+        self._packed_version = self._packed_ids = None
         self._init_parameters()
 
     # ------------------------------------------------------------------------------------------------
@@ -378,13 +385,28 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------------------------------------
     # weight packing (one-time / on parameter change; plain torch ops -- not on the hot path)
     # ------------------------------------------------------------------------------------------------
-    def _param_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+    def _param_ids(self):
+        return tuple(p.data_ptr() for p in self.parameters())
 
-    def _ensure_packed(self, device):
-        ver = (str(device), self._param_version())
-        if self._packed is not None and self._packed_version == ver:
-            return self._packed
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters())
+
+    def _ensure_packed(self, device, training=False):
+        """packed copies of the parameters.  A change of parameter *storage* (load onto another device, .to(), a new
+        tensor assigned) rebuilds everything and drops the plans; a change of parameter *values* only (optimizer step, EMA
+        copy_, load_state_dict) re-packs in place, so plans, TMA descriptors and CUDA graphs stay valid.  `training` skips
+        what only the sampling plans read (Upsample phase weights)."""
+        ids, ver = (str(device), self._param_ids()), self._param_version()
+        pk = self._packed
+        if pk is not None and self._packed_ids == ids and (self._packed_version == ver or not pk["w3"]):
+            if pk["ver_main"] != ver:
+                self._refresh_packed(pk, phases=False)
+                pk["ver_main"] = ver
+            if not training and pk["ver_phases"] != ver:
+                self._refresh_packed(pk, phases=True)
+                pk["ver_phases"] = ver
+            self._packed_version = ver
+            return pk
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()}
         down, middle, up, out_ch = unet_block_structure(self._cfg())
         temb = self.model_channels * 4
@@ -466,13 +488,113 @@ class UNet(nn.Module):
             wlog=wlog, w3={},
             sd=sd, wblob=wblob, woffs=offs, wshape={k: tuple(v.shape) for k, v in W.items()},
             bias={k: v.contiguous() for k, v in Bv.items()}, wt_all=wt_all, bt_all=bt_all, ytab=ytab, freqs=freqs,
-            ncols=wt_all.shape[0], temb=temb,
+            ncols=wt_all.shape[0], temb=temb, ver_main=ver, ver_phases=ver, refresh=None,
         )
-        self._packed_version = ver
-        for pl in self._plans.values():
+        self._packed_version, self._packed_ids = ver, ids
+        for pl in list(self._plans.values()) + list(self._train_engines.values()):
             pl.destroy()
-        self._plans = {}
+        self._plans, self._train_engines = {}, {}
         return self._packed
+
+    def _refresh_packed(self, pk, phases):
+        """re-pack the bf16 GEMM weights / fused biases / conditioning tables in place from the current parameter values"""
+        sd, device = pk["sd"], pk["wblob"].device
+        with torch.no_grad():
+            for k, v in self.state_dict().items():  # no-op aliases for fp32 parameters already on the device
+                if sd[k].data_ptr() != v.data_ptr():
+                    sd[k].copy_(v)
+            if pk["refresh"] is None:
+                pk["refresh"] = self._refresh_lists(pk)
+            r = pk["refresh"]
+            if phases:
+                for dst, wkey, ph in r["phases"]:
+                    dst.copy_(phase_weights(sd[wkey], ph))
+                return
+            torch._foreach_copy_(r["w_dst"], r["w_src"])
+            torch._foreach_copy_(r["b_dst"], r["b_src"])
+            if r["b2_dst"]:
+                torch._foreach_add_(r["b2_dst"], r["b2_src"])
+            torch.cat(r["wt"], dim=0, out=pk["wt_all"])
+            torch.cat(r["bt"], dim=0, out=pk["bt_all"])
+            torch._foreach_add_(r["bt_dst"], r["bt_add"])
+            if pk["ytab"] is not None:
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                try:
+                    torch.mm(torch.nn.functional.silu(sd["label_embed.weight"]), torch.cat(r["wy"], dim=0).t(), out=pk["ytab"])
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _refresh_lists(self, pk):
+        """(destination view, source view) pairs of the in-place re-pack: one strided converting copy per weight"""
+        sd = pk["sd"]
+        down, middle, up, out_ch = unet_block_structure(self._cfg())
+        r = dict(w_dst=[], w_src=[], b_dst=[], b_src=[], b2_dst=[], b2_src=[], wt=[], bt=[], bt_dst=[], bt_add=[], wy=[],
+                 phases=[])
+
+        def wview(name):
+            rows, K = pk["wshape"][name]
+            o = pk["woffs"][name] // 2
+            return pk["wblob"][o: o + rows * K].view(rows, K)
+
+        def w3x3(dst, w):  # dst [Cout, 9*Cin] (possibly a column range of a wider matrix) <- [Cout, Cin, 3, 3]
+            co, ci = w.shape[0], w.shape[1]
+            r["w_dst"].append(dst.view(co, 3, 3, ci))
+            r["w_src"].append(w.permute(0, 2, 3, 1))
+
+        def w1x1(dst, w):
+            r["w_dst"].append(dst)
+            r["w_src"].append(w.view(w.shape[0], w.shape[1]))
+
+        col = 0
+
+        def entry(prefix, layers):
+            nonlocal col
+            for j, l in enumerate(layers):
+                p = f"{prefix}.{j}"
+                if l[0] == "res":
+                    w3x3(wview(p + ".conv1"), sd[p + ".conv1.2.weight"])
+                    r["wt"].append(sd[p + ".time_mlp.1.weight"])
+                    r["bt"].append(sd[p + ".time_mlp.1.bias"])
+                    r["bt_dst"].append(pk["bt_all"][col: col + l[2]])
+                    r["bt_add"].append(sd[p + ".conv1.2.bias"])
+                    col += l[2]
+                    if self.num_classes is not None:
+                        r["wy"].append(sd[p + ".label_proj.1.weight"])
+                    if l[1] != l[2]:
+                        v = wview(p + ".conv2+sc")
+                        w3x3(v[:, : 9 * l[2]], sd[p + ".conv2.3.weight"])
+                        w1x1(v[:, 9 * l[2]:], sd[p + ".shortcut.weight"])
+                        r["b_dst"].append(pk["bias"][p + ".conv2+sc"])
+                        r["b_src"].append(sd[p + ".conv2.3.bias"])
+                        r["b2_dst"].append(pk["bias"][p + ".conv2+sc"])
+                        r["b2_src"].append(sd[p + ".shortcut.bias"])
+                    else:
+                        w3x3(wview(p + ".conv2"), sd[p + ".conv2.3.weight"])
+                        r["b_dst"].append(pk["bias"][p + ".conv2"])
+                        r["b_src"].append(sd[p + ".conv2.3.bias"])
+                elif l[0] == "attn":
+                    for nm in (".qkv", ".proj"):
+                        w1x1(wview(p + nm), sd[p + nm + ".weight"])
+                        r["b_dst"].append(pk["bias"][p + nm])
+                        r["b_src"].append(sd[p + nm + ".bias"])
+                elif l[0] in ("down", "up"):
+                    w3x3(wview(p + ".conv"), sd[p + ".conv.weight"])
+                    r["b_dst"].append(pk["bias"][p + ".conv"])
+                    r["b_src"].append(sd[p + ".conv.bias"])
+                    if l[0] == "up":
+                        for ph in range(4):
+                            r["phases"].append((wview(f"{p}.conv.ph{ph}"), p + ".conv.weight", ph))
+
+        for i, layers in enumerate(down):
+            entry(f"down_blocks.{i}", layers)
+        entry("middle_block", middle)
+        for i, layers in enumerate(up):
+            entry(f"up_blocks.{i}", layers)
+        w3x3(wview("output.2")[: self.out_channels], sd["output.2.weight"])
+        r["b_dst"].append(pk["bias"]["output.2"])
+        r["b_src"].append(sd["output.2.bias"])
+        return r
 
     @staticmethod
     def _split_weight(pk, wname, sc_slice=None):
@@ -509,9 +631,12 @@ class UNet(nn.Module):
     def _run(self, x, t, y, cfg):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise _lib.DmcError("UNet.forward: CUDA tensors only -- the B200 hot path has no CPU / PyTorch fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("the native UNet implements the inference forward only (sampling); "
-                                      "wrap calls in torch.no_grad() / model.eval()")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the native UNet does not differentiate with respect to its image input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if cfg:
+                raise NotImplementedError("forward_cfg is a sampling call: wrap it in torch.no_grad()")
+            return self._run_train(x, t, y)
         _lib.load()
         device = x.device
         self._ensure_packed(device)
@@ -538,6 +663,36 @@ class UNet(nn.Module):
                 pl.run(x[s:s + n], t[s:s + n], y[s:s + n] if has_y else None, cfg,
                        out[s:s + n], out[B + s:B + s + n] if cfg else None)
         return out
+
+    def _run_train(self, x, t, y):
+        """training forward (autograd enabled): native forward with every activation kept, wired into autograd as a chain of
+        per-entry nodes whose backward runs the native backward kernels (models/unet_train.py)"""
+        from .unet_train import UNetTrainEngine
+
+        _lib.load()
+        device = x.device
+        Hh, Ww = self._hw
+        if x.dim() != 4 or x.shape[1] != self.in_channels or tuple(x.shape[2:]) != (Hh, Ww):
+            raise ValueError(f"UNet.forward: expected x of shape [B, {self.in_channels}, {Hh}, {Ww}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        if t.shape[0] != B or (y is not None and y.shape[0] != B):
+            raise ValueError("UNet.forward: t / y batch size mismatch")
+        if self.precision != "bf16":
+            raise NotImplementedError("native UNet training runs in the bf16 mode only")
+        x = x.detach().contiguous().float()
+        t = t.to(device=device, dtype=torch.long).contiguous()
+        has_y = self.num_classes is not None and y is not None
+        if has_y:
+            y = y.to(device=device, dtype=torch.long).contiguous()
+        drop_p = float(self.dropout) if self.training else 0.0
+        with torch.cuda.device(device):
+            self._ensure_packed(device, training=True)  # before the engine lookup: a storage change drops the engines too
+            key = (str(device), B, has_y, drop_p)
+            eng = self._train_engines.get(key)
+            if eng is None:
+                eng = self._train_engines[key] = UNetTrainEngine(self, device, B, has_y, drop_p)
+            eng.forward(x, t, y)
+            return eng.attach()
 
     @contextlib.contextmanager
     def uniform_timesteps(self):
@@ -585,13 +740,15 @@ class UNet(nn.Module):
 class _UNetPlan:
     """Owns one dmc_plan (C side), its workspace and the small staging tensors of one (batch, mode) signature."""
 
-    def __init__(self, net: UNet, pk, device, nimg, x_batch, has_y, uniform_t):
+    def __init__(self, net: UNet, pk, device, nimg, x_batch, has_y, uniform_t, keep=False, drop_p=0.0):
         lib = _lib.load()
         self.lib = lib
         self.nimg, self.x_batch, self.has_y = nimg, x_batch, has_y
         conv_impl = int(os.environ.get("DMC_DEBUG_CONV_IMPL", "0"))
-        split = net.precision == "bf16x3"
-        b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl, split=split).build()
+        split = net.precision == "bf16x3" and not keep
+        b = _PlanBuilder(net, nimg, x_batch, has_y, uniform_t, conv_impl, split=split, keep=keep, drop_p=drop_p).build()
+        self.builder = b if keep else None  # the training engine derives the backward pass from the recorded forward ops
+        self.op_index = []                  # plan op index of every builder op
         self.workspace_bytes = b.arena.peak
         Hh, Ww = net._hw
         R = 1 if uniform_t else nimg
@@ -624,6 +781,7 @@ class _UNetPlan:
 
         self.stem_idx = self.cond_idx = self.head_idx = -1
         for kind, o in b.ops:
+            self.op_index.append(len(self.op_names))
             if kind == "cond":
                 d = _lib.CondDesc()
                 d.t, d.y = self.t_stage.data_ptr(), (self.y_stage.data_ptr() if has_y else None)
@@ -659,6 +817,7 @@ class _UNetPlan:
                 d.B, d.HW, d.groups = nimg, o["srcs"][0].H * o["srcs"][0].W, 8
                 d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
                 d.eps, d.silu, d.out, d.out_lo = 1e-5, o["silu"], ap(o["out"]), ap_lo(o["out"])
+                d.drop_p = o["drop_p"]
                 add(lib.dmc_plan_add_gn_apply, d, o["prefix"])
             elif kind == "conv":
                 d = _lib.ConvDesc()

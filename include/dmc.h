@@ -170,6 +170,8 @@ DMC_API int dmc_channel_sum(const void* src_bf16, float* out, int32_t B, int32_t
 /* dlow[n, i, j, :] (+)= the 2x2 block sum of dhigh (backward of the nearest 2x upsample, models/unet.py:119) */
 DMC_API int dmc_block_sum2x2(const void* dhigh_bf16, void* dlow_bf16, int32_t B, int32_t H, int32_t W, int32_t C,
                      int32_t accumulate, void* stream);
+/* dst (+)= src over n bf16 elements, n % 8 == 0 (gradient of an identity residual branch, models/unet.py:72,99) */
+DMC_API int dmc_add_bf16(void* dst_bf16, const void* src_bf16, int64_t n, int32_t accumulate, void* stream);
 /* fp32 NCHW [B, Csrc, H*W] -> bf16 NHWC [B, H*W, Cdst >= Csrc] with zero-padded channels */
 DMC_API int dmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t Csrc, int32_t HW, int32_t Cdst,
                               void* stream);
@@ -198,6 +200,8 @@ DMC_API double dmc_plan_gemm_flops(const dmc_plan* p);
  *   which = 0: primary input  (stem / patch_embed: x, cond / dit_cond: t)     which = 1: secondary input (cond: y, may be NULL)
  *   which = 2: primary output (conv: out_f32_nchw, head: out)                                                     */
 DMC_API int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* ptr);
+/* new dropout seed of GroupNorm pass `op_index` (training: a fresh mask every step, models/unet.py:53) */
+DMC_API int dmc_plan_set_seed(dmc_plan* p, int32_t op_index, uint32_t seed);
 /* Per-op device timing: runs every op `iters` times between CUDA events on `stream`, writes the average
  * milliseconds per op into ms_out[num ops].  Debug / profiling aid used by bench.py's roofline leg. */
 DMC_API int dmc_plan_time_ops(dmc_plan* p, void* stream, int32_t iters, float* ms_out, int32_t n_out);

@@ -86,7 +86,9 @@ def unet_forward(sd, cfg, x, t, y=None, num_classes=None):
     e = F.linear(e, sd["time_embed.1.weight"], sd["time_embed.1.bias"])
     t_emb = F.linear(F.silu(e), sd["time_embed.3.weight"], sd["time_embed.3.bias"])
     if num_classes is not None and y is not None:
-        y_emb = F.embedding(torch.clamp(y, 0, num_classes), sd["label_embed.weight"])  # unet.py:257-258
+        # unet.py:257-258; the table is nn.Embedding(..., padding_idx=0) (unet.py:183): same forward, and under autograd the null
+        # row 0 receives no gradient
+        y_emb = F.embedding(torch.clamp(y, 0, num_classes), sd["label_embed.weight"], padding_idx=0)
     else:
         y_emb = None
     down, middle, up, _ = unet_block_structure(cfg)
