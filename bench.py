@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="global batch (images per step); default 4096 (256 for ddpm1000)")
-    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50", "dit64_ddim50"],
+    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50", "dit64_ddim50", "train"],
                     help="ddim50_cfg: BASELINE configs[2], the bench line (default); ddpm1000: configs[1] (uncond UNet, DDPM "
                          "1000 steps, batch 256); dit_ddim50: configs[3] (same as --model dit).  The last two are side "
                          "measurements recorded under profiles/, not the headline metric")
@@ -180,7 +180,7 @@ def main():
     if args.workload is None:
         args.workload = "dit_ddim50" if args.model == "dit" else "ddim50_cfg"
     if args.batch is None:
-        args.batch = 256 if args.workload in ("ddpm1000", "dit64_ddim50") else 4096
+        args.batch = 256 if args.workload in ("ddpm1000", "dit64_ddim50") else (128 if args.workload == "train" else 4096)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -196,6 +196,10 @@ def main():
                    os.path.abspath(__file__)] + sys.argv[1:]
             sys.exit(subprocess.call(cmd))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    if args.workload == "train":
+        run_train_workload(args, rank, local_rank, world)
+        return
 
     import torch.distributed as dist
 
@@ -317,6 +321,125 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
         line["cpu_baseline"] = cb
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_train_workload(args, rank, local_rank, world):
+    """BASELINE.json configs[4] (side measurement): the reference trainer's inner loop (utils/trainer.py:221-262) on the native
+    UNet -- labels + 1 with CFG label dropout 0.2, t ~ U[0, 1000), p_losses (q_sample + eps-MSE), backward, clip_grad_norm_(1.0),
+    AdamW(lr 2e-4, wd 1e-4), EMA(0.9999) on rank 0 -- per-GPU batch `--batch` (default 128, weak scaling), DistributedDataParallel
+    over NCCL for N > 1 (gradient all-reduce overlapped with the backward kernels)."""
+    import torch.distributed as dist
+
+    from diffusion_models_collection_b200 import synth
+    from diffusion_models_collection_b200.diffusion import DDPM
+    from diffusion_models_collection_b200.models import UNet
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)
+    net = UNet(**synth.CIFAR_UNET, num_classes=10)
+    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    net = net.to(dev).train()
+    ema = [p.detach().clone() for p in net.parameters()] if rank == 0 else None
+    model = torch.nn.parallel.DistributedDataParallel(net) if world > 1 else net
+    ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
+    B = args.batch
+    g = torch.Generator().manual_seed(42 + rank)
+    nbuf = 4  # rotating host batches (the DataLoader's pinned buffers)
+    x_host = [torch.rand(B, 3, 32, 32, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(nbuf)]
+    y_host = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(nbuf)]
+    x_dev, y_dev = [t.to(dev) for t in x_host], [t.to(dev) for t in y_host]
+    it = [0]
+
+    def step(images, labels, read_loss):
+        labels = labels + 1  # 0 is the null label (utils/trainer.py:225-230)
+        drop = torch.rand(labels.shape, device=dev) < 0.2
+        labels = torch.where(drop, torch.zeros_like(labels), labels)
+        t = torch.randint(0, 1000, (B,), device=dev).long()
+        loss = ddpm.p_losses(model, images, t, labels, loss_type="l2")
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        if ema is not None:
+            torch._foreach_mul_(ema, 0.9999)
+            torch._foreach_add_(ema, [p.detach() for p in net.parameters()], alpha=1 - 0.9999)
+        return loss.item() if read_loss else loss
+
+    def step_resident():
+        i = it[0] = (it[0] + 1) % nbuf
+        return step(x_dev[i], y_dev[i], False)
+
+    def step_e2e():
+        i = it[0] = (it[0] + 1) % nbuf
+        return step(x_host[i].to(dev, non_blocking=True), y_host[i].to(dev, non_blocking=True), True)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    with ClockSampler(local_rank) as cs:
+        ms = timed(step_resident, args.steps)
+    clocks = cs.summary()
+    value = world * B * args.steps / (ms / 1e3)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    loss_now = step_e2e()
+
+    eng = next(iter(net._train_engines.values()))
+    info = eng.describe()
+    line = {"metric": "train_unet_cifar10_images_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "UNet cond (10+1 null) CIFAR-10 32x32 training step: CFG label dropout 0.2, t~U[0,1000), q_sample, "
+                                   "eps-MSE, backward, clip_grad_norm 1.0, fused AdamW, EMA on rank 0 (BASELINE.json configs[4]); "
+                                   "side measurement, not the headline metric",
+                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"DDP x{world} (NCCL all-reduce overlapped)",
+                       "l2": "activations + gradients of one step are > 10x the 126 MB L2", "dropout": 0.1},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},
+            "gpu_launches": int((info["forward_launches"] + info["backward_launches"]) * args.steps),
+            "loss": loss_now}
+    pk = peaks()
+    flops = info["gemm_flops"]
+    line["model_flops_utilization"] = {"achieved_tflops": flops * args.steps / (ms / 1e3) / 1e12, "gemm_flops_per_step": flops,
+                                       "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
+    if rank == 0 and not args.no_roofline:
+        ops = eng.time_ops(iters=3)
+        if args.ops_out:
+            json.dump(ops, open(args.ops_out, "w"), indent=1)
+        tc = [o for o in ops if o["flops"] > 0]
+        tms, tfl = sum(o["ms"] for o in tc), sum(o["flops"] for o in tc)
+        line["roofline"] = {"bound": "tensor", "achieved": tfl / (tms / 1e3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": tfl / (tms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                            "kernel": "tcgen05 convolution family of one training step: forward + input-gradient (same kernel) + "
+                                      "weight-gradient GEMMs, each timed alone (burst peak)",
+                            "tensor_ms": tms, "all_ops_ms": sum(o["ms"] for o in ops), "step_ms": ms / args.steps,
+                            "by_kind_ms": {k: sum(o["ms"] for o in ops if o["kind"] == k) for k in sorted({o["kind"] for o in ops})}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -139,7 +139,8 @@ SYMBOLS = {
     "dmc_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
     "dmc_gn_backward": (C.c_int, [C.POINTER(GnBwdDesc), vp]),
     "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
-    "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "dmc_dilate2x": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_add_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp]),
     "dmc_block_sum2x2": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

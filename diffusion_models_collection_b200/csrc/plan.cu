@@ -169,8 +169,11 @@ int dmc_attention_backward(const dmc_attn_bwd_desc* d, void* stream) {
   return launch_attention_backward(*d, static_cast<cudaStream_t>(stream));
 }
 int dmc_channel_sum(const void* src, float* out, int32_t B, int32_t HW, int32_t C, int32_t per_image, int32_t accumulate,
-                    void* stream) {
-  return launch_channel_sum(src, out, B, HW, C, per_image, accumulate, static_cast<cudaStream_t>(stream));
+                    float* scratch, void* stream) {
+  return launch_channel_sum(src, out, B, HW, C, per_image, accumulate, scratch, static_cast<cudaStream_t>(stream));
+}
+int dmc_dilate2x(const void* src, void* dst, int32_t B, int32_t h, int32_t w, int32_t C, void* stream) {
+  return launch_dilate2x(src, dst, B, h, w, C, static_cast<cudaStream_t>(stream));
 }
 int dmc_add_bf16(void* dst, const void* src, int64_t n, int32_t accumulate, void* stream) {
   DMC_REQUIRE(n > 0, "dmc_add_bf16: n=%lld", static_cast<long long>(n));

@@ -408,6 +408,10 @@ int launch_attention_backward(const dmc_attn_bwd_desc& d, cudaStream_t st) {
   const int hd = d.C / d.heads;
   DMC_REQUIRE(d.C == d.heads * hd && hd == 64 && d.L >= 1 && d.L <= 256, "attention_backward: head dim 64 and L <= 256 (C=%d heads=%d L=%d)",
               d.C, d.heads, d.L);
+  {
+    const char* e = getenv("DMC_ATTN_BWD_IMPL");  // 1: the CUDA-core fp32 kernel below (debug / A-B)
+    if (!(e && e[0] == '1')) return launch_attention_backward_mma(d, st);
+  }
   const size_t smem = static_cast<size_t>(4) * d.L * hd * 2 + static_cast<size_t>(3) * d.L * 4;
   static bool attr = false;
   if (!attr) {
@@ -426,30 +430,100 @@ int launch_attention_backward(const dmc_attn_bwd_desc& d, cudaStream_t st) {
 // =============================================================================================
 // Small reductions and layout kernels
 // =============================================================================================
-// out[n or 0][c] = sum over the pixels (and, if !per_image, the images) of src[n, p, c]   (bias / conditioning-row grads)
-__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ out,
-                                                          int B, int HW, int C, int per_image, int accumulate) {
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane_row = threadIdx.x >> 6;  // 4 rows of 64 channels
-  __shared__ float red[4][64];
-  const int n0 = per_image ? blockIdx.y : 0, n1 = per_image ? blockIdx.y + 1 : B;
-  float s = 0.f;
-  if (c < C)
-    for (int n = n0; n < n1; ++n)
-      for (int p = lane_row; p < HW; p += 4) s += __bfloat162float(src[(static_cast<size_t>(n) * HW + p) * C + c]);
-  red[lane_row][threadIdx.x & 63] = s;
+// out[n][c] (+)= sum over the pixels of src[n, p, c]  (per-image conditioning-row gradients); the bias gradient adds the
+// images in index order in a second small kernel (deterministic).  One CTA = one image x 128 channels; 16 pixel lanes x
+// 16 channel vectors of 16 bytes.
+__global__ void __launch_bounds__(256) channel_sum_image_kernel(const uint4* __restrict__ src, float* __restrict__ out, int HW,
+                                                                int C, int accumulate) {
+  __shared__ float red[16][129];
+  const int C8 = C >> 3;
+  const int n = blockIdx.y, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int v8 = blockIdx.x * 16 + tx;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (v8 < C8) {
+    const uint4* base = src + static_cast<size_t>(n) * HW * C8 + v8;
+    int p = ty;
+    for (; p + 48 < HW; p += 64) {  // four independent loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(base + static_cast<size_t>(p + 16 * u) * C8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(w[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      }
+    }
+    for (; p < HW; p += 16) {
+      const uint4 v = __ldg(base + static_cast<size_t>(p) * C8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(w[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
   __syncthreads();
-  if (lane_row == 0 && c < C) {
-    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    float* o = out + static_cast<size_t>(per_image ? blockIdx.y : 0) * C + c;
-    *o = accumulate ? *o + s : s;
+  if (threadIdx.x < 128) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < C) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s2 += red[r][threadIdx.x];
+      float* o = out + static_cast<size_t>(n) * C + c;
+      *o = accumulate ? *o + s2 : s2;
+    }
   }
 }
 
-int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int per_image, int accumulate, cudaStream_t st) {
-  DMC_REQUIRE(src && out && B > 0 && HW > 0 && C > 0, "channel_sum: bad arguments");
-  dim3 grid((C + 63) / 64, per_image ? B : 1);
-  channel_sum_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), out, B, HW, C, per_image, accumulate);
+__global__ void __launch_bounds__(256) channel_sum_total_kernel(const float* __restrict__ per_image, float* __restrict__ out, int B,
+                                                                int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s2 = 0.f;
+  for (int n = 0; n < B; ++n) s2 += per_image[static_cast<size_t>(n) * C + c];
+  out[c] = accumulate ? out[c] + s2 : s2;
+}
+
+int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int per_image, int accumulate, float* scratch,
+                       cudaStream_t st) {
+  DMC_REQUIRE(src && out && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "channel_sum: bad arguments");
+  DMC_REQUIRE(per_image || scratch, "channel_sum: the all-image sum needs a [B, C] fp32 scratch buffer");
+  dim3 grid((C + 127) / 128, B);
+  channel_sum_image_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), per_image ? out : scratch, HW, C,
+                                                 per_image ? accumulate : 0);
+  DMC_CUDA_OK(cudaGetLastError());
+  if (!per_image) {
+    channel_sum_total_kernel<<<(C + 255) / 256, 256, 0, st>>>(scratch, out, B, C, accumulate);
+    DMC_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// dst[n, 2i, 2j, :] = src[n, i, j, :], zeros elsewhere: the gradient of a stride-2 convolution's output spread onto the
+// input grid, so that its input gradient is an ordinary stride-1 3x3 convolution (tensor-core kernel) with flipped weights
+__global__ void __launch_bounds__(256) dilate2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int h, int w,
+                                                       int C8) {
+  const size_t total = static_cast<size_t>(B) * 4 * h * w * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cb = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int x = static_cast<int>(pix % (2 * w)), y = static_cast<int>((pix / (2 * w)) % (2 * h));
+    const size_t n = pix / (static_cast<size_t>(4) * w * h);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (((x | y) & 1) == 0) v = __ldg(src + ((n * h + (y >> 1)) * w + (x >> 1)) * C8 + cb);
+    dst[i] = v;
+  }
+}
+
+int launch_dilate2x(const void* src, void* dst, int B, int h, int w, int C, cudaStream_t st) {
+  DMC_REQUIRE(src && dst && B > 0 && h > 0 && w > 0 && C % 8 == 0, "dilate2x: bad arguments");
+  const size_t total = static_cast<size_t>(B) * 4 * h * w * (C / 8);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  dilate2x_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, h, w, C / 8);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

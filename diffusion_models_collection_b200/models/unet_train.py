@@ -164,18 +164,18 @@ class UNetTrainEngine:
         gn_scratch_need = 64
         cur = None
 
-        def emit(fn, *args):
-            cur.append((fn, args))
+        def emit(fn, *args, kind="", name="", flops=0.0):
+            cur.append((fn, args, dict(kind=kind, name=name, flops=float(flops))))
 
-        def emit_py(fn):
-            cur.append((fn, None))
+        def emit_py(fn, name=""):
+            cur.append((fn, None, dict(kind="torch_copy", name=name, flops=0.0)))
 
         def dgrad_matrix(kind, wkey, rows, K, extra=None):
             t = torch.zeros((rows, K), dtype=bf16, device=device)
             self.dgrad_items.append((t, kind, wkey, extra))
             return t
 
-        def conv_dgrad(dyp, dyC, taps, Ho, Wo, wmat, dst):
+        def conv_dgrad(dyp, dyC, taps, Ho, Wo, wmat, dst, name, real_c=None, flops_scale=1.0):
             ptr, acc = contribute(dst)
             d = _lib.ConvDesc()
             d.nsrc = 1
@@ -186,20 +186,26 @@ class UNetTrainEngine:
             if acc:
                 d.residual = ptr  # accumulate: out = conv + out (every element is read, then written, by the same thread)
             idx = _lib.check(lib.dmc_plan_add_conv(handle, C.byref(d)), "dgrad conv")
-            emit(lib.dmc_plan_run_op, handle, idx)
+            emit(lib.dmc_plan_run_op, handle, idx, kind="conv_dgrad", name=name,
+                 flops=2.0 * B * Ho * Wo * dst.C * taps * (real_c or dyC) * flops_scale)
 
-        def wgrad(xp, xC, dyp, dyC, H, W, stride, taps, dw):
+        def wgrad(xp, xC, dyp, dyC, H, W, stride, taps, dw, name, real=None):
             d = _lib.WgradDesc()
             d.x, d.dy, d.B, d.Hin, d.Win, d.Cin, d.Cout, d.stride, d.taps = xp, dyp, B, H, W, xC, dyC, stride, taps
             d.splits = _lib.check(lib.dmc_conv_wgrad_splits(C.byref(d)), "dmc_conv_wgrad_splits")
             d.dw, d.accumulate = dw.data_ptr(), 0
             wg_descs.append(d)
             self._keep.append(dw)
-            emit(lib.dmc_conv_wgrad, C.byref(d))
+            emit(lib.dmc_conv_wgrad, C.byref(d), kind="conv_wgrad", name=name,
+                 flops=2.0 * B * (H // stride) * (W // stride) * taps * (real or xC * dyC))
+
+        cs_scratch = torch.empty(B * 1024, dtype=f32, device=device)  # [B, C <= 1024] per-image partial sums
+        self._keep.append(cs_scratch)
 
         def channel_sum(dyp, out, HW, Cc, per_image):
+            assert Cc <= 1024
             self._keep.append(out)
-            emit(lib.dmc_channel_sum, dyp, out.data_ptr(), B, HW, Cc, per_image, 0)
+            emit(lib.dmc_channel_sum, dyp, out.data_ptr(), B, HW, Cc, per_image, 0, cs_scratch.data_ptr(), kind="channel_sum")
 
         def copy_op(dst, src):
             emit_py(lambda: dst.copy_(src))
@@ -249,32 +255,36 @@ class UNetTrainEngine:
                 a_in = srcs[0]
                 if head:
                     tmpw = torch.empty((128, a_in.C, 3, 3), dtype=f32, device=device)
-                    wgrad(ap(a_in), a_in.C, dyp, 128, H, W, 1, 9, tmpw)
+                    wgrad(ap(a_in), a_in.C, dyp, 128, H, W, 1, 9, tmpw, wname, real=a_in.C * net.out_channels)
                     copy_op(self.gview[wkey], tmpw[: net.out_channels])
                 else:
-                    wgrad(ap(a_in), a_in.C, dyp, dyC, H, W, stride, taps[0], self.gview[wkey])
+                    wgrad(ap(a_in), a_in.C, dyp, dyC, H, W, stride, taps[0], self.gview[wkey], wname)
                 off = 0
                 cin_sc = sum(s.C for s in srcs[1:])
                 for s_ in srcs[1:]:  # fused 1x1 shortcut over the raw block inputs: one slice of shortcut.weight per source
                     tmp = torch.empty((dyC, s_.C), dtype=f32, device=device)
-                    wgrad(ap(s_), s_.C, dyp, dyC, H, W, 1, 1, tmp)
+                    wgrad(ap(s_), s_.C, dyp, dyC, H, W, 1, 1, tmp, p + ".shortcut")
                     copy_op(self.gview[p + ".shortcut.weight"].view(dyC, cin_sc)[:, off: off + s_.C], tmp)
                     off += s_.C
                 # --- input gradients
                 off = 0
                 for s_ in srcs[1:]:
                     wm = dgrad_matrix("1x1", p + ".shortcut.weight", s_.C, dyC, (off, s_.C))
-                    conv_dgrad(dyp, dyC, 1, Ho, Wo, wm, s_)
+                    conv_dgrad(dyp, dyC, 1, Ho, Wo, wm, s_, p + ".shortcut")
                     off += s_.C
                 if stride == 2:
-                    ptr, acc = contribute(a_in)
-                    emit(lib.dmc_conv_dgrad_strided, dyp, sd[wkey].data_ptr(), ptr, B, H, W, a_in.C, dyC, 2, acc)
+                    # Downsample: spread dY onto the input grid (zeros between), then the ordinary stride-1 input-gradient GEMM
+                    dil = torch.empty((B, H, W, dyC), dtype=bf16, device=device)
+                    self._keep.append(dil)
+                    emit(lib.dmc_dilate2x, dyp, dil.data_ptr(), B, Ho, Wo, dyC, kind="dilate2x", name=wname)
+                    wm = dgrad_matrix("3x3", wkey, a_in.C, 9 * dyC, None)
+                    conv_dgrad(dil.data_ptr(), dyC, 9, H, W, wm, a_in, wname, flops_scale=0.25)
                 elif taps[0] == 9:
                     wm = dgrad_matrix("3x3", wkey, a_in.C, 9 * dyC, None)
-                    conv_dgrad(dyp, dyC, 9, Ho, Wo, wm, a_in)
+                    conv_dgrad(dyp, dyC, 9, Ho, Wo, wm, a_in, wname, real_c=net.out_channels if head else None)
                 else:
                     wm = dgrad_matrix("1x1", wkey, a_in.C, dyC, (0, a_in.C))
-                    conv_dgrad(dyp, dyC, 1, Ho, Wo, wm, a_in)
+                    conv_dgrad(dyp, dyC, 1, Ho, Wo, wm, a_in, wname)
                 # --- identity residual branch (models/unet.py:72 with an Identity shortcut, :99)
                 res = o["residual"]
                 if res is not None:
@@ -282,7 +292,7 @@ class UNetTrainEngine:
                         G[id(res)] = G[id(o["out"])]
                         written.add(id(res))
                     else:
-                        emit(lib.dmc_add_bf16, gbuf(res).data_ptr(), dyp, B * res.H * res.W * res.C, 1)
+                        emit(lib.dmc_add_bf16, gbuf(res).data_ptr(), dyp, B * res.H * res.W * res.C, 1, kind="add")
 
             elif kind == "gn_apply":
                 out, srcs = o["out"], o["srcs"]
@@ -304,7 +314,7 @@ class UNetTrainEngine:
                 if o["drop_p"] > 0:
                     self.drop_ops.append((pl.op_index[i], d, layer_no))
                     layer_no += 1
-                emit(lib.dmc_gn_backward, C.byref(d))
+                emit(lib.dmc_gn_backward, C.byref(d), kind="gn_backward", name=o["prefix"])
 
             elif kind == "attention":
                 qkv, ao = o["qkv"], o["out"]
@@ -314,20 +324,20 @@ class UNetTrainEngine:
                 d.qkv, d.out, d.dout, d.dqkv = ap(qkv), ap(ao), dy_of(ao), ptr
                 d.B, d.L, d.heads, d.C = B, o["L"], 4, o["C"]
                 self._keep.append(d)
-                emit(lib.dmc_attention_backward, C.byref(d))
+                emit(lib.dmc_attention_backward, C.byref(d), kind="attention_backward")
 
             elif kind == "upsample":
                 src, upb = o["src"], o["out"]
                 dyp = dy_of(upb)
                 ptr, acc = contribute(src)
-                emit(lib.dmc_block_sum2x2, dyp, ptr, B, src.H, src.W, src.C, acc)
+                emit(lib.dmc_block_sum2x2, dyp, ptr, B, src.H, src.W, src.C, acc, kind="block_sum2x2")
 
             elif kind == "stem":
                 h0 = o["out"]
                 dyp = dy_of(h0)
                 channel_sum(dyp, self.gview["input_conv.bias"], Hh * Ww, h0.C, 0)
                 tmpw = torch.empty((h0.C, 64, 3, 3), dtype=f32, device=device)
-                wgrad(self.xpad.data_ptr(), 64, dyp, h0.C, Hh, Ww, 1, 9, tmpw)
+                wgrad(self.xpad.data_ptr(), 64, dyp, h0.C, Hh, Ww, 1, 9, tmpw, "input_conv", real=net.in_channels * h0.C)
                 copy_op(self.gview["input_conv.weight"], tmpw[:, : net.in_channels])
 
         need = max(d.splits * d.Cout * d.taps * d.Cin for d in wg_descs)
@@ -401,7 +411,7 @@ class UNetTrainEngine:
     def _run_ops(self, ops):
         st = _lib.stream_ptr()
         lib = self.lib
-        for fn, args in ops:
+        for fn, args, _ in ops:
             if args is None:
                 fn()
             elif fn(*args, st) < 0:
@@ -453,6 +463,34 @@ class UNetTrainEngine:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return list(grads)
+
+    def describe(self):
+        """launch and FLOP counts of one training step (bench.py's gpu_launches / utilisation claims)"""
+        per = {"conv_wgrad": 2, "gn_backward": 2, "torch_copy": 0}
+        ops = [m for s in self.segs for _, _, m in self.bwd[s]]
+        return dict(forward_launches=self.fwd.num_launches + 1,
+                    backward_launches=sum(per.get(m["kind"], 1) for m in ops) + 1,
+                    gemm_flops=float(self.fwd.gemm_flops) + sum(m["flops"] for m in ops))
+
+    def time_ops(self, iters=3):
+        """device time of every forward and backward op run alone (CUDA events on the launching stream); call after a step"""
+        out = [dict(o, phase="forward") for o in self.fwd.time_ops(iters)]
+        st = _lib.stream_ptr()
+        for s in reversed(self.segs):
+            for fn, args, m in self.bwd[s]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for it in range(iters + 1):
+                    if it == 1:
+                        e0.record()
+                    if args is None:
+                        fn()
+                    elif fn(*args, st) < 0:
+                        raise _lib.DmcError(f"time_ops: {self.lib.dmc_last_error().decode()}")
+                e1.record()
+                e1.synchronize()
+                out.append(dict(name=m["name"], kind=m["kind"], ms=e0.elapsed_time(e1) / iters, flops=m["flops"], bytes=0.0,
+                                phase="backward"))
+        return out
 
     def destroy(self):
         if getattr(self, "bplan", None) is not None:

@@ -154,7 +154,7 @@ typedef struct {
 DMC_API int dmc_gn_backward(const dmc_gn_bwd_desc* d, void* stream);
 
 /* Attention backward (models/unet.py:88-96 under autograd): dqkv from qkv, the forward output and its gradient.
- * CUDA-core fp32 kernel, head dim 64, L <= 256 (first version: the tensor-core form is future work). */
+ * Head dim 64, L <= 256; warp-level tensor-core kernel (mma.sync bf16, fp32 accumulate), one CTA per (image, head). */
 typedef struct {
   const void* qkv;  /* bf16 [B, L, 3C] */
   const void* out;  /* bf16 [B, L, C] forward output */
@@ -164,9 +164,14 @@ typedef struct {
 } dmc_attn_bwd_desc;
 DMC_API int dmc_attention_backward(const dmc_attn_bwd_desc* d, void* stream);
 
-/* out[n or 0][c] (+)= sum over pixels (and images unless per_image) of src[n, p, c]: bias and conditioning-row gradients */
+/* out[n or 0][c] (+)= sum over pixels (and images unless per_image) of src[n, p, c]: bias and conditioning-row gradients.
+ * scratch: fp32 [B, C], needed when per_image == 0 (the images are added in index order by a second kernel) */
 DMC_API int dmc_channel_sum(const void* src_bf16, float* out, int32_t B, int32_t HW, int32_t C, int32_t per_image,
-                    int32_t accumulate, void* stream);
+                    int32_t accumulate, float* scratch, void* stream);
+/* dst[n, 2i, 2j, :] = src[n, i, j, :], zeros elsewhere (bf16 NHWC, src [B, h, w, C] -> dst [B, 2h, 2w, C]): spreads the output
+ * gradient of a stride-2 convolution (Downsample, models/unet.py:106-109) onto the input grid, so that its input gradient is
+ * the stride-1 tensor-core convolution with transposed, tap-flipped weights */
+DMC_API int dmc_dilate2x(const void* src_bf16, void* dst_bf16, int32_t B, int32_t h, int32_t w, int32_t C, void* stream);
 /* dlow[n, i, j, :] (+)= the 2x2 block sum of dhigh (backward of the nearest 2x upsample, models/unet.py:119) */
 DMC_API int dmc_block_sum2x2(const void* dhigh_bf16, void* dlow_bf16, int32_t B, int32_t H, int32_t W, int32_t C,
                      int32_t accumulate, void* stream);

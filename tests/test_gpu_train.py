@@ -184,7 +184,7 @@ def test_dropout_mask_is_the_same_in_forward_and_backward():
     assert rel_l2(dg, rg) < 1e-4 and rel_l2(db, rb) < 1e-4
 
 
-@pytest.mark.parametrize("L,heads,B", [(256, 4, 2), (64, 4, 3), (16, 4, 2), (128, 2, 1)])
+@pytest.mark.parametrize("L,heads,B", [(256, 4, 2), (64, 4, 3), (16, 4, 2), (128, 2, 1), (100, 4, 2), (200, 1, 1)])
 def test_attention_backward(L, heads, B):
     lib = _lib.load()
     hd, C_ = 64, heads * 64
@@ -201,7 +201,10 @@ def test_attention_backward(L, heads, B):
     _lib.check(lib.dmc_attention_backward(C.byref(d), _lib.stream_ptr()), "attention_backward")
     torch.cuda.synchronize()
     assert torch.isfinite(dqkv).all()
-    assert rel_l2(dqkv.float(), ref) < 8e-3  # o is read in bf16 for D = do . o; outputs stored in bf16
+    # o is read in bf16 for D = do . o, P and dS are rounded to bf16 for the second GEMMs, outputs stored in bf16
+    assert rel_l2(dqkv.float(), ref) < 1.2e-2
+    for i in range(3):  # q, k and v parts separately
+        assert rel_l2(dqkv[..., i * C_:(i + 1) * C_].float(), ref[..., i * C_:(i + 1) * C_]) < 1.5e-2, i
 
 
 def test_small_training_kernels():
@@ -210,9 +213,15 @@ def test_small_training_kernels():
     B, H, C_ = 3, 8, 128
     t = _rand((B, H * H, C_), 1).to(torch.bfloat16)
     out = torch.zeros(C_, device="cuda")
-    _lib.check(lib.dmc_channel_sum(t.data_ptr(), out.data_ptr(), B, H * H, C_, 0, 0, st), "channel_sum")
+    scratch = torch.empty(B * C_, device="cuda")
+    _lib.check(lib.dmc_channel_sum(t.data_ptr(), out.data_ptr(), B, H * H, C_, 0, 0, scratch.data_ptr(), st), "channel_sum")
     per = torch.zeros(B, C_, device="cuda")
-    _lib.check(lib.dmc_channel_sum(t.data_ptr(), per.data_ptr(), B, H * H, C_, 1, 0, st), "channel_sum per image")
+    _lib.check(lib.dmc_channel_sum(t.data_ptr(), per.data_ptr(), B, H * H, C_, 1, 0, None, st), "channel_sum per image")
+    big = _rand((5, 32 * 32, 768), 7).to(torch.bfloat16)  # several channel chunks, unrolled pixel loop + tail
+    big_out, big_scr = torch.full((768,), 3.0, device="cuda"), torch.empty(5 * 768, device="cuda")
+    _lib.check(lib.dmc_channel_sum(big.data_ptr(), big_out.data_ptr(), 5, 1024, 768, 0, 1, big_scr.data_ptr(), st), "channel_sum acc")
+    dil = torch.full((B, 2 * H, 2 * H, C_), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dmc_dilate2x(t.data_ptr(), dil.data_ptr(), B, H, H, C_, st), "dilate2x")
     hi = _rand((B, 2 * H, 2 * H, C_), 2).to(torch.bfloat16)
     lo = torch.zeros((B, H, H, C_), device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.dmc_block_sum2x2(hi.data_ptr(), lo.data_ptr(), B, H, H, C_, 0, st), "block_sum")
@@ -222,6 +231,10 @@ def test_small_training_kernels():
     torch.cuda.synchronize()
     assert rel_l2(out, t.float().sum(dim=(0, 1))) < 1e-5
     assert rel_l2(per, t.float().sum(dim=1)) < 1e-5
+    assert rel_l2(big_out, 3.0 + big.float().sum(dim=(0, 1))) < 1e-5
+    want_d = torch.zeros_like(dil)
+    want_d[:, ::2, ::2] = t.reshape(B, H, H, C_)
+    assert torch.equal(dil, want_d)
     want = hi.float().reshape(B, H, 2, H, 2, C_).sum(dim=(2, 4))
     assert rel_l2(lo.float(), want) < 5e-3
     assert torch.equal(dst[..., :3].float(), src.permute(0, 2, 3, 1).to(torch.bfloat16).float()) and float(dst[..., 3:].abs().max()) == 0.0
@@ -240,3 +253,37 @@ def test_strided_conv_input_gradient(cin, cout, H, B):
     _lib.check(lib.dmc_conv_dgrad_strided(dyn.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, cin, cout, 2, 0, _lib.stream_ptr()), "dgrad")
     torch.cuda.synchronize()
     assert rel_l2(dx.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+@pytest.mark.parametrize("cin,cout,H,B", [(128, 128, 32, 2), (256, 256, 16, 3), (256, 256, 8, 2)])
+def test_strided_conv_input_gradient_as_dilate_plus_conv(cin, cout, H, B):
+    """Downsample backward on tensor cores: dY spread onto the input grid, then the stride-1 flipped/transposed-weight conv"""
+    lib = _lib.load()
+    x = _q(_rand((B, cin, H, H), 1)).requires_grad_(True)
+    w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
+    y = F.conv2d(x, w, None, stride=2, padding=1)
+    dy = _q(_rand(tuple(y.shape), 3))
+    (ref,) = torch.autograd.grad(y, x, dy)
+    dyn = nhwc_bf16(dy)
+    dil = torch.empty((B, H, H, cout), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dmc_dilate2x(dyn.data_ptr(), dil.data_ptr(), B, H // 2, H // 2, cout, _lib.stream_ptr()), "dilate2x")
+    wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    out, _ = run_conv([dil], [9], pack3(wt), cin)
+    assert rel_l2(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+def test_conv_accumulates_in_place_through_its_residual():
+    """the training engine accumulates input gradients with out == residual (each element read, then written, by one thread)"""
+    B, cin, cout, H = 2, 256, 128, 16
+    x = nhwc_bf16(_q(_rand((B, cin, H, H), 1)))
+    w = _q(_rand((cout, cin, 3, 3), 2, (cin * 9) ** -0.5))
+    base = nhwc_bf16(_q(_rand((B, cout, H, H), 3)))
+    sep, _ = run_conv([x], [9], pack3(w), cout, residual=base)
+    inplace = base.clone()
+    run_conv([x], [9], pack3(w), cout, residual=inplace, out_tensor=inplace)
+    assert torch.equal(sep, inplace)
+    w1 = _q(_rand((cout, cin, 1, 1), 4, cin ** -0.5)).reshape(cout, cin)  # short-K variant (resident weights, TMA epilogue)
+    sep1, _ = run_conv([x], [1], w1, cout, residual=base)
+    inplace1 = base.clone()
+    run_conv([x], [1], w1, cout, residual=inplace1, out_tensor=inplace1)
+    assert torch.equal(sep1, inplace1)
