@@ -221,7 +221,9 @@ int conv_wgrad_splits(const dmc_wgrad_desc& d) {
   const int Ho = d.Hin / d.stride, Wo = d.Win / d.stride;
   const long long tiles = (static_cast<long long>(d.B) * Ho * Wo + WG_PIX - 1) / WG_PIX;
   const int items = (d.Cout / 128) * (d.Cin / 64) * ((d.taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS);
-  int splits = std::max(1, (2 * num_sms() + items - 1) / std::max(items, 1));
+  // whole waves: one CTA per SM (226 KB of shared memory each), so the grid is the largest multiple of `items` that fits in two
+  // waves (a grid of 2 * SMs + a few CTAs would run a third, almost empty wave)
+  int splits = std::max(1, (2 * num_sms()) / std::max(items, 1));
   return static_cast<int>(std::min<long long>(splits, std::max<long long>(tiles, 1)));
 }
 

@@ -103,8 +103,10 @@ __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, cons
       if (a.drop_thresh != 0u) d = dropout_keep(a.seed, idx0 + c, a.drop_thresh) ? d * a.drop_scale : 0.f;
       if (a.silu) {
         const float z = fmaf(xh[c], gam[c], bet[c]);
-        const float sg = 1.0f / (1.0f + __expf(-z));
-        d *= sg * (1.0f + z * (1.0f - sg));
+        float th;  // sigmoid(z) = 0.5 + 0.5 tanh(z / 2): one MUFU op (the forward pass uses the same form)
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
+        const float sg = fmaf(0.5f, th, 0.5f);
+        d *= sg * fmaf(z, 1.0f - sg, 1.0f);
       }
       dz[c] = d;
     }
@@ -112,7 +114,7 @@ __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, cons
 }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   __shared__ float s_mean[32], s_rstd[32], s_g1[32], s_g2[32];
   extern __shared__ float red[];  // pass A: [rows][C8][18]
   const int C8 = a.C0_8 + a.C1_8;
@@ -170,9 +172,19 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) dgam[j] = dbet[j] = 0.f;
   if (active) {
+    uint4 xn = make_uint4(0, 0, 0, 0), dn = xn, on = xn;
+    if (p0 + r0 < p1) {  // software pipeline: the next pixel's loads are in flight while this one is processed
+      xn = __ldg(src + static_cast<size_t>(p0 + r0) * sstride);
+      dn = __ldg(dout + static_cast<size_t>(p0 + r0) * C8);
+      if (APPLY && acc) on = *(dsrc + static_cast<size_t>(p0 + r0) * sstride);
+    }
     for (int p = p0 + r0; p < p1; p += rpi) {
-      const uint4 xv = __ldg(src + static_cast<size_t>(p) * sstride);
-      const uint4 dv = __ldg(dout + static_cast<size_t>(p) * C8);
+      const uint4 xv = xn, dv = dn, old = on;
+      if (p + rpi < p1) {
+        xn = __ldg(src + static_cast<size_t>(p + rpi) * sstride);
+        dn = __ldg(dout + static_cast<size_t>(p + rpi) * C8);
+        if (APPLY && acc) on = *(dsrc + static_cast<size_t>(p + rpi) * sstride);
+      }
       float xh[8], dz[8];
       gn_dz8(a, xv, dv, mean, rstd, gam, bet, ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8, xh, dz);
       if (!APPLY) {
@@ -191,7 +203,6 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
         for (int j = 0; j < 8; ++j) dx[j] = rstd * (dz[j] * gam[j] - m1 - xh[j] * m2);
         uint4* o = dsrc + static_cast<size_t>(p) * sstride;
         if (acc) {
-          const uint4 old = *o;
           const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -238,19 +249,37 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
   }
 }
 
-// dgamma[c], dbeta[c] = sum over (image, slab) of the partials, in index order
-__global__ void __launch_bounds__(256) gn_param_reduce_kernel(const float2* __restrict__ pgb, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, int rows, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// dgamma[c], dbeta[c] = sum over (image, slab) of the partials: 32 row lanes per channel, each adding its rows in index
+// order, then the 32 lane sums in lane order (fixed association: bit-reproducible)
+__global__ void __launch_bounds__(1024) gn_param_reduce_kernel(const float2* __restrict__ pgb, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, int rows, int C) {
+  __shared__ float2 red[32][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float g = 0.f, b = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float2 v = pgb[static_cast<size_t>(r) * C + c];
-    g += v.x;
-    b += v.y;
+  if (c < C) {
+    int r = rl;
+    for (; r + 96 < rows; r += 128) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = pgb[static_cast<size_t>(r + 32 * u) * C + c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { g += v[u].x; b += v[u].y; }
+    }
+    for (; r < rows; r += 32) {
+      const float2 v = pgb[static_cast<size_t>(r) * C + c];
+      g += v.x; b += v.y;
+    }
   }
-  dgamma[c] = g;
-  dbeta[c] = b;
+  red[rl][cl] = make_float2(g, b);
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    g = 0.f; b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { g += red[k][cl].x; b += red[k][cl].y; }
+    dgamma[c] = g;
+    dbeta[c] = b;
+  }
 }
 
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
@@ -288,7 +317,7 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   }
   gn_bwd_kernel<false><<<grid, 256, smem, st>>>(a);
   gn_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
-  gn_param_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
+  gn_param_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
                                                           d.B * slabs, C);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;

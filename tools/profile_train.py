@@ -1,0 +1,42 @@
+"""Runs selected backward ops of one training step inside a cudaProfiler range (for ncu --profile-from-start off).
+   python tools/profile_train.py kind[:name] ...   e.g.  conv_wgrad:down_blocks.4.0.conv2 gn_backward:up_blocks.9.0.conv1.0"""
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, ".")
+from diffusion_models_collection_b200 import _lib, synth  # noqa: E402
+from diffusion_models_collection_b200.models import UNet  # noqa: E402
+
+
+def main():
+    sel = [a.split(":", 1) + [""] for a in sys.argv[1:]]
+    B = 128
+    torch.manual_seed(0)
+    net = UNet(**synth.CIFAR_UNET, num_classes=10)
+    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    net = net.cuda().train()
+    x = torch.randn(B, 3, 32, 32, device="cuda")
+    t = torch.randint(0, 1000, (B,), device="cuda")
+    y = torch.randint(0, 11, (B,), device="cuda")
+    for _ in range(2):
+        F.mse_loss(torch.randn_like(x), net(x, t, y)).backward()
+    torch.cuda.synchronize()
+    eng = next(iter(net._train_engines.values()))
+    st = _lib.stream_ptr()
+    picked = []
+    for s in reversed(eng.segs):
+        for fn, args, m in eng.bwd[s]:
+            if args is not None and any(m["kind"] == k[0] and (not k[1] or m["name"] == k[1]) for k in sel):
+                picked.append((fn, args, m))
+    print("profiling", [(m["kind"], m["name"]) for _, _, m in picked])
+    torch.cuda.profiler.start()
+    for fn, args, m in picked:
+        fn(*args, st)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()
