@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -184,6 +185,147 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-slab variant (stride 1, image width 8..64, Cin % 128 == 0): one CTA = 128 output channels x 128 input channels x the
+// three VERTICAL taps of one column shift dw (or the single tap of a 1x1 convolution) x one slice of the pixels.
+// A stage is BH full image rows (64 pixels).  The X operand of the three taps is ONE TMA box of BH + 2 rows: the tap (dh, dw)
+// is the same shared-memory slab read BW pixels (a whole number of 1024-byte swizzle atoms) further down, so X moves
+// L2 -> SM once instead of three times, and every MMA is 128 x 128 x 16 (half the shared-memory operand bytes per MAC of the
+// 128 x 64 form above).
+// ---------------------------------------------------------------------------------------------------------------------
+struct WgradSlabParams {
+  int BW, BH, tiles_h, num_tiles;
+  int Cin, Cout, taps, ndw, splits;
+  int nst, stage_bytes, slab_block_bytes, halo;
+  float* partial;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const __grid_constant__ WgradSlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.nst * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int item = blockIdx.x;
+  const int co_tiles = p.Cout / 128, ci_tiles = p.Cin / 128;
+  const int co_tile = item % co_tiles; item /= co_tiles;
+  const int ci_tile = item % ci_tiles; item /= ci_tiles;
+  const int dwi = item % p.ndw; item /= p.ndw;
+  const int split = item;
+  const int nv = p.taps == 9 ? 3 : 1;      // vertical taps sharing the slab
+  const int dw = p.taps == 9 ? dwi - 1 : 0;
+  const int t_begin = static_cast<int>(static_cast<long long>(split) * p.num_tiles / p.splits);
+  const int t_end = static_cast<int>(static_cast<long long>(split + 1) * p.num_tiles / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.nst; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int h0 = (t % p.tiles_h) * p.BH;
+        const int n0 = t / p.tiles_h;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * WG_TILE_BYTES + 2 * p.slab_block_bytes));
+        uint8_t* sa = smem + stage * p.stage_bytes;
+        tma_load_4d(sa, &tmDY, &full_bar[stage], co_tile * 128, 0, h0, n0);
+        tma_load_4d(sa + WG_TILE_BYTES, &tmDY, &full_bar[stage], co_tile * 128 + 64, 0, h0, n0);
+        tma_load_4d(sa + 2 * WG_TILE_BYTES, &tmX, &full_bar[stage], ci_tile * 128, dw, h0 - p.halo, n0);
+        tma_load_4d(sa + 2 * WG_TILE_BYTES + p.slab_block_bytes, &tmX, &full_bar[stage], ci_tile * 128 + 64, dw, h0 - p.halo, n0);
+        if (++stage == p.nst) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 1) | (1u << 15);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0, accum = 0;
+      const uint32_t tap_bytes = static_cast<uint32_t>(p.BW) * 128u;  // one image row further down the slab
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+#pragma unroll
+        for (int kk = 0; kk < WG_PIX / 16; ++kk) {
+          const uint64_t adesc = umma_desc_mn_sw128_lbo(sa + kk * 2048, WG_TILE_BYTES);
+          for (int v = 0; v < nv; ++v) {
+            const uint64_t bdesc = umma_desc_mn_sw128_lbo(sa + 2 * WG_TILE_BYTES + v * tap_bytes + kk * 2048,
+                                                          static_cast<uint32_t>(p.slab_block_bytes));
+            umma_bf16(tmem_base + v * 128, adesc, bdesc, idesc, (accum | kk) != 0 ? 1u : 0u);
+          }
+        }
+        accum = 1;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.nst) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int co = co_tile * 128 + q * 32 + lane;
+    if (t_end > t_begin) {
+      mbar_wait(done_bar, 0u);
+      tc_fence_after();
+    }
+    for (int v = 0; v < nv; ++v) {
+      const int tap = p.taps == 9 ? v * 3 + dwi : 0;
+      float* dst = p.partial + ((static_cast<size_t>(split) * p.Cout + co) * p.taps + tap) * p.Cin + ci_tile * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        if (t_end > t_begin) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + v * 128 + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(dst + c0)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dW[co][ci][tap] (+)= sum_split partial[split][co][tap][ci], slices added in index order
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                                 int splits, int Cout, int taps, int Cin, int accumulate) {
@@ -217,14 +359,53 @@ static int encode4d(CUtensorMap* m, const void* base, int C, int W, int H, int B
   return 0;
 }
 
+// the row-slab kernel covers: stride 1, rows of 8..64 pixels, at least 64 pixels per image, 128-channel input tiles
+static bool wgrad_use_slab(const dmc_wgrad_desc& d) {
+  const char* e = getenv("DMC_WGRAD_SLAB");
+  if (e && e[0] == '0') return false;
+  const int W = d.Win, H = d.Hin;
+  return d.stride == 1 && d.Cin % 128 == 0 && (W == 8 || W == 16 || W == 32 || W == 64) && H * W >= WG_PIX && H % (WG_PIX / W) == 0;
+}
+
 int conv_wgrad_splits(const dmc_wgrad_desc& d) {
   const int Ho = d.Hin / d.stride, Wo = d.Win / d.stride;
   const long long tiles = (static_cast<long long>(d.B) * Ho * Wo + WG_PIX - 1) / WG_PIX;
-  const int items = (d.Cout / 128) * (d.Cin / 64) * ((d.taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS);
-  // whole waves: one CTA per SM (226 KB of shared memory each), so the grid is the largest multiple of `items` that fits in two
-  // waves (a grid of 2 * SMs + a few CTAs would run a third, almost empty wave)
+  const int items = wgrad_use_slab(d) ? (d.Cout / 128) * (d.Cin / 128) * (d.taps == 9 ? 3 : 1)
+                                      : (d.Cout / 128) * (d.Cin / 64) * ((d.taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS);
+  // whole waves: one CTA per SM (most of the shared memory each), so the grid is the largest multiple of `items` that fits in
+  // two waves (a grid of 2 * SMs + a few CTAs would run a third, almost empty wave)
   int splits = std::max(1, (2 * num_sms()) / std::max(items, 1));
   return static_cast<int>(std::min<long long>(splits, std::max<long long>(tiles, 1)));
+}
+
+static int launch_conv_wgrad_slab(const dmc_wgrad_desc& d, cudaStream_t st) {
+  WgradSlabParams p;
+  memset(&p, 0, sizeof(p));
+  const int W = d.Win, H = d.Hin;
+  p.BW = W; p.BH = WG_PIX / W;
+  p.tiles_h = H / p.BH;
+  p.num_tiles = d.B * p.tiles_h;
+  p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps;
+  p.ndw = d.taps == 9 ? 3 : 1;
+  p.halo = d.taps == 9 ? 1 : 0;
+  p.splits = d.splits;
+  p.slab_block_bytes = (p.BH + 2 * p.halo) * W * 128;
+  p.stage_bytes = 2 * WG_TILE_BYTES + 2 * p.slab_block_bytes;
+  p.nst = std::min(8, (WG_SMEM_LIMIT - 1024 - 256) / p.stage_bytes);
+  p.partial = d.partial;
+  CUtensorMap tmX, tmDY;
+  if (encode4d(&tmX, d.x, d.Cin, W, H, d.B, W, p.BH + 2 * p.halo, 1, 1) != 0) return -1;
+  if (encode4d(&tmDY, d.dy, d.Cout, W, H, d.B, W, p.BH, 1, 1) != 0) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMC_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int grid = (d.Cout / 128) * (d.Cin / 128) * p.ndw * p.splits;
+  const size_t smem = static_cast<size_t>(p.nst) * p.stage_bytes + 1024 + 256;
+  conv_wgrad_slab_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmDY, p);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
@@ -250,6 +431,14 @@ int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
   p.splits = d.splits;
   DMC_REQUIRE(d.splits >= 1 && d.splits == conv_wgrad_splits(d), "wgrad: splits=%d, expected dmc_conv_wgrad_splits() = %d", d.splits,
               conv_wgrad_splits(d));
+  const size_t total = static_cast<size_t>(d.Cout) * d.taps * d.Cin;
+  const int rblocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  if (wgrad_use_slab(d)) {
+    if (launch_conv_wgrad_slab(d, st) != 0) return -1;
+    conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, d.splits, d.Cout, d.taps, d.Cin, d.accumulate);
+    DMC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   p.stage_bytes = (2 + std::min(d.taps, WG_MAX_TAPS)) * WG_TILE_BYTES;
   p.nst = std::min(8, (WG_SMEM_LIMIT - 1024 - 256) / p.stage_bytes);
   p.partial = d.partial;
@@ -265,8 +454,6 @@ int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(p.nst) * p.stage_bytes + 1024 + 256;
   conv_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmDY, p);
   DMC_CUDA_OK(cudaGetLastError());
-  const size_t total = static_cast<size_t>(d.Cout) * d.taps * d.Cin;
-  const int rblocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, p.splits, d.Cout, d.taps, d.Cin, d.accumulate);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;

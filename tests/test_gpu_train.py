@@ -34,6 +34,7 @@ def _q(x):
 @pytest.mark.parametrize("cin,cout,H,B,k,stride", [
     (128, 128, 32, 2, 3, 1), (256, 256, 16, 3, 3, 1), (128, 256, 16, 2, 3, 1), (256, 256, 8, 5, 3, 1), (256, 256, 4, 7, 3, 1),
     (256, 768, 16, 2, 1, 1), (256, 256, 8, 3, 1, 1), (128, 128, 32, 2, 3, 2), (512, 256, 16, 1, 3, 1), (64, 128, 32, 1, 3, 1),
+    (384, 128, 32, 2, 3, 1), (256, 128, 32, 1, 1, 1), (128, 128, 8, 130, 3, 1),
 ])
 def test_conv_weight_gradient(cin, cout, H, B, k, stride):
     """dW of conv(x, W) for a random upstream gradient vs autograd (fp32 accumulation over up to B*H*W = 4096 pixels)"""
