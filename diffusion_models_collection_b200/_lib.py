@@ -99,6 +99,20 @@ class WgradDesc(C.Structure):
                 ("dw", vp), ("accumulate", C.c_int32)]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp)] + [(n, C.c_int32) for n in ("cout", "cin_total", "ci0", "cin", "taps", "mode", "ld", "col0",
+                                                                     "cpad", "pad_")]
+
+
+def pack_table(items, device):
+    """device copy of an array of PackItem (dmc_pack_weights reads its items from device memory)"""
+    import torch
+
+    arr = (PackItem * len(items))(*items)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(items)
+
+
 class HeadDesc(C.Structure):
     _fields_ = [("src", vp), ("stats", vp), ("stats_slots", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("C", C.c_int32), ("Cout", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
@@ -141,6 +155,7 @@ SYMBOLS = {
     "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
     "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "dmc_dilate2x": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_pack_weights": (C.c_int, [vp, C.c_int32, vp]),
     "dmc_add_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp]),
     "dmc_block_sum2x2": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

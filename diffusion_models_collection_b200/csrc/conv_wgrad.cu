@@ -373,8 +373,9 @@ int conv_wgrad_splits(const dmc_wgrad_desc& d) {
   const int items = wgrad_use_slab(d) ? (d.Cout / 128) * (d.Cin / 128) * (d.taps == 9 ? 3 : 1)
                                       : (d.Cout / 128) * (d.Cin / 64) * ((d.taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS);
   // whole waves: one CTA per SM (most of the shared memory each), so the grid is the largest multiple of `items` that fits in
-  // two waves (a grid of 2 * SMs + a few CTAs would run a third, almost empty wave)
-  int splits = std::max(1, (2 * num_sms()) / std::max(items, 1));
+  // the wave budget (a grid of k * SMs + a few CTAs would run one more, almost empty wave)
+  const int waves = wgrad_use_slab(d) ? 1 : 2;  // slab kernel: one wave (half the fp32 partial-sum traffic, half the epilogues)
+  int splits = std::max(1, (waves * num_sms()) / std::max(items, 1));
   return static_cast<int>(std::min<long long>(splits, std::max<long long>(tiles, 1)));
 }
 

@@ -175,6 +175,9 @@ int dmc_channel_sum(const void* src, float* out, int32_t B, int32_t HW, int32_t 
 int dmc_dilate2x(const void* src, void* dst, int32_t B, int32_t h, int32_t w, int32_t C, void* stream) {
   return launch_dilate2x(src, dst, B, h, w, C, static_cast<cudaStream_t>(stream));
 }
+int dmc_pack_weights(const dmc_pack_item* items_dev, int32_t n_items, void* stream) {
+  return launch_pack_weights(items_dev, n_items, static_cast<cudaStream_t>(stream));
+}
 int dmc_add_bf16(void* dst, const void* src, int64_t n, int32_t accumulate, void* stream) {
   DMC_REQUIRE(n > 0, "dmc_add_bf16: n=%lld", static_cast<long long>(n));
   return launch_add_bf16(dst, src, static_cast<size_t>(n), accumulate, static_cast<cudaStream_t>(stream));

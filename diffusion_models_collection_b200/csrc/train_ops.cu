@@ -600,6 +600,48 @@ int launch_block_sum2x2(const void* dhigh, void* dlow, int B, int H, int W, int 
   return 0;
 }
 
+// Re-pack of the convolution weights after an optimizer step: fp32 [Cout, Cin, kh, kw] parameters -> the bf16 GEMM operands of
+// the forward convolution (mode 0: [Cout][tap][ci], a column range of a possibly wider K-concatenated matrix) and of the
+// input-gradient convolution (mode 1: [ci][flipped tap][co], zero-padded co).  ONE launch for all layers: blockIdx.y = item,
+// 32 x 32 (co, ci) tiles staged through shared memory so that both the fp32 reads and the bf16 writes are contiguous runs.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const dmc_pack_item* __restrict__ items) {
+  __shared__ float tile[32][32 * 9 + 1];
+  const dmc_pack_item it = items[blockIdx.y];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it.dst);
+  const int tci = (it.cin + 31) / 32, ntile = ((it.cout + 31) / 32) * tci;
+  for (int tl = blockIdx.x; tl < ntile; tl += gridDim.x) {
+    const int co0 = (tl / tci) * 32, cc0 = (tl % tci) * 32;
+    const int nci = min(32, it.cin - cc0), ncol = nci * it.taps;
+    for (int e = threadIdx.x; e < 32 * ncol; e += 256) {
+      const int r = e / ncol, c = e - r * ncol, co = co0 + r;
+      tile[r][c] = co < it.cout ? __ldg(it.src + (static_cast<size_t>(co) * it.cin_total + it.ci0 + cc0) * it.taps + c) : 0.f;
+    }
+    __syncthreads();
+    if (it.mode == 0) {
+      for (int e = threadIdx.x; e < 32 * ncol; e += 256) {
+        const int ci = e % nci, tap = (e / nci) % it.taps, r = e / ncol, co = co0 + r;
+        if (co < it.cout)
+          dst[static_cast<size_t>(co) * it.ld + it.col0 + tap * it.cin + cc0 + ci] = __float2bfloat16_rn(tile[r][ci * it.taps + tap]);
+      }
+    } else {
+      for (int e = threadIdx.x; e < 32 * ncol; e += 256) {
+        const int r = e & 31, tap = (e >> 5) % it.taps, ci = (e >> 5) / it.taps, co = co0 + r;
+        if (co < it.cout)
+          dst[static_cast<size_t>(cc0 + ci) * it.ld + it.col0 + (it.taps - 1 - tap) * it.cpad + co] =
+              __float2bfloat16_rn(tile[r][ci * it.taps + tap]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_pack_weights(const dmc_pack_item* items_dev, int n, cudaStream_t st) {
+  DMC_REQUIRE(items_dev && n > 0 && n <= 65535, "pack_weights: bad arguments (n=%d)", n);
+  pack_weights_kernel<<<dim3(32, n), 256, 0, st>>>(items_dev);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // dst (+)= src over n bf16 elements (n % 8 == 0): gradient of an identity residual branch / fan-out accumulation
 __global__ void __launch_bounds__(256) add_bf16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n8,
                                                        int accumulate) {

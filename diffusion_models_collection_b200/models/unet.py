@@ -510,7 +510,12 @@ class UNet(nn.Module):
                 for dst, wkey, ph in r["phases"]:
                     dst.copy_(phase_weights(sd[wkey], ph))
                 return
-            torch._foreach_copy_(r["w_dst"], r["w_src"])
+            if device.type == "cuda":  # all GEMM weights in one launch of the native pack kernel
+                if r["table"] is None:
+                    r["table"] = _lib.pack_table(r["items"], device)
+                _lib.check(_lib.load().dmc_pack_weights(r["table"][0].data_ptr(), r["table"][1], _lib.stream_ptr()), "dmc_pack_weights")
+            else:
+                torch._foreach_copy_(r["w_dst"], r["w_src"])
             torch._foreach_copy_(r["b_dst"], r["b_src"])
             if r["b2_dst"]:
                 torch._foreach_add_(r["b2_dst"], r["b2_src"])
@@ -530,7 +535,14 @@ class UNet(nn.Module):
         sd = pk["sd"]
         down, middle, up, out_ch = unet_block_structure(self._cfg())
         r = dict(w_dst=[], w_src=[], b_dst=[], b_src=[], b2_dst=[], b2_src=[], wt=[], bt=[], bt_dst=[], bt_add=[], wy=[],
-                 phases=[])
+                 phases=[], items=[], table=None)
+
+        def item(dst, w, taps):  # forward layout: dst[co, tap * cin + ci], dst possibly a column range of a wider matrix
+            it = _lib.PackItem()
+            it.src, it.dst = w.data_ptr(), dst.data_ptr()
+            it.cout, it.cin_total, it.ci0, it.cin, it.taps, it.mode = w.shape[0], w.shape[1], 0, w.shape[1], taps, 0
+            it.ld, it.col0, it.cpad = dst.stride(0), 0, 0
+            r["items"].append(it)
 
         def wview(name):
             rows, K = pk["wshape"][name]
@@ -541,10 +553,12 @@ class UNet(nn.Module):
             co, ci = w.shape[0], w.shape[1]
             r["w_dst"].append(dst.view(co, 3, 3, ci))
             r["w_src"].append(w.permute(0, 2, 3, 1))
+            item(dst, w, 9)
 
         def w1x1(dst, w):
             r["w_dst"].append(dst)
             r["w_src"].append(w.view(w.shape[0], w.shape[1]))
+            item(dst, w, 1)
 
         col = 0
 

@@ -121,7 +121,7 @@ class UNetTrainEngine:
         self.deps_pad = torch.zeros((B, Hh, Ww, 128), dtype=torch.bfloat16, device=device)
         self._deps = None
         self._build_backward()
-        self._dgrad_ver = None
+        self._dgrad_ver, self._dgrad_table = None, None
 
     # ------------------------------------------------------------------------------------------------------------------
     def _build_backward(self):
@@ -355,25 +355,26 @@ class UNetTrainEngine:
 
     # ------------------------------------------------------------------------------------------------------------------
     def _refresh_dgrad(self):
-        """transposed, tap-flipped bf16 copies of the convolution weights for the input-gradient GEMMs"""
+        """transposed, tap-flipped bf16 copies of the convolution weights for the input-gradient GEMMs (one pack-kernel launch)"""
         ver = self.net._param_version()
         if self._dgrad_ver == ver:
             return
-        sd = self.pk["sd"]
-        dsts, srcs = [], []
-        with torch.no_grad():
+        if self._dgrad_table is None:
+            sd = self.pk["sd"]
+            items = []
             for t, kind, wkey, extra in self.dgrad_items:
                 w = sd[wkey]
-                co, ci = w.shape[0], w.shape[1]
+                it = _lib.PackItem()
+                it.src, it.dst = w.data_ptr(), t.data_ptr()
+                it.cout, it.cin_total, it.mode, it.ld, it.col0 = w.shape[0], w.shape[1], 1, t.shape[1], 0
                 if kind == "3x3":  # [ci, (2-r, 2-s), co_pad] <- w[co, ci, r, s]
-                    copad = t.shape[1] // 9
-                    dsts.append(t.view(ci, 3, 3, copad)[..., :co])
-                    srcs.append(w.flip(2, 3).permute(1, 2, 3, 0))
-                else:
-                    off, c = extra
-                    dsts.append(t)
-                    srcs.append(w.view(co, ci)[:, off: off + c].t())
-            torch._foreach_copy_(dsts, srcs)
+                    it.ci0, it.cin, it.taps, it.cpad = 0, w.shape[1], 9, t.shape[1] // 9
+                else:             # [c, co] <- w[co, off + c]
+                    it.ci0, it.cin, it.taps, it.cpad = extra[0], extra[1], 1, t.shape[1]
+                items.append(it)
+            self._dgrad_table = _lib.pack_table(items, self.device)
+        _lib.check(self.lib.dmc_pack_weights(self._dgrad_table[0].data_ptr(), self._dgrad_table[1], _lib.stream_ptr()),
+                   "dmc_pack_weights")
         self._dgrad_ver = ver
 
     def forward(self, x, t, y):

@@ -175,6 +175,18 @@ DMC_API int dmc_dilate2x(const void* src_bf16, void* dst_bf16, int32_t B, int32_
 /* dlow[n, i, j, :] (+)= the 2x2 block sum of dhigh (backward of the nearest 2x upsample, models/unet.py:119) */
 DMC_API int dmc_block_sum2x2(const void* dhigh_bf16, void* dlow_bf16, int32_t B, int32_t H, int32_t W, int32_t C,
                      int32_t accumulate, void* stream);
+/* Re-pack of convolution weights after an optimizer step, all layers in ONE launch.  Item i converts the fp32 parameter
+ * src [cout, cin_total, kh, kw] (taps = kh * kw; input channels ci0 .. ci0 + cin) into a bf16 GEMM operand:
+ *   mode 0 (forward conv, dmc_conv_desc.weight):     dst[co * ld + col0 + tap * cin + ci]
+ *   mode 1 (input-gradient conv, transposed + flipped): dst[ci * ld + col0 + (taps - 1 - tap) * cpad + co]
+ * `items_dev` is an array in DEVICE memory. */
+typedef struct {
+  const float* src;
+  void* dst;
+  int32_t cout, cin_total, ci0, cin, taps, mode, ld, col0, cpad;
+  int32_t pad_;
+} dmc_pack_item;
+DMC_API int dmc_pack_weights(const dmc_pack_item* items_dev, int32_t n_items, void* stream);
 /* dst (+)= src over n bf16 elements, n % 8 == 0 (gradient of an identity residual branch, models/unet.py:72,99) */
 DMC_API int dmc_add_bf16(void* dst_bf16, const void* src_bf16, int64_t n, int32_t accumulate, void* stream);
 /* fp32 NCHW [B, Csrc, H*W] -> bf16 NHWC [B, H*W, Cdst >= Csrc] with zero-padded channels */
