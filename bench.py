@@ -349,7 +349,8 @@ def run_train_workload(args, rank, local_rank, world):
     net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
     net = net.to(dev).train()
     ema = [p.detach().clone() for p in net.parameters()] if rank == 0 else None
-    model = torch.nn.parallel.DistributedDataParallel(net) if world > 1 else net
+    bucket_mb = float(os.environ.get("DMC_DDP_BUCKET_MB", "25"))  # 25 = torch default (the reference's setting)
+    model = torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb) if world > 1 else net
     ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
     opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
     B = args.batch
@@ -409,6 +410,12 @@ def run_train_workload(args, rank, local_rank, world):
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     loss_now = step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()  # host enqueue time per step (no synchronisation inside): is the GPU ever waiting for Python?
+    for _ in range(args.steps):
+        step_resident()
+    host_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    torch.cuda.synchronize()
 
     eng = next(iter(net._train_engines.values()))
     info = eng.describe()
@@ -423,7 +430,8 @@ def run_train_workload(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},
             "gpu_launches": int((info["forward_launches"] + info["backward_launches"]) * args.steps),
-            "loss": loss_now}
+            "loss": loss_now, "host_enqueue_ms_per_step": host_ms}
+    line["config"]["ddp_bucket_mb"] = bucket_mb if world > 1 else None
     pk = peaks()
     flops = info["gemm_flops"]
     line["model_flops_utilization"] = {"achieved_tflops": flops * args.steps / (ms / 1e3) / 1e12, "gemm_flops_per_step": flops,

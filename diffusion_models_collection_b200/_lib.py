@@ -56,7 +56,7 @@ class GnApplyDesc(C.Structure):
     _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2), ("stats_slots", C.c_int32 * 2),
                 ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
                 ("silu", C.c_int32), ("out", vp), ("src_lo", vp * 2), ("out_lo", vp), ("drop_p", C.c_float),
-                ("seed", C.c_uint32)]
+                ("seed", C.c_uint32), ("seed_dev", vp)]
 
 
 class ConvDesc(C.Structure):
@@ -84,8 +84,8 @@ class GnBwdDesc(C.Structure):
     _fields_ = [("nsrc", C.c_int32), ("src", vp * 2), ("src_c", C.c_int32 * 2), ("stats", vp * 2),
                 ("stats_slots", C.c_int32 * 2), ("dout", vp), ("dsrc", vp * 2), ("accumulate", C.c_int32 * 2),
                 ("B", C.c_int32), ("HW", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
-                ("silu", C.c_int32), ("drop_p", C.c_float), ("seed", C.c_uint32), ("dgamma", vp), ("dbeta", vp),
-                ("scratch", vp)]
+                ("silu", C.c_int32), ("drop_p", C.c_float), ("seed", C.c_uint32), ("seed_dev", vp), ("dgamma", vp),
+                ("dbeta", vp), ("scratch", vp)]
 
 
 class AttnBwdDesc(C.Structure):

@@ -313,6 +313,7 @@ struct GnApplyArgs {
   int silu;
   float drop_scale;       // training: 1 / (1 - p) for kept elements
   uint32_t drop_thresh, seed;
+  const uint32_t* seed_dev;  // optional per-step seed in device memory (added to `seed`): lets a captured graph draw new masks
 };
 
 // counter-based dropout mask (the same function as in train_ops.cu: forward and backward regenerate the same mask)
@@ -440,8 +441,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
           }
           if (a.drop_thresh != 0u) {  // dropout after SiLU (ResidualBlock.conv2, models/unet.py:53), training only
             const uint64_t idx = ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8 + 2 * j;
-            y0 = gn_dropout_keep(a.seed, idx, a.drop_thresh) ? y0 * a.drop_scale : 0.f;
-            y1 = gn_dropout_keep(a.seed, idx + 1, a.drop_thresh) ? y1 * a.drop_scale : 0.f;
+            const uint32_t seed = a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0u);
+            y0 = gn_dropout_keep(seed, idx, a.drop_thresh) ? y0 * a.drop_scale : 0.f;
+            y1 = gn_dropout_keep(seed, idx + 1, a.drop_thresh) ? y1 * a.drop_scale : 0.f;
           }
           o[j] = pack_bf16x2(y0, y1);
           if (LO) {
@@ -476,6 +478,7 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.drop_thresh = dropout_threshold(d.drop_p);
   a.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
   a.seed = d.seed;
+  a.seed_dev = d.seed_dev;
   a.slots0 = d.stats_slots[0];
   a.slots1 = d.nsrc == 2 ? d.stats_slots[1] : 0;
   DMC_REQUIRE(a.slots0 > 0 && (d.nsrc == 1 || a.slots1 > 0), "gn_apply: stats_slots must be positive");

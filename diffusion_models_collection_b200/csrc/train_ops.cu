@@ -45,6 +45,7 @@ struct GnBwdArgs {
   int silu;
   float drop_scale;                          // 1 / (1 - p), or 1
   uint32_t drop_thresh, seed;
+  const uint32_t* seed_dev;                  // optional per-step seed in device memory, added to `seed`
 };
 
 __device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, float* s_mean, float* s_rstd) {
@@ -88,6 +89,7 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, float*
 __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, const uint4& dv, float mean, float rstd,
                                        const float (&gam)[8], const float (&bet)[8], uint64_t idx0, float (&xh)[8],
                                        float (&dz)[8]) {
+  const uint32_t seed = a.drop_thresh != 0u ? a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0u) : 0u;
   const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
   const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
@@ -100,7 +102,7 @@ __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, cons
       const int c = 2 * j + k;
       xh[c] = (xs[k] - mean) * rstd;
       float d = ds[k];
-      if (a.drop_thresh != 0u) d = dropout_keep(a.seed, idx0 + c, a.drop_thresh) ? d * a.drop_scale : 0.f;
+      if (a.drop_thresh != 0u) d = dropout_keep(seed, idx0 + c, a.drop_thresh) ? d * a.drop_scale : 0.f;
       if (a.silu) {
         const float z = fmaf(xh[c], gam[c], bet[c]);
         float th;  // sigmoid(z) = 0.5 + 0.5 tanh(z / 2): one MUFU op (the forward pass uses the same form)
@@ -307,6 +309,7 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   a.drop_thresh = dropout_threshold(d.drop_p);
   a.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
   a.seed = d.seed;
+  a.seed_dev = d.seed_dev;
   const int C8 = C / 8, rows = std::max(1, 256 / C8);
   dim3 grid(slabs, d.B);
   const size_t smem = static_cast<size_t>(rows) * C8 * 18 * sizeof(float);

@@ -314,6 +314,7 @@ class UNet(nn.Module):
         self._uniform_t = False
         self._plans = {}
         self._train_engines = {}
+        self._plist = None
         self._packed = None
         self._packed_version = self._packed_ids = None
         self._init_parameters()
@@ -385,11 +386,25 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------------------------------------
     # weight packing (one-time / on parameter change; plain torch ops -- not on the hot path)
     # ------------------------------------------------------------------------------------------------
+    def parameters(self, recurse: bool = True):
+        """nn.Module.parameters() walks the module tree (one small container per dotted-name component: ~1.5 ms for the 357
+        tensors); the trainer calls it several times per step (optimizer, clip_grad_norm_), so the flat list is cached."""
+        if not recurse:
+            return super().parameters(recurse)
+        if self._plist is None:
+            self._plist = list(super().parameters())
+        return iter(self._plist)
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._plist = None
+        return r
+
     def _param_ids(self):
-        return tuple(p.data_ptr() for p in self.parameters())
+        return tuple([p.data_ptr() for p in self.parameters()])
 
     def _param_version(self):
-        return tuple(p._version for p in self.parameters())
+        return tuple([p._version for p in self.parameters()])
 
     def _ensure_packed(self, device, training=False):
         """packed copies of the parameters.  A change of parameter *storage* (load onto another device, .to(), a new
@@ -751,10 +766,15 @@ class UNet(nn.Module):
                               bool(self._uniform_t))
 
 
+def layer_seed(op_index):
+    """dropout seed constant of the GroupNorm pass that is op `op_index` of the forward plan"""
+    return ((op_index + 1) * 0x9E3779B1) & 0xFFFFFFFF
+
+
 class _UNetPlan:
     """Owns one dmc_plan (C side), its workspace and the small staging tensors of one (batch, mode) signature."""
 
-    def __init__(self, net: UNet, pk, device, nimg, x_batch, has_y, uniform_t, keep=False, drop_p=0.0):
+    def __init__(self, net: UNet, pk, device, nimg, x_batch, has_y, uniform_t, keep=False, drop_p=0.0, seed_dev=None):
         lib = _lib.load()
         self.lib = lib
         self.nimg, self.x_batch, self.has_y = nimg, x_batch, has_y
@@ -832,6 +852,9 @@ class _UNetPlan:
                 d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
                 d.eps, d.silu, d.out, d.out_lo = 1e-5, o["silu"], ap(o["out"]), ap_lo(o["out"])
                 d.drop_p = o["drop_p"]
+                if o["drop_p"] > 0:  # per-layer constant + the per-step seed the training engine keeps in device memory
+                    d.seed = layer_seed(len(self.op_names))
+                    d.seed_dev = seed_dev.data_ptr() if seed_dev is not None else None
                 add(lib.dmc_plan_add_gn_apply, d, o["prefix"])
             elif kind == "conv":
                 d = _lib.ConvDesc()

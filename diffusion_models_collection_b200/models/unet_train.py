@@ -25,15 +25,16 @@ replaying it in PyTorch from the per-image sums of the conv1 output gradients.  
 from __future__ import annotations
 
 import ctypes as C
-import math
+import os
 
 import torch
 import torch.nn.functional as F
 
 from .. import _lib
 from ..synth import unet_block_structure
+from .unet import layer_seed
 
-_GOLD = 0x9E3779B1
+USE_GRAPHS = os.environ.get("DMC_TRAIN_GRAPHS", "1") != "0"
 
 
 def _seg_of(name):
@@ -90,7 +91,8 @@ class UNetTrainEngine:
         if B > 4096:
             raise NotImplementedError("native UNet training: at most 4096 images per step per GPU")
         pk = self.pk = net._ensure_packed(device, training=True)
-        self.fwd = _UNetPlan(net, pk, device, B, B, has_y, False, keep=True, drop_p=self.drop_p)
+        self.seed_dev = torch.zeros(1, dtype=torch.int32, device=device)  # per-step dropout seed (read by the kernels)
+        self.fwd = _UNetPlan(net, pk, device, B, B, has_y, False, keep=True, drop_p=self.drop_p, seed_dev=self.seed_dev)
         self.step_id = 0
         self.eps_out = None
         self._keep = []
@@ -119,9 +121,15 @@ class UNetTrainEngine:
         Hh, Ww = net._hw
         self.xpad = torch.zeros((B, Hh, Ww, 64), dtype=torch.bfloat16, device=device)
         self.deps_pad = torch.zeros((B, Hh, Ww, 128), dtype=torch.bfloat16, device=device)
-        self._deps = None
+        # static staging buffers: the launch lists (and the CUDA graphs made of them) never see a caller-owned pointer
+        self.x_static = torch.zeros((B, net.in_channels, Hh, Ww), dtype=torch.float32, device=device)
+        self.deps_static = torch.zeros((B, net.out_channels, Hh, Ww), dtype=torch.float32, device=device)
+        _lib.check(lib.dmc_plan_rebind(self.fwd.handle, self.fwd.stem_idx, 0, self.x_static.data_ptr()), "rebind x")
         self._build_backward()
         self._dgrad_ver, self._dgrad_table = None, None
+        self._seg_param_objs = None
+        self._cond_param_objs = None
+        self.graphs = None
 
     # ------------------------------------------------------------------------------------------------------------------
     def _build_backward(self):
@@ -210,8 +218,10 @@ class UNetTrainEngine:
         def copy_op(dst, src):
             emit_py(lambda: dst.copy_(src))
 
-        layer_no = 0
         cur_seg = "output"
+        cur = self.bwd["output"]
+        emit(lib.dmc_nchw_f32_to_nhwc_bf16, self.deps_static.data_ptr(), self.deps_pad.data_ptr(), B, net.out_channels, Hh * Ww, 128,
+             kind="pack", name="d(eps)")
         for i in reversed(range(len(b.ops))):
             kind, o = b.ops[i]
             nm = o.get("wname") or o.get("prefix")
@@ -308,12 +318,13 @@ class UNetTrainEngine:
                 d.dout, d.B, d.HW, d.groups = dy_of(out), B, HW, 8
                 d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
                 d.eps, d.silu, d.drop_p, d.seed = 1e-5, o["silu"], o["drop_p"], 0
+                if o["drop_p"] > 0:  # the same (constant + device seed) pair as the forward pass
+                    d.seed, d.seed_dev = layer_seed(pl.op_index[i]), self.seed_dev.data_ptr()
                 d.dgamma, d.dbeta = self.gview[o["prefix"] + ".weight"].data_ptr(), self.gview[o["prefix"] + ".bias"].data_ptr()
                 gn_scratch_need = max(gn_scratch_need, B * ((HW + 127) // 128) * (2 * Ctot + Ctot // 4))
                 gn_descs.append(d)
                 if o["drop_p"] > 0:
-                    self.drop_ops.append((pl.op_index[i], d, layer_no))
-                    layer_no += 1
+                    self.drop_ops.append(pl.op_index[i])
                 emit(lib.dmc_gn_backward, C.byref(d), kind="gn_backward", name=o["prefix"])
 
             elif kind == "attention":
@@ -381,31 +392,55 @@ class UNetTrainEngine:
         lib, net, B = self.lib, self.net, self.B
         self._refresh_dgrad()  # (the caller has just re-packed the forward weights: UNet._run_train)
         if self.drop_ops:
-            base = int(torch.empty((), dtype=torch.int64).random_().item())  # CPU generator: follows torch.manual_seed
-            for idx, d, ln in self.drop_ops:
-                seed = (base + (ln + 1) * _GOLD) & 0xFFFFFFFF
-                d.seed = seed
-                _lib.check(lib.dmc_plan_set_seed(self.fwd.handle, idx, seed), "dmc_plan_set_seed")
+            base = int(torch.empty((), dtype=torch.int64).random_(0, 2 ** 31 - 1).item())  # CPU generator: follows torch.manual_seed
+            self.seed_dev.fill_(base)
+        pl = self.fwd
+        self.x_static.copy_(x)
+        pl.t_stage.copy_(t)
+        if self.has_y:
+            pl.y_stage.copy_(y)
+        if USE_GRAPHS and self.graphs is None and self.step_id >= 2:
+            self._capture()
+        if self.graphs is not None:
+            self.graphs["forward"].replay()
+        else:
+            self._forward_ops()
+        self.step_id += 1
+        self.eps_out = pl.eps.clone()
+        return self.eps_out
+
+    def _forward_ops(self):
+        lib, net, pl = self.lib, self.net, self.fwd
         Hh, Ww = net._hw
         st = _lib.stream_ptr()
-        _lib.check(lib.dmc_nchw_f32_to_nhwc_bf16(x.data_ptr(), self.xpad.data_ptr(), B, net.in_channels, Hh * Ww, 64, st),
-                   "pack x")
-        eps = torch.empty((B, net.out_channels, Hh, Ww), device=self.device, dtype=torch.float32)
-        self.fwd.run(x, t, y if self.has_y else None, False, eps, None)
-        self.step_id += 1
-        self.eps_out = eps
-        return eps
+        _lib.check(lib.dmc_nchw_f32_to_nhwc_bf16(self.x_static.data_ptr(), self.xpad.data_ptr(), self.B, net.in_channels, Hh * Ww,
+                                                 64, st), "pack x")
+        _lib.check(lib.dmc_plan_run(pl.handle, st), "dmc_plan_run")
+
+    def _capture(self):
+        """after two eager steps (every lazily initialised kernel attribute is set): the forward launch list and the backward
+        launch list of every segment become CUDA graphs -- all their pointers are static, the dropout seed lives in device
+        memory -- so a step costs 1 + 26 graph launches instead of ~550 kernel launches from Python"""
+        graphs = {}
+        torch.cuda.synchronize()
+        pool = None
+        for name, fn in [("forward", self._forward_ops)] + [(s, (lambda s=s: self._run_ops(self.bwd[s]))) for s in reversed(self.segs)]:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                fn()
+            pool = g.pool()
+            graphs[name] = g
+        self.graphs = graphs
 
     def attach(self):
         """wires the autograd chain for the forward that has just been enqueued; returns eps with a grad_fn"""
-        net = self.net
+        if self._seg_param_objs is None:  # (parameter objects are stable: a storage change rebuilds the engine)
+            net = self.net
+            self._seg_param_objs = [[net.get_parameter(n) for n in self.seg_params[s] + (self.cond_names if k == 0 else [])]
+                                    for k, s in enumerate(self.segs)]
         tok = None
-        last = len(self.segs) - 1
-        for k, s in enumerate(self.segs):
-            names = self.seg_params[s] + (self.cond_names if k == 0 else [])
-            params = [net.get_parameter(n) for n in names]
+        for k, params in enumerate(self._seg_param_objs):
             tok = _Segment.apply(self, k, tok, *params)
-        assert last >= 0
         return tok
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -439,12 +474,11 @@ class UNetTrainEngine:
     def backward_segment(self, k, g):
         seg = self.segs[k]
         if seg == "output":
-            g = g.contiguous().float()
-            Hh, Ww = self.net._hw
-            _lib.check(self.lib.dmc_nchw_f32_to_nhwc_bf16(g.data_ptr(), self.deps_pad.data_ptr(), self.B, self.net.out_channels,
-                                                          Hh * Ww, 128, _lib.stream_ptr()), "pack d(eps)")
-            self._deps = g  # alive until the kernels that read it have been enqueued (same stream)
-        self._run_ops(self.bwd[seg])
+            self.deps_static.copy_(g)
+        if self.graphs is not None:
+            self.graphs[seg].replay()
+        else:
+            self._run_ops(self.bwd[seg])
         flat = self.flat[seg].clone()
         grads = [flat[o: o + n].view(shp) for _, o, n, shp in self.layout[seg]]
         if k == 0:
@@ -458,7 +492,9 @@ class UNetTrainEngine:
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
             with torch.enable_grad():
-                P = {n: net.get_parameter(n).detach().float().requires_grad_(True) for n in self.cond_names}
+                if self._cond_param_objs is None:
+                    self._cond_param_objs = [net.get_parameter(n) for n in self.cond_names]
+                P = {n: p.detach().float().requires_grad_(True) for n, p in zip(self.cond_names, self._cond_param_objs)}
                 cond = self._cond_torch(P, self.fwd.t_stage, self.fwd.y_stage if self.has_y else None)
                 grads = torch.autograd.grad(cond, [P[n] for n in self.cond_names], dcond, allow_unused=True)
         finally:

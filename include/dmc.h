@@ -147,6 +147,7 @@ typedef struct {
   int32_t silu;
   float drop_p;            /* dropout probability applied after SiLU in the forward pass (0: none) */
   uint32_t seed;           /* the forward pass's dropout seed */
+  const uint32_t* seed_dev; /* the forward pass's seed_dev (see dmc_gn_apply_desc) */
   float* dgamma;           /* fp32 [C] */
   float* dbeta;            /* fp32 [C] */
   float* scratch;          /* fp32 [B * ceil(HW/128) * (2*C + C/4)] */
@@ -307,6 +308,8 @@ typedef struct {
   void* out_lo;           /* optional low part of the output */
   float drop_p;           /* training: dropout after SiLU (models/unet.py:53), counter-based mask from `seed`; 0 = none */
   uint32_t seed;
+  const uint32_t* seed_dev; /* optional: a per-step seed in DEVICE memory, added to `seed` when the kernel runs -- a captured
+                               CUDA graph of the step then draws a new mask on every replay */
 } dmc_gn_apply_desc;
 DMC_API int dmc_plan_add_gn_apply(dmc_plan* p, const dmc_gn_apply_desc* d);
 

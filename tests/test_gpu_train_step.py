@@ -179,3 +179,29 @@ def test_ddp_wrapper_single_process():
             assert torch.equal(p.grad, want[n]), n
     finally:
         dist.destroy_process_group()
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    """from the third step on the engine replays CUDA graphs (forward + one per UNet entry); with the same torch seed they
+    reproduce the eager launch lists bit for bit, dropout mask included"""
+    net = _model(10).train()
+    x, t, y, noise = _batch(8, 10)
+
+    def grads():
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(11)
+        loss = F.mse_loss(noise, net(x, t, y))
+        loss.backward()
+        return loss.item(), [p.grad.clone() for p in net.parameters()]
+
+    l_eager, g_eager = grads()
+    grads()
+    eng = next(iter(net._train_engines.values()))
+    assert eng.graphs is None
+    l_graph, g_graph = grads()
+    from diffusion_models_collection_b200.models import unet_train
+    if unet_train.USE_GRAPHS:
+        assert eng.graphs is not None and len(eng.graphs) == len(eng.segs) + 1
+    assert l_eager == l_graph
+    for a, b in zip(g_eager, g_graph):
+        assert torch.equal(a, b)
