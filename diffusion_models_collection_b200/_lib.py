@@ -152,6 +152,7 @@ SYMBOLS = {
     "dmc_conv_wgrad_splits": (C.c_int, [C.POINTER(WgradDesc)]),
     "dmc_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
     "dmc_gn_backward": (C.c_int, [C.POINTER(GnBwdDesc), vp]),
+    "dmc_gn_backward_scratch": (C.c_int64, [C.POINTER(GnBwdDesc)]),
     "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
     "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "dmc_dilate2x": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

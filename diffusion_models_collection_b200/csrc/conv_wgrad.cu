@@ -376,7 +376,9 @@ int conv_wgrad_splits(const dmc_wgrad_desc& d) {
   // the wave budget (a grid of k * SMs + a few CTAs would run one more, almost empty wave)
   const int waves = wgrad_use_slab(d) ? 1 : 2;  // slab kernel: one wave (half the fp32 partial-sum traffic, half the epilogues)
   int splits = std::max(1, (waves * num_sms()) / std::max(items, 1));
-  return static_cast<int>(std::min<long long>(splits, std::max<long long>(tiles, 1)));
+  // at least 4 pixel tiles per CTA: below that the fp32 partial sums (splits x the weight tensor, written and read back) cost
+  // more than the idle SMs
+  return static_cast<int>(std::min<long long>(splits, std::max<long long>(tiles / 4, 1)));
 }
 
 static int launch_conv_wgrad_slab(const dmc_wgrad_desc& d, cudaStream_t st) {

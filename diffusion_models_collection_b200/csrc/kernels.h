@@ -54,6 +54,7 @@ int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int pe
 int launch_dilate2x(const void* src, void* dst, int B, int h, int w, int C, cudaStream_t st);
 int launch_attention_backward_mma(const dmc_attn_bwd_desc& d, cudaStream_t st);
 int launch_pack_weights(const dmc_pack_item* items_dev, int n, cudaStream_t st);
+long long gn_backward_scratch_floats(const dmc_gn_bwd_desc& d);
 int launch_add_bf16(void* dst, const void* src, size_t n, int accumulate, cudaStream_t st);
 int launch_block_sum2x2(const void* dhigh, void* dlow, int B, int H, int W, int C, int accumulate, cudaStream_t st);
 int launch_nchw_to_nhwc_pad(const float* src, void* dst, int B, int Cs, int HW, int Cd, cudaStream_t st);

@@ -178,6 +178,10 @@ int dmc_dilate2x(const void* src, void* dst, int32_t B, int32_t h, int32_t w, in
 int dmc_pack_weights(const dmc_pack_item* items_dev, int32_t n_items, void* stream) {
   return launch_pack_weights(items_dev, n_items, static_cast<cudaStream_t>(stream));
 }
+int64_t dmc_gn_backward_scratch(const dmc_gn_bwd_desc* d) {
+  if (!d) return -1;
+  return gn_backward_scratch_floats(*d);
+}
 int dmc_add_bf16(void* dst, const void* src, int64_t n, int32_t accumulate, void* stream) {
   DMC_REQUIRE(n > 0, "dmc_add_bf16: n=%lld", static_cast<long long>(n));
   return launch_add_bf16(dst, src, static_cast<size_t>(n), accumulate, static_cast<cudaStream_t>(stream));

@@ -28,7 +28,7 @@ uint32_t dropout_threshold(float p) {
 // pass A writes per (image, 128-pixel slab) partial sums, pass B applies; both recompute xh / z from x and the forward
 // statistics (nothing but x and the partial sums of the forward pass is kept).
 // =============================================================================================
-constexpr int GB_SLAB = 128;
+constexpr int GB_SLAB = 64;
 
 struct GnBwdArgs {
   const uint4* src0; const uint4* src1;      // bf16 [B, HW, c_i]
@@ -40,6 +40,8 @@ struct GnBwdArgs {
   const float* gamma; const float* beta;
   float* pgb;                                // [B, slabs, C, 2]   partial dgamma / dbeta
   float* ps;                                 // [B, slabs, C/8, 2] partial sum(g), sum(g xh) per 8-channel block
+  float* gm;                                 // [B, groups, 2] forward (mean, rstd) of every group
+  float* gg;                                 // [B, groups, 2] mean_grp(g), mean_grp(g xh)
   int HW, C0_8, C1_8, groups;
   float eps;
   int silu;
@@ -115,6 +117,41 @@ __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, cons
   }
 }
 
+// per (image, group) quantities computed ONCE by two tiny kernels (one CTA per image) instead of by every CTA of the two passes
+__global__ void __launch_bounds__(256) gn_group_moments_kernel(GnBwdArgs a) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int n = blockIdx.x;
+  gn_group_stats(a, n, s_mean, s_rstd);
+  __syncthreads();
+  if (threadIdx.x < a.groups)
+    reinterpret_cast<float2*>(a.gm)[n * a.groups + threadIdx.x] = make_float2(s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) gn_group_grads_kernel(GnBwdArgs a, int slabs) {
+  // group sums of g and g xh over all slabs (fixed order)
+  const int C8 = a.C0_8 + a.C1_8;
+  const int n = blockIdx.x;
+  const int gs8 = C8 / a.groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < a.groups; g += 8) {
+    float s1 = 0.f, s2 = 0.f;
+    const float2* base = reinterpret_cast<const float2*>(a.ps) + static_cast<size_t>(n) * slabs * C8;
+    for (int e = lane; e < gs8 * slabs; e += 32) {
+      const float2 v = base[static_cast<size_t>(e / gs8) * C8 + g * gs8 + e % gs8];
+      s1 += v.x; s2 += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+      s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    }
+    if (lane == 0) {
+      const float inv_m = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.HW));
+      reinterpret_cast<float2*>(a.gg)[n * a.groups + g] = make_float2(s1 * inv_m, s2 * inv_m);
+    }
+  }
+}
+
 template <bool APPLY>
 __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   __shared__ float s_mean[32], s_rstd[32], s_g1[32], s_g2[32];
@@ -122,28 +159,14 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   const int C8 = a.C0_8 + a.C1_8;
   const int n = blockIdx.y;
   const int gs8 = C8 / a.groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  gn_group_stats(a, n, s_mean, s_rstd);
-  if (APPLY) {
-    // group sums of g and g xh over all slabs (fixed order)
-    const int slabs = gridDim.x;
-    for (int g = warp; g < a.groups; g += 8) {
-      float s1 = 0.f, s2 = 0.f;
-      const float2* base = reinterpret_cast<const float2*>(a.ps) + static_cast<size_t>(n) * slabs * C8;
-      for (int e = lane; e < gs8 * slabs; e += 32) {
-        const float2 v = base[static_cast<size_t>(e / gs8) * C8 + g * gs8 + e % gs8];
-        s1 += v.x; s2 += v.y;
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
-        s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-      }
-      if (lane == 0) {
-        const float inv_m = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(a.HW));
-        s_g1[g] = s1 * inv_m;
-        s_g2[g] = s2 * inv_m;
-      }
+  if (threadIdx.x < a.groups) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(a.gm) + n * a.groups + threadIdx.x);
+    s_mean[threadIdx.x] = m.x;
+    s_rstd[threadIdx.x] = m.y;
+    if (APPLY) {
+      const float2 gq = __ldg(reinterpret_cast<const float2*>(a.gg) + n * a.groups + threadIdx.x);
+      s_g1[threadIdx.x] = gq.x;
+      s_g2[threadIdx.x] = gq.y;
     }
   }
   __syncthreads();
@@ -284,6 +307,12 @@ __global__ void __launch_bounds__(1024) gn_param_reduce_kernel(const float2* __r
   }
 }
 
+long long gn_backward_scratch_floats(const dmc_gn_bwd_desc& d) {
+  const long long C = d.src_c[0] + (d.nsrc == 2 ? d.src_c[1] : 0);
+  const long long slabs = (d.HW + GB_SLAB - 1) / GB_SLAB;
+  return static_cast<long long>(d.B) * slabs * (2 * C + C / 4) + 4LL * d.B * d.groups;
+}
+
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.nsrc == 1 || d.nsrc == 2, "gn_backward: nsrc=%d", d.nsrc);
   DMC_REQUIRE(d.src[0] && d.stats[0] && d.dout && d.dsrc[0] && d.gamma && d.beta && d.dgamma && d.dbeta && d.scratch,
@@ -305,6 +334,8 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   const int slabs = (d.HW + GB_SLAB - 1) / GB_SLAB;
   a.pgb = d.scratch;
   a.ps = d.scratch + static_cast<size_t>(d.B) * slabs * C * 2;
+  a.gm = a.ps + static_cast<size_t>(d.B) * slabs * (C / 8) * 2;
+  a.gg = a.gm + static_cast<size_t>(d.B) * d.groups * 2;
   a.HW = d.HW; a.C0_8 = C0 / 8; a.C1_8 = C1 / 8; a.groups = d.groups; a.eps = d.eps; a.silu = d.silu;
   a.drop_thresh = dropout_threshold(d.drop_p);
   a.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
@@ -318,7 +349,9 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
     DMC_CUDA_OK(cudaFuncSetAttribute(gn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
+  gn_group_moments_kernel<<<d.B, 256, 0, st>>>(a);
   gn_bwd_kernel<false><<<grid, 256, smem, st>>>(a);
+  gn_group_grads_kernel<<<d.B, 256, 0, st>>>(a, slabs);
   gn_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
   gn_param_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
                                                           d.B * slabs, C);

@@ -321,7 +321,7 @@ class UNetTrainEngine:
                 if o["drop_p"] > 0:  # the same (constant + device seed) pair as the forward pass
                     d.seed, d.seed_dev = layer_seed(pl.op_index[i]), self.seed_dev.data_ptr()
                 d.dgamma, d.dbeta = self.gview[o["prefix"] + ".weight"].data_ptr(), self.gview[o["prefix"] + ".bias"].data_ptr()
-                gn_scratch_need = max(gn_scratch_need, B * ((HW + 127) // 128) * (2 * Ctot + Ctot // 4))
+                gn_scratch_need = max(gn_scratch_need, int(lib.dmc_gn_backward_scratch(C.byref(d))))
                 gn_descs.append(d)
                 if o["drop_p"] > 0:
                     self.drop_ops.append(pl.op_index[i])

@@ -150,8 +150,10 @@ typedef struct {
   const uint32_t* seed_dev; /* the forward pass's seed_dev (see dmc_gn_apply_desc) */
   float* dgamma;           /* fp32 [C] */
   float* dbeta;            /* fp32 [C] */
-  float* scratch;          /* fp32 [B * ceil(HW/128) * (2*C + C/4)] */
+  float* scratch;          /* fp32, dmc_gn_backward_scratch() floats */
 } dmc_gn_bwd_desc;
+/* number of fp32 scratch elements dmc_gn_backward needs for this geometry (B, HW, channels, groups) */
+DMC_API int64_t dmc_gn_backward_scratch(const dmc_gn_bwd_desc* d);
 DMC_API int dmc_gn_backward(const dmc_gn_bwd_desc* d, void* stream);
 
 /* Attention backward (models/unet.py:88-96 under autograd): dqkv from qkv, the forward output and its gradient.

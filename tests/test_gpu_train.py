@@ -123,8 +123,6 @@ def test_groupnorm_silu_backward(cs, H, B, silu):
     dout = nhwc_bf16(dy)
     dsrc = [torch.full_like(x, float("nan")) for x in xn]
     dgamma, dbeta = torch.full((C_,), float("nan"), device="cuda"), torch.full((C_,), float("nan"), device="cuda")
-    nslab = (H * H + 127) // 128
-    scratch = torch.empty(B * nslab * (2 * C_ + C_ // 4), device="cuda")
     d = _lib.GnBwdDesc()
     d.nsrc = len(cs)
     for i in range(len(cs)):
@@ -132,6 +130,7 @@ def test_groupnorm_silu_backward(cs, H, B, silu):
         d.dsrc[i], d.accumulate[i] = dsrc[i].data_ptr(), 0
     d.dout, d.B, d.HW, d.groups = dout.data_ptr(), B, H * H, 8
     d.gamma, d.beta, d.eps, d.silu = gamma.detach().data_ptr(), beta.detach().data_ptr(), 1e-5, silu
+    scratch = torch.empty(int(lib.dmc_gn_backward_scratch(C.byref(d))), device="cuda")
     d.dgamma, d.dbeta, d.scratch = dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr()
     _lib.check(lib.dmc_gn_backward(C.byref(d), _lib.stream_ptr()), "gn_backward")
     torch.cuda.synchronize()
@@ -172,12 +171,12 @@ def test_dropout_mask_is_the_same_in_forward_and_backward():
     dout = nhwc_bf16(dy)
     dsrc = torch.empty_like(x)
     dg, db = torch.empty(C_, device="cuda"), torch.empty(C_, device="cuda")
-    scratch = torch.empty(B * 2 * (2 * C_ + C_ // 4), device="cuda")
     d = _lib.GnBwdDesc()
     d.nsrc = 1
     d.src[0], d.src_c[0], d.stats[0], d.stats_slots[0], d.dsrc[0] = x.data_ptr(), C_, stats[0].data_ptr(), slots, dsrc.data_ptr()
     d.dout, d.B, d.HW, d.groups = dout.data_ptr(), B, H * H, 8
     d.gamma, d.beta, d.eps, d.silu, d.drop_p, d.seed = gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, p, seed
+    scratch = torch.empty(int(lib.dmc_gn_backward_scratch(C.byref(d))), device="cuda")
     d.dgamma, d.dbeta, d.scratch = dg.data_ptr(), db.data_ptr(), scratch.data_ptr()
     _lib.check(lib.dmc_gn_backward(C.byref(d), _lib.stream_ptr()), "gn_backward")
     torch.cuda.synchronize()

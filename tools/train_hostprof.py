@@ -13,7 +13,7 @@ from diffusion_models_collection_b200.models import UNet  # noqa: E402
 
 
 def main():
-    B = 128
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     dev = torch.device("cuda")
     net = UNet(**synth.CIFAR_UNET, num_classes=10)
     net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
