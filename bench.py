@@ -350,7 +350,9 @@ def run_train_workload(args, rank, local_rank, world):
     net = net.to(dev).train()
     ema = [p.detach().clone() for p in net.parameters()] if rank == 0 else None
     bucket_mb = float(os.environ.get("DMC_DDP_BUCKET_MB", "25"))  # 25 = torch default (the reference's setting)
-    model = torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb) if world > 1 else net
+    bucket_view = os.environ.get("DMC_DDP_BUCKET_VIEW", "0") == "1"  # default False = torch default (the reference's setting)
+    model = (torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb, gradient_as_bucket_view=bucket_view)
+             if world > 1 else net)
     ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
     opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
     B = args.batch
@@ -432,6 +434,7 @@ def run_train_workload(args, rank, local_rank, world):
             "gpu_launches": int((info["forward_launches"] + info["backward_launches"]) * args.steps),
             "loss": loss_now, "host_enqueue_ms_per_step": host_ms}
     line["config"]["ddp_bucket_mb"] = bucket_mb if world > 1 else None
+    line["config"]["ddp_gradient_as_bucket_view"] = bucket_view if world > 1 else None
     pk = peaks()
     flops = info["gemm_flops"]
     line["model_flops_utilization"] = {"achieved_tflops": flops * args.steps / (ms / 1e3) / 1e12, "gemm_flops_per_step": flops,

@@ -287,3 +287,41 @@ def test_conv_accumulates_in_place_through_its_residual():
     inplace1 = base.clone()
     run_conv([x], [1], w1, cout, residual=inplace1, out_tensor=inplace1)
     assert torch.equal(sep1, inplace1)
+
+
+def test_weight_pack_kernel_matches_torch_bit_for_bit():
+    """the one-launch re-pack of the GEMM operands after an optimizer step: forward layout [co][tap][ci] (also as a column range
+    of a K-concatenated matrix) and input-gradient layout [ci][flipped tap][co padded]"""
+    lib = _lib.load()
+    w3 = _rand((96, 160, 3, 3), 1)       # not multiples of 32 tiles on purpose
+    w1 = _rand((96, 200, 1, 1), 2)
+    head = _rand((3, 128, 3, 3), 3)
+    K = 9 * 160 + 200
+    fwd = torch.full((96, K), float("nan"), device="cuda", dtype=torch.bfloat16)      # fused conv2 + shortcut operand
+    dg3 = torch.full((160, 9 * 96), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dg1 = torch.full((64, 96), float("nan"), device="cuda", dtype=torch.bfloat16)      # input channels 100 .. 163 of the 1x1
+    dgh = torch.zeros((128, 9 * 128), device="cuda", dtype=torch.bfloat16)             # head: co padded 3 -> 128
+    items = []
+
+    def item(src, dst, ci0, cin, taps, mode, ld, col0, cpad):
+        it = _lib.PackItem()
+        it.src, it.dst = src.data_ptr(), dst.data_ptr()
+        it.cout, it.cin_total, it.ci0, it.cin, it.taps, it.mode, it.ld, it.col0, it.cpad = (src.shape[0], src.shape[1], ci0, cin, taps,
+                                                                                         mode, ld, col0, cpad)
+        items.append(it)
+
+    item(w3, fwd, 0, 160, 9, 0, K, 0, 0)
+    item(w1, fwd, 0, 200, 1, 0, K, 9 * 160, 0)
+    item(w3, dg3, 0, 160, 9, 1, 9 * 96, 0, 96)
+    item(w1, dg1, 100, 64, 1, 1, 96, 0, 96)
+    item(head, dgh, 0, 128, 9, 1, 9 * 128, 0, 128)
+    table, n = _lib.pack_table(items, torch.device("cuda"))
+    _lib.check(lib.dmc_pack_weights(table.data_ptr(), n, _lib.stream_ptr()), "pack")
+    torch.cuda.synchronize()
+    want_fwd = torch.cat([pack3(w3), w1.reshape(96, 200)], dim=1).to(torch.bfloat16)
+    assert torch.equal(fwd, want_fwd)
+    assert torch.equal(dg3, pack3(w3.flip(2, 3).permute(1, 0, 2, 3)).to(torch.bfloat16))
+    assert torch.equal(dg1, w1.reshape(96, 200)[:, 100:164].t().to(torch.bfloat16))
+    want_h = torch.zeros((128, 9, 128), device="cuda")
+    want_h[:, :, :3] = head.flip(2, 3).permute(1, 2, 3, 0).reshape(128, 9, 3)
+    assert torch.equal(dgh, want_h.reshape(128, -1).to(torch.bfloat16))
