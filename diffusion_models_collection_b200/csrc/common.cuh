@@ -297,6 +297,16 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 
 // instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
 // N>>3 at bits [17,23), M>>4 at bits [24,29).  b_mn_major=1 selects an MN-major (transposed) B operand.
+// counter-based dropout: one 32-bit hash per PAIR of consecutive elements (even index `idx_even`), 16 bits each; an element is
+// kept when its 16 bits are >= thresh16 = round(p * 65536).  Forward (gn_apply) and backward (gn_backward) regenerate the same
+// mask from (seed, element index).
+__device__ __forceinline__ uint32_t dropout_hash2(uint32_t seed, uint64_t idx_even) {
+  const uint64_t pr = idx_even >> 1;
+  uint32_t h = static_cast<uint32_t>(pr) * 0x9E3779B1u ^ (static_cast<uint32_t>(pr >> 32) * 0x85EBCA77u) ^ seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);

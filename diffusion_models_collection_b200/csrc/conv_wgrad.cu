@@ -336,7 +336,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
     const int tap = static_cast<int>((i / Cin) % taps);
     const int co = static_cast<int>(i / (static_cast<size_t>(Cin) * taps));
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[static_cast<size_t>(k) * total + i];
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {  // four loads in flight, added in index order
+      const float v0 = partial[static_cast<size_t>(k) * total + i], v1 = partial[static_cast<size_t>(k + 1) * total + i];
+      const float v2 = partial[static_cast<size_t>(k + 2) * total + i], v3 = partial[static_cast<size_t>(k + 3) * total + i];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; k < splits; ++k) s += partial[static_cast<size_t>(k) * total + i];
     float* o = dw + (static_cast<size_t>(co) * Cin + ci) * taps + tap;  // [Cout, Cin, kh, kw]
     *o = accumulate ? *o + s : s;
   }

@@ -316,13 +316,6 @@ struct GnApplyArgs {
   const uint32_t* seed_dev;  // optional per-step seed in device memory (added to `seed`): lets a captured graph draw new masks
 };
 
-// counter-based dropout mask (the same function as in train_ops.cu: forward and backward regenerate the same mask)
-__device__ __forceinline__ bool gn_dropout_keep(uint32_t seed, uint64_t idx, uint32_t thresh) {
-  uint32_t h = static_cast<uint32_t>(idx) * 0x9E3779B1u ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u) ^ seed;
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h >= thresh;
-}
-
 // Phase 1 (per CTA, cheap): warp g reduces the partial sums of group g (slots x 8-channel blocks, possibly from both
 // sources of a concat) with lane-strided loads and a fixed shuffle tree -> mean / rstd, bit-reproducible.
 // Phase 2: every thread owns ONE 8-channel block (its 8 scales / shifts live in registers) and walks the pixels of the
@@ -442,8 +435,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
           if (a.drop_thresh != 0u) {  // dropout after SiLU (ResidualBlock.conv2, models/unet.py:53), training only
             const uint64_t idx = ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8 + 2 * j;
             const uint32_t seed = a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0u);
-            y0 = gn_dropout_keep(seed, idx, a.drop_thresh) ? y0 * a.drop_scale : 0.f;
-            y1 = gn_dropout_keep(seed, idx + 1, a.drop_thresh) ? y1 * a.drop_scale : 0.f;
+            const uint32_t h = dropout_hash2(seed, idx);
+            y0 = (h & 0xFFFFu) >= a.drop_thresh ? y0 * a.drop_scale : 0.f;
+            y1 = (h >> 16) >= a.drop_thresh ? y1 * a.drop_scale : 0.f;
           }
           o[j] = pack_bf16x2(y0, y1);
           if (LO) {

@@ -8,16 +8,11 @@
 
 namespace dmc {
 
-// counter-based dropout mask: the same (seed, element index) gives the same decision in forward and backward
-__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint64_t idx, uint32_t thresh) {
-  uint32_t h = static_cast<uint32_t>(idx) * 0x9E3779B1u ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u) ^ seed;
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h >= thresh;
-}
+// 16-bit keep threshold of the pair hash (common.cuh: dropout_hash2); 0 = no dropout
 uint32_t dropout_threshold(float p) {
   if (p <= 0.f) return 0u;
-  const double t = static_cast<double>(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+  const double t = static_cast<double>(p) * 65536.0 + 0.5;
+  return t >= 65535.0 ? 65535u : std::max(1u, static_cast<uint32_t>(t));
 }
 
 // =============================================================================================
@@ -88,24 +83,30 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, float*
 }
 
 // dz of the 8 channels of one pixel-block from x, dout
+template <bool SILU, bool DROP>
 __device__ __forceinline__ void gn_dz8(const GnBwdArgs& a, const uint4& xv, const uint4& dv, float mean, float rstd,
-                                       const float (&gam)[8], const float (&bet)[8], uint64_t idx0, float (&xh)[8],
+                                       const float (&gam)[8], const float (&bet)[8], uint64_t idx0, uint32_t seed, float (&xh)[8],
                                        float (&dz)[8]) {
-  const uint32_t seed = a.drop_thresh != 0u ? a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0u) : 0u;
   const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
   const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+  const float nmr = -mean * rstd;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 xf = unpack_bf16x2(xw[j]);
     const float2 df = unpack_bf16x2(dw[j]);
-    const float xs[2] = {xf.x, xf.y}, ds[2] = {df.x, df.y};
+    const float xs[2] = {xf.x, xf.y};
+    float ds[2] = {df.x, df.y};
+    if (DROP) {
+      const uint32_t h = dropout_hash2(seed, idx0 + 2 * j);
+      ds[0] = (h & 0xFFFFu) >= a.drop_thresh ? ds[0] * a.drop_scale : 0.f;
+      ds[1] = (h >> 16) >= a.drop_thresh ? ds[1] * a.drop_scale : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int c = 2 * j + k;
-      xh[c] = (xs[k] - mean) * rstd;
+      xh[c] = fmaf(xs[k], rstd, nmr);
       float d = ds[k];
-      if (a.drop_thresh != 0u) d = dropout_keep(seed, idx0 + c, a.drop_thresh) ? d * a.drop_scale : 0.f;
-      if (a.silu) {
+      if (SILU) {
         const float z = fmaf(xh[c], gam[c], bet[c]);
         float th;  // sigmoid(z) = 0.5 + 0.5 tanh(z / 2): one MUFU op (the forward pass uses the same form)
         asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) gn_group_grads_kernel(GnBwdArgs a, int sl
   }
 }
 
-template <bool APPLY>
+template <bool APPLY, bool SILU, bool DROP>
 __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   __shared__ float s_mean[32], s_rstd[32], s_g1[32], s_g2[32];
   extern __shared__ float red[];  // pass A: [rows][C8][18]
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   const uint4* dout = a.dout + static_cast<size_t>(n) * a.HW * C8 + cb;
   const int p0 = blockIdx.x * GB_SLAB;
   const int p1 = min(p0 + GB_SLAB, a.HW);
+  const uint32_t seed = DROP ? a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0u) : 0u;
   float dgam[8], dbet[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) dgam[j] = dbet[j] = 0.f;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
         if (APPLY && acc) on = *(dsrc + static_cast<size_t>(p + rpi) * sstride);
       }
       float xh[8], dz[8];
-      gn_dz8(a, xv, dv, mean, rstd, gam, bet, ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8, xh, dz);
+      gn_dz8<SILU, DROP>(a, xv, dv, mean, rstd, gam, bet, ((static_cast<uint64_t>(n) * a.HW + p) * C8 + cb) * 8, seed, xh, dz);
       if (!APPLY) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -344,15 +346,20 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   const int C8 = C / 8, rows = std::max(1, 256 / C8);
   dim3 grid(slabs, d.B);
   const size_t smem = static_cast<size_t>(rows) * C8 * 18 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    DMC_CUDA_OK(cudaFuncSetAttribute(gn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+  DMC_REQUIRE(smem <= 48 * 1024, "gn_backward: %zu bytes of shared memory", smem);
+  const bool silu = d.silu != 0, drop = a.drop_thresh != 0u;
   gn_group_moments_kernel<<<d.B, 256, 0, st>>>(a);
-  gn_bwd_kernel<false><<<grid, 256, smem, st>>>(a);
+#define DMC_GN_BWD(APPLY, SM)                                                                             \
+  do {                                                                                                    \
+    if (silu && drop) gn_bwd_kernel<APPLY, true, true><<<grid, 256, SM, st>>>(a);                         \
+    else if (silu) gn_bwd_kernel<APPLY, true, false><<<grid, 256, SM, st>>>(a);                           \
+    else if (drop) gn_bwd_kernel<APPLY, false, true><<<grid, 256, SM, st>>>(a);                           \
+    else gn_bwd_kernel<APPLY, false, false><<<grid, 256, SM, st>>>(a);                                    \
+  } while (0)
+  DMC_GN_BWD(false, smem);
   gn_group_grads_kernel<<<d.B, 256, 0, st>>>(a, slabs);
-  gn_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
+  DMC_GN_BWD(true, 0);
+#undef DMC_GN_BWD
   gn_param_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
                                                           d.B * slabs, C);
   DMC_CUDA_OK(cudaGetLastError());

@@ -1,5 +1,7 @@
 """Runs selected backward ops of one training step inside a cudaProfiler range (for ncu --profile-from-start off).
-   python tools/profile_train.py kind[:name] ...   e.g.  conv_wgrad:down_blocks.4.0.conv2 gn_backward:up_blocks.9.0.conv1.0"""
+   python tools/profile_train.py kind[:name[:max]] ...   e.g.  conv_wgrad:down_blocks.4.0.conv2 gn_backward:up_blocks.9.0.conv1.0
+   attention_backward::1   (an empty name matches every op of the kind; max caps how many of them run -- ncu --set full replays
+   each kernel ~40 times, keep the selection to a dozen kernels)"""
 import sys
 
 import torch
@@ -11,7 +13,8 @@ from diffusion_models_collection_b200.models import UNet  # noqa: E402
 
 
 def main():
-    sel = [a.split(":", 1) + [""] for a in sys.argv[1:]]
+    sel = [(a.split(":") + ["", ""])[:3] for a in sys.argv[1:]]
+    left = {i: (int(k[2]) if k[2] else 10 ** 9) for i, k in enumerate(sel)}
     B = 128
     torch.manual_seed(0)
     net = UNet(**synth.CIFAR_UNET, num_classes=10)
@@ -28,8 +31,13 @@ def main():
     picked = []
     for s in reversed(eng.segs):
         for fn, args, m in eng.bwd[s]:
-            if args is not None and any(m["kind"] == k[0] and (not k[1] or m["name"] == k[1]) for k in sel):
-                picked.append((fn, args, m))
+            if args is None:
+                continue
+            for i, k in enumerate(sel):
+                if m["kind"] == k[0] and (not k[1] or m["name"] == k[1]) and left[i] > 0:
+                    left[i] -= 1
+                    picked.append((fn, args, m))
+                    break
     print("profiling", [(m["kind"], m["name"]) for _, _, m in picked])
     torch.cuda.profiler.start()
     for fn, args, m in picked:
