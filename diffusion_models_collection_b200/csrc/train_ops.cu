@@ -276,36 +276,42 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(GnBwdArgs a) {
   }
 }
 
-// dgamma[c], dbeta[c] = sum over (image, slab) of the partials: 32 row lanes per channel, each adding its rows in index
-// order, then the 32 lane sums in lane order (fixed association: bit-reproducible)
+// dgamma[c], dbeta[c] = sum over (image, slab) of the partials: one CTA per 8 channels, 128 row lanes each adding its rows in
+// index order, then the 128 lane sums in lane order (fixed association: bit-reproducible).  Many short chains instead of a few
+// long ones: the kernel is pure latency (a few MB).
 __global__ void __launch_bounds__(1024) gn_param_reduce_kernel(const float2* __restrict__ pgb, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, int rows, int C) {
-  __shared__ float2 red[32][33];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ float2 red[128][8];
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float g = 0.f, b = 0.f;
   if (c < C) {
     int r = rl;
-    for (; r + 96 < rows; r += 128) {
+    for (; r + 384 < rows; r += 512) {
       float2 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = pgb[static_cast<size_t>(r + 32 * u) * C + c];
+      for (int u = 0; u < 4; ++u) v[u] = pgb[static_cast<size_t>(r + 128 * u) * C + c];
 #pragma unroll
       for (int u = 0; u < 4; ++u) { g += v[u].x; b += v[u].y; }
     }
-    for (; r < rows; r += 32) {
+    for (; r < rows; r += 128) {
       const float2 v = pgb[static_cast<size_t>(r) * C + c];
       g += v.x; b += v.y;
     }
   }
   red[rl][cl] = make_float2(g, b);
   __syncthreads();
-  if (rl == 0 && c < C) {
-    g = 0.f; b = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { g += red[k][cl].x; b += red[k][cl].y; }
-    dgamma[c] = g;
-    dbeta[c] = b;
+  if (threadIdx.x < 32) {  // 4 lanes per channel add 32 lane sums each (in order), then lane order across the 4
+    const int ch = threadIdx.x & 7, part = threadIdx.x >> 3;
+    float gs = 0.f, bs = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) { gs += red[part * 32 + k][ch].x; bs += red[part * 32 + k][ch].y; }
+    const float g1 = __shfl_sync(0xFFFFFFFFu, gs, ch + 8), g2 = __shfl_sync(0xFFFFFFFFu, gs, ch + 16), g3 = __shfl_sync(0xFFFFFFFFu, gs, ch + 24);
+    const float b1 = __shfl_sync(0xFFFFFFFFu, bs, ch + 8), b2 = __shfl_sync(0xFFFFFFFFu, bs, ch + 16), b3 = __shfl_sync(0xFFFFFFFFu, bs, ch + 24);
+    if (part == 0 && blockIdx.x * 8 + ch < C) {
+      dgamma[blockIdx.x * 8 + ch] = ((gs + g1) + g2) + g3;
+      dbeta[blockIdx.x * 8 + ch] = ((bs + b1) + b2) + b3;
+    }
   }
 }
 
@@ -360,7 +366,7 @@ int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st) {
   gn_group_grads_kernel<<<d.B, 256, 0, st>>>(a, slabs);
   DMC_GN_BWD(true, 0);
 #undef DMC_GN_BWD
-  gn_param_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
+  gn_param_reduce_kernel<<<(C + 7) / 8, 1024, 0, st>>>(reinterpret_cast<const float2*>(a.pgb), d.dgamma, d.dbeta,
                                                           d.B * slabs, C);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -550,13 +556,22 @@ __global__ void __launch_bounds__(256) channel_sum_image_kernel(const uint4* __r
   }
 }
 
-__global__ void __launch_bounds__(256) channel_sum_total_kernel(const float* __restrict__ per_image, float* __restrict__ out, int B,
-                                                                int C, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024) channel_sum_total_kernel(const float* __restrict__ per_image, float* __restrict__ out, int B,
+                                                                 int C, int accumulate) {
+  __shared__ float red[32][33];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s2 = 0.f;
-  for (int n = 0; n < B; ++n) s2 += per_image[static_cast<size_t>(n) * C + c];
-  out[c] = accumulate ? out[c] + s2 : s2;
+  if (c < C)
+    for (int n = nl; n < B; n += 32) s2 += per_image[static_cast<size_t>(n) * C + c];
+  red[nl][cl] = s2;
+  __syncthreads();
+  if (nl == 0 && c < C) {
+    s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s2 += red[k][cl];
+    out[c] = accumulate ? out[c] + s2 : s2;
+  }
 }
 
 int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int per_image, int accumulate, float* scratch,
@@ -568,7 +583,7 @@ int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int pe
                                                  per_image ? accumulate : 0);
   DMC_CUDA_OK(cudaGetLastError());
   if (!per_image) {
-    channel_sum_total_kernel<<<(C + 255) / 256, 256, 0, st>>>(scratch, out, B, C, accumulate);
+    channel_sum_total_kernel<<<(C + 31) / 32, 1024, 0, st>>>(scratch, out, B, C, accumulate);
     DMC_CUDA_OK(cudaGetLastError());
   }
   return 0;
