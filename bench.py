@@ -351,8 +351,12 @@ def run_train_workload(args, rank, local_rank, world):
     ema = [p.detach().clone() for p in net.parameters()] if rank == 0 else None
     bucket_mb = float(os.environ.get("DMC_DDP_BUCKET_MB", "25"))  # 25 = torch default (the reference's setting)
     bucket_view = os.environ.get("DMC_DDP_BUCKET_VIEW", "0") == "1"  # default False = torch default (the reference's setting)
-    model = (torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb, gradient_as_bucket_view=bucket_view)
-             if world > 1 else net)
+    native_ar = os.environ.get("DMC_NATIVE_ALLREDUCE", "0") == "1"  # UNet.set_gradient_allreduce() instead of DDP(model)
+    if world > 1 and native_ar:
+        model = net.set_gradient_allreduce()
+    else:
+        model = (torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb, gradient_as_bucket_view=bucket_view)
+                 if world > 1 else net)
     ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
     opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
     B = args.batch
@@ -427,7 +431,7 @@ def run_train_workload(args, rank, local_rank, world):
             "config": {"workload": "UNet cond (10+1 null) CIFAR-10 32x32 training step: CFG label dropout 0.2, t~U[0,1000), q_sample, "
                                    "eps-MSE, backward, clip_grad_norm 1.0, fused AdamW, EMA on rank 0 (BASELINE.json configs[4]); "
                                    "side measurement, not the headline metric",
-                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"DDP x{world} (NCCL all-reduce overlapped)",
+                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": (f"native per-entry all-reduce x{world} (NCCL, overlapped, no DDP wrapper)" if (world > 1 and os.environ.get("DMC_NATIVE_ALLREDUCE", "0") == "1") else f"DDP x{world} (NCCL all-reduce overlapped)"),
                        "l2": "activations + gradients of one step are > 10x the 126 MB L2", "dropout": 0.1},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},

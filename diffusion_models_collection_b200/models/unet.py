@@ -315,6 +315,7 @@ class UNet(nn.Module):
         self._plans = {}
         self._train_engines = {}
         self._plist = None
+        self._grad_allreduce = None  # process group of the native data-parallel mode (set_gradient_allreduce)
         self._packed = None
         self._packed_version = self._packed_ids = None
         self._init_parameters()
@@ -722,6 +723,28 @@ class UNet(nn.Module):
                 eng = self._train_engines[key] = UNetTrainEngine(self, device, B, has_y, drop_p)
             eng.forward(x, t, y)
             return eng.attach()
+
+    def set_gradient_allreduce(self, process_group=None, enabled=True, broadcast_parameters=True):
+        """Native data-parallel training WITHOUT the DistributedDataParallel wrapper: every backward pass averages the gradients
+        over `process_group` (default: the world) with one asynchronous NCCL all-reduce per UNet entry, issued straight from
+        the engine's flat per-entry gradient buffers while the earlier entries' backward kernels run, and assigns `.grad`
+        itself.  It replaces `DDP(model)` (utils/trainer.py:58-61) -- use one or the other, not both: DDP's per-parameter
+        bucket copies (714 small kernels and their hooks per step) cost 1.5 - 3 ms of a 15 ms step.  Gradient accumulation
+        over several backward passes averages every pass (there is no no_sync())."""
+        import torch.distributed as dist
+
+        if not enabled:
+            self._grad_allreduce = None
+            return self
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("set_gradient_allreduce: torch.distributed is not initialised")
+        group = process_group if process_group is not None else dist.group.WORLD
+        if broadcast_parameters:  # what DDP does when it wraps the model: rank 0's parameters everywhere
+            with torch.no_grad():
+                for p in self.parameters():
+                    dist.broadcast(p.data, src=dist.get_global_rank(group, 0), group=group)
+        self._grad_allreduce = group
+        return self
 
     @contextlib.contextmanager
     def uniform_timesteps(self):

@@ -71,7 +71,7 @@ class _Segment(torch.autograd.Function):
         if ctx.step != eng.step_id:
             raise RuntimeError("UNet backward: the activations of this forward have been overwritten by a later forward of the same "
                                "batch size (run backward() before the next training forward)")
-        grads = eng.backward_segment(ctx.k, g)
+        grads = eng.backward_segment(ctx.k, g, ctx.mask)
         grads = [gr if m else None for gr, m in zip(grads, ctx.mask)]
         tok = None if ctx.k == 0 else torch.zeros(0, device=eng.device, dtype=torch.float32)
         return (None, None, tok, *grads)
@@ -130,6 +130,7 @@ class UNetTrainEngine:
         self._seg_param_objs = None
         self._cond_param_objs = None
         self.graphs = None
+        self._pending = []
 
     # ------------------------------------------------------------------------------------------------------------------
     def _build_backward(self):
@@ -471,7 +472,7 @@ class UNetTrainEngine:
             cond = cond + F.linear(F.silu(yemb), wy)
         return cond
 
-    def backward_segment(self, k, g):
+    def backward_segment(self, k, g, mask):
         seg = self.segs[k]
         if seg == "output":
             self.deps_static.copy_(g)
@@ -481,9 +482,45 @@ class UNetTrainEngine:
             self._run_ops(self.bwd[seg])
         flat = self.flat[seg].clone()
         grads = [flat[o: o + n].view(shp) for _, o, n, shp in self.layout[seg]]
+        ar = self.net._grad_allreduce
+        if ar is None:
+            if k == 0:
+                grads += self._cond_grads()
+            return grads
+        # native data-parallel mode (UNet.set_gradient_allreduce): ONE asynchronous NCCL all-reduce per UNet entry over its flat
+        # gradient buffer, launched as soon as the entry's backward kernels are enqueued (it overlaps the earlier entries'
+        # kernels); .grad is assigned by the engine after the last entry -- no per-parameter bucket copies, no hooks
+        import torch.distributed as dist
+
+        params = self._seg_param_objs[k]
+        self._pending.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=ar, async_op=True), params, grads, mask))
         if k == 0:
-            grads += self._cond_grads()
-        return grads
+            cg = self._cond_grads()
+            idx = [i for i, t in enumerate(cg) if t is not None]
+            if idx:
+                cflat = torch.cat([cg[i].reshape(-1) for i in idx])
+                dist.all_reduce(cflat, op=dist.ReduceOp.AVG, group=ar)
+                off = 0
+                for i in idx:
+                    n = cg[i].numel()
+                    cg[i] = cflat[off: off + n].view(cg[i].shape)
+                    off += n
+            grads += cg
+            fresh_p, acc_p, acc_g = [], [], []
+            for work, ps, gs, mk in self._pending:
+                work.wait()  # the current stream waits for the collective; the host does not
+                for p_, g_, m_ in zip(ps, gs, mk):
+                    if not m_ or g_ is None:
+                        continue
+                    if p_.grad is None:
+                        p_.grad = g_
+                    else:
+                        acc_p.append(p_.grad)
+                        acc_g.append(g_)
+            if acc_p:
+                torch._foreach_add_(acc_p, acc_g)
+            self._pending = []
+        return [None] * len(mask)
 
     def _cond_grads(self):
         net = self.net

@@ -205,3 +205,18 @@ def test_cuda_graph_replay_equals_eager_launches():
     assert l_eager == l_graph
     for a, b in zip(g_eager, g_graph):
         assert torch.equal(a, b)
+
+
+def test_native_gradient_allreduce_matches_ddp_on_two_gpus():
+    """UNet.set_gradient_allreduce() (the DDP-free data-parallel mode) under torchrun on 2 GPUs: same gradients as DDP(model)"""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(root, "tools", "check_native_allreduce.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "native all-reduce == DDP" in r.stdout
