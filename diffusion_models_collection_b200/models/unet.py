@@ -724,6 +724,14 @@ class UNet(nn.Module):
             eng.forward(x, t, y)
             return eng.attach()
 
+    @property
+    def module(self):
+        """DDP-compatibility alias, only in the native data-parallel mode: the reference's trainer reaches the wrapped model as
+        `self.model.module` when distributed (utils/trainer.py:127,159-162,193,335)"""
+        if self._grad_allreduce is None:
+            raise AttributeError("module")
+        return self
+
     def set_gradient_allreduce(self, process_group=None, enabled=True, broadcast_parameters=True):
         """Native data-parallel training WITHOUT the DistributedDataParallel wrapper: every backward pass averages the gradients
         over `process_group` (default: the world) with one asynchronous NCCL all-reduce per UNet entry, issued straight from
