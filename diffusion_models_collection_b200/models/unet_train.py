@@ -490,16 +490,14 @@ class UNetTrainEngine:
         # native data-parallel mode (UNet.set_gradient_allreduce): ONE asynchronous NCCL all-reduce per UNet entry over its flat
         # gradient buffer, launched as soon as the entry's backward kernels are enqueued (it overlaps the earlier entries'
         # kernels); .grad is assigned by the engine after the last entry -- no per-parameter bucket copies, no hooks
-        import torch.distributed as dist
-
         params = self._seg_param_objs[k]
-        self._pending.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=ar, async_op=True), params, grads, mask))
+        self._pending.append((self._allreduce_mean(flat, ar, True), params, grads, mask))
         if k == 0:
             cg = self._cond_grads()
             idx = [i for i, t in enumerate(cg) if t is not None]
             if idx:
                 cflat = torch.cat([cg[i].reshape(-1) for i in idx])
-                dist.all_reduce(cflat, op=dist.ReduceOp.AVG, group=ar)
+                self._allreduce_mean(cflat, ar, False)
                 off = 0
                 for i in idx:
                     n = cg[i].numel()
@@ -521,6 +519,16 @@ class UNetTrainEngine:
                 torch._foreach_add_(acc_p, acc_g)
             self._pending = []
         return [None] * len(mask)
+
+    @staticmethod
+    def _allreduce_mean(buf, group, async_op):
+        """in-place mean over the group: ReduceOp.AVG where the backend has it (NCCL), else SUM of pre-divided values (gloo)"""
+        import torch.distributed as dist
+
+        if dist.get_backend(group) == "nccl":
+            return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        buf.div_(dist.get_world_size(group))
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     def _cond_grads(self):
         net = self.net
