@@ -4,7 +4,6 @@ parameter exactly once, reads no activation gradient before a producer wrote it,
 parameter, and the DDP-free data-parallel mode averages the per-entry flat buffers over a world of 2 (gloo)."""
 
 import contextlib
-import ctypes as C
 import os
 
 import pytest
