@@ -128,8 +128,55 @@ def cpu_reference_images_per_sec(batch=8, sub_steps=4, cfg_scale=3.0, repeats=1)
                                     f"dynamic threshold), fp32 oracle port on the host, time scaled by 50/{sub_steps}"}
 
 
+def cpu_reference_train_images_per_sec(batch=8, steps=1):
+    """images/s of the reference's training step on the host: autograd through the fp32 oracle restatement of the UNet
+    (eps-MSE loss of q_sample'd images, backward, clip_grad_norm_ 1.0, AdamW) on `batch` images, all host threads."""
+    from diffusion_models_collection_b200 import synth
+    from oracle import model_oracle, sched_oracle as so
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = synth.CIFAR_UNET
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.make_unet_state_dict(cfg, 10, seed=42).items()}
+    params = list(sd.values())
+    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=1e-4)
+    tb = so.make_tables()
+    g = torch.Generator().manual_seed(42)
+    x0 = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    y = torch.randint(0, 10, (batch,), generator=g) + 1
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        t = torch.randint(0, 1000, (batch,), generator=g)
+        noise = torch.randn(batch, 3, 32, 32, generator=g)
+        eps = model_oracle.unet_forward.__wrapped__(sd, cfg, so.q_sample(tb, x0, t, noise), t, y, 10)
+        loss = torch.nn.functional.mse_loss(noise, eps)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return batch / best, {"value": batch / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                          "sample": f"{steps} training step(s) of {batch} images (q_sample, UNet forward + autograd backward through the "
+                                    "fp32 oracle port, clip_grad_norm_, AdamW) on the host"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
+        return
+    if args.workload == "train":  # side measurement: the reference's training step on the host cores
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_train_images_per_sec(batch=2, steps=1)
+        t0 = time.perf_counter()
+        v, cb = cpu_reference_train_images_per_sec(batch=args.ref_batch, steps=args.steps)
+        wall = time.perf_counter() - t0
+        print(json.dumps({"impl": "reference", "metric": "train_unet_cifar10_images_per_sec", "value": v, "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "UNet cond CIFAR-10 training step (BASELINE.json configs[4]), reference algorithm on "
+                                                 "the host cores", "per_gpu_batch": args.ref_batch},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
         return
     for _ in range(args.warmup):
         cpu_reference_images_per_sec(batch=2, sub_steps=1)
@@ -455,6 +502,8 @@ def run_train_workload(args, rank, local_rank, world):
                                       "weight-gradient GEMMs, each timed alone (burst peak)",
                             "tensor_ms": tms, "all_ops_ms": sum(o["ms"] for o in ops), "step_ms": ms / args.steps,
                             "by_kind_ms": {k: sum(o["ms"] for o in ops if o["kind"] == k) for k in sorted({o["kind"] for o in ops})}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, line["cpu_baseline"] = cpu_reference_train_images_per_sec(batch=args.ref_batch, steps=2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
