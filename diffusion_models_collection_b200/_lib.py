@@ -96,7 +96,8 @@ class AttnBwdDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [("x", vp), ("dy", vp), ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin", C.c_int32),
                 ("Cout", C.c_int32), ("stride", C.c_int32), ("taps", C.c_int32), ("splits", C.c_int32), ("partial", vp),
-                ("dw", vp), ("accumulate", C.c_int32)]
+                ("dw", vp), ("accumulate", C.c_int32), ("dw_cout", C.c_int32), ("dw_cin", C.c_int32), ("dw_cin_total", C.c_int32),
+                ("dw_ci0", C.c_int32)]
 
 
 class PackItem(C.Structure):

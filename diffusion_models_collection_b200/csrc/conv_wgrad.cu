@@ -327,14 +327,18 @@ conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 }
 
 // dW[co][ci][tap] (+)= sum_split partial[split][co][tap][ci], slices added in index order
+// dw may be a window of a larger parameter: rows co < dw_cout, columns ci0 .. ci0 + dw_cin of [dw_cout, dw_cin_total, kh, kw]
+// (real channels of a zero-padded operand; one source of a fused 1x1 shortcut over concatenated inputs)
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                                                int splits, int Cout, int taps, int Cin, int accumulate) {
+                                                                int splits, int Cout, int taps, int Cin, int accumulate,
+                                                                int dw_cout, int dw_cin, int dw_cin_total, int dw_ci0) {
   const size_t total = static_cast<size_t>(Cout) * taps * Cin;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int ci = static_cast<int>(i % Cin);
     const int tap = static_cast<int>((i / Cin) % taps);
     const int co = static_cast<int>(i / (static_cast<size_t>(Cin) * taps));
+    if (co >= dw_cout || ci >= dw_cin) continue;  // zero-padded rows / columns of the GEMM: not part of the parameter
     float s = 0.f;
     int k = 0;
     for (; k + 4 <= splits; k += 4) {  // four loads in flight, added in index order
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
       s += v0; s += v1; s += v2; s += v3;
     }
     for (; k < splits; ++k) s += partial[static_cast<size_t>(k) * total + i];
-    float* o = dw + (static_cast<size_t>(co) * Cin + ci) * taps + tap;  // [Cout, Cin, kh, kw]
+    float* o = dw + (static_cast<size_t>(co) * dw_cin_total + dw_ci0 + ci) * taps + tap;  // [Cout, Cin, kh, kw]
     *o = accumulate ? *o + s : s;
   }
 }
@@ -440,11 +444,16 @@ int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
   p.splits = d.splits;
   DMC_REQUIRE(d.splits >= 1 && d.splits == conv_wgrad_splits(d), "wgrad: splits=%d, expected dmc_conv_wgrad_splits() = %d", d.splits,
               conv_wgrad_splits(d));
+  const int w_cout = d.dw_cout > 0 ? d.dw_cout : d.Cout, w_cin = d.dw_cin > 0 ? d.dw_cin : d.Cin;
+  const int w_cin_total = d.dw_cin_total > 0 ? d.dw_cin_total : w_cin;
+  DMC_REQUIRE(w_cout <= d.Cout && w_cin <= d.Cin && d.dw_ci0 >= 0 && d.dw_ci0 + w_cin <= w_cin_total,
+              "wgrad: bad dw window (%d x %d at column %d of %d)", w_cout, w_cin, d.dw_ci0, w_cin_total);
   const size_t total = static_cast<size_t>(d.Cout) * d.taps * d.Cin;
   const int rblocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   if (wgrad_use_slab(d)) {
     if (launch_conv_wgrad_slab(d, st) != 0) return -1;
-    conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, d.splits, d.Cout, d.taps, d.Cin, d.accumulate);
+    conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, d.splits, d.Cout, d.taps, d.Cin, d.accumulate, w_cout, w_cin,
+                                                      w_cin_total, d.dw_ci0);
     DMC_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -463,7 +472,8 @@ int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(p.nst) * p.stage_bytes + 1024 + 256;
   conv_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmDY, p);
   DMC_CUDA_OK(cudaGetLastError());
-  conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, p.splits, d.Cout, d.taps, d.Cin, d.accumulate);
+  conv_wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d.partial, d.dw, p.splits, d.Cout, d.taps, d.Cin, d.accumulate, w_cout, w_cin,
+                                                    w_cin_total, d.dw_ci0);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

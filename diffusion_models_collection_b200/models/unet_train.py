@@ -198,11 +198,13 @@ class UNetTrainEngine:
             emit(lib.dmc_plan_run_op, handle, idx, kind="conv_dgrad", name=name,
                  flops=2.0 * B * Ho * Wo * dst.C * taps * (real_c or dyC) * flops_scale)
 
-        def wgrad(xp, xC, dyp, dyC, H, W, stride, taps, dw, name, real=None):
+        def wgrad(xp, xC, dyp, dyC, H, W, stride, taps, dw, name, real=None, window=None):
             d = _lib.WgradDesc()
             d.x, d.dy, d.B, d.Hin, d.Win, d.Cin, d.Cout, d.stride, d.taps = xp, dyp, B, H, W, xC, dyC, stride, taps
             d.splits = _lib.check(lib.dmc_conv_wgrad_splits(C.byref(d)), "dmc_conv_wgrad_splits")
             d.dw, d.accumulate = dw.data_ptr(), 0
+            if window is not None:  # (rows, columns, columns of the parameter, first column): dw is a window of a parameter
+                d.dw_cout, d.dw_cin, d.dw_cin_total, d.dw_ci0 = window
             wg_descs.append(d)
             self._keep.append(dw)
             emit(lib.dmc_conv_wgrad, C.byref(d), kind="conv_wgrad", name=name,
@@ -265,17 +267,15 @@ class UNetTrainEngine:
                 # --- weight gradients
                 a_in = srcs[0]
                 if head:
-                    tmpw = torch.empty((128, a_in.C, 3, 3), dtype=f32, device=device)
-                    wgrad(ap(a_in), a_in.C, dyp, 128, H, W, 1, 9, tmpw, wname, real=a_in.C * net.out_channels)
-                    copy_op(self.gview[wkey], tmpw[: net.out_channels])
+                    wgrad(ap(a_in), a_in.C, dyp, 128, H, W, 1, 9, self.gview[wkey], wname, real=a_in.C * net.out_channels,
+                          window=(net.out_channels, a_in.C, a_in.C, 0))  # dY is zero-padded 3 -> 128 channels
                 else:
                     wgrad(ap(a_in), a_in.C, dyp, dyC, H, W, stride, taps[0], self.gview[wkey], wname)
                 off = 0
                 cin_sc = sum(s.C for s in srcs[1:])
                 for s_ in srcs[1:]:  # fused 1x1 shortcut over the raw block inputs: one slice of shortcut.weight per source
-                    tmp = torch.empty((dyC, s_.C), dtype=f32, device=device)
-                    wgrad(ap(s_), s_.C, dyp, dyC, H, W, 1, 1, tmp, p + ".shortcut")
-                    copy_op(self.gview[p + ".shortcut.weight"].view(dyC, cin_sc)[:, off: off + s_.C], tmp)
+                    wgrad(ap(s_), s_.C, dyp, dyC, H, W, 1, 1, self.gview[p + ".shortcut.weight"], p + ".shortcut",
+                          window=(dyC, s_.C, cin_sc, off))
                     off += s_.C
                 # --- input gradients
                 off = 0
@@ -348,9 +348,8 @@ class UNetTrainEngine:
                 h0 = o["out"]
                 dyp = dy_of(h0)
                 channel_sum(dyp, self.gview["input_conv.bias"], Hh * Ww, h0.C, 0)
-                tmpw = torch.empty((h0.C, 64, 3, 3), dtype=f32, device=device)
-                wgrad(self.xpad.data_ptr(), 64, dyp, h0.C, Hh, Ww, 1, 9, tmpw, "input_conv", real=net.in_channels * h0.C)
-                copy_op(self.gview["input_conv.weight"], tmpw[:, : net.in_channels])
+                wgrad(self.xpad.data_ptr(), 64, dyp, h0.C, Hh, Ww, 1, 9, self.gview["input_conv.weight"], "input_conv",
+                      real=net.in_channels * h0.C, window=(h0.C, net.in_channels, net.in_channels, 0))  # x is zero-padded 3 -> 64
 
         need = max(d.splits * d.Cout * d.taps * d.Cin for d in wg_descs)
         self.wg_partial = torch.empty(need, dtype=f32, device=device)

@@ -124,6 +124,10 @@ typedef struct {
   float* partial;   /* scratch, fp32 [splits, Cout, taps, Cin] */
   float* dw;        /* fp32 [Cout, Cin, kh, kw] (the reference's parameter layout) */
   int32_t accumulate; /* 1: dw += ..., 0: dw = ... */
+  /* optional window: dw is the parameter [dw_cout, dw_cin_total, kh, kw] and receives rows co < dw_cout, input channels
+   * ci < dw_cin at columns dw_ci0 + ci (zero-padded operands: stem Cin 3 -> 64, head Cout 3 -> 128; one source of a fused 1x1
+   * shortcut over concatenated inputs).  All zero = the whole [Cout, Cin, kh, kw] tensor. */
+  int32_t dw_cout, dw_cin, dw_cin_total, dw_ci0;
 } dmc_wgrad_desc;
 DMC_API int dmc_conv_wgrad_splits(const dmc_wgrad_desc* d);
 DMC_API int dmc_conv_wgrad(const dmc_wgrad_desc* d, void* stream);

@@ -325,3 +325,43 @@ def test_weight_pack_kernel_matches_torch_bit_for_bit():
     want_h = torch.zeros((128, 9, 128), device="cuda")
     want_h[:, :, :3] = head.flip(2, 3).permute(1, 2, 3, 0).reshape(128, 9, 3)
     assert torch.equal(dgh, want_h.reshape(128, -1).to(torch.bfloat16))
+
+
+def test_weight_gradient_written_into_a_window_of_the_parameter():
+    """zero-padded operands (head: 3 real output channels of 128) and one source of a fused 1x1 shortcut over concatenated inputs
+    write straight into the parameter's gradient instead of a staging tensor"""
+    lib = _lib.load()
+    B, H = 2, 16
+    x = _q(_rand((B, 128, H, H), 1))
+    dy = torch.zeros((B, 128, H, H), device="cuda")
+    dy[:, :3] = _q(_rand((B, 3, H, H), 2))
+    w = torch.zeros((3, 128, 3, 3), device="cuda", requires_grad=True)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, None, padding=1), w, dy[:, :3])
+    xs, dys = nhwc_bf16(x), nhwc_bf16(dy)
+    d = _lib.WgradDesc()
+    d.x, d.dy, d.B, d.Hin, d.Win, d.Cin, d.Cout, d.stride, d.taps = xs.data_ptr(), dys.data_ptr(), B, H, H, 128, 128, 1, 9
+    d.splits = _lib.check(lib.dmc_conv_wgrad_splits(C.byref(d)), "splits")
+    partial = torch.empty((d.splits, 128, 9, 128), device="cuda")
+    dw = torch.full((3, 128, 3, 3), float("nan"), device="cuda")
+    guard = torch.full((64,), 7.0, device="cuda")
+    d.partial, d.dw, d.accumulate = partial.data_ptr(), dw.data_ptr(), 0
+    d.dw_cout, d.dw_cin, d.dw_cin_total, d.dw_ci0 = 3, 128, 128, 0
+    _lib.check(lib.dmc_conv_wgrad(C.byref(d), _lib.stream_ptr()), "wgrad window")
+    torch.cuda.synchronize()
+    assert rel_l2(dw, ref) < 1e-5 and float(guard.min()) == 7.0
+    # 1x1 over the second of two concatenated sources: columns 256 .. 384 of a [128, 384, 1, 1] parameter
+    x2 = _q(_rand((B, 128, H, H), 3))
+    dy2 = _q(_rand((B, 128, H, H), 4))
+    w2 = torch.zeros((128, 128, 1, 1), device="cuda", requires_grad=True)
+    (ref2,) = torch.autograd.grad(F.conv2d(x2, w2), w2, dy2)
+    full = torch.full((128, 384, 1, 1), float("nan"), device="cuda")
+    x2s, dy2s = nhwc_bf16(x2), nhwc_bf16(dy2)
+    d2 = _lib.WgradDesc()
+    d2.x, d2.dy, d2.B, d2.Hin, d2.Win, d2.Cin, d2.Cout, d2.stride, d2.taps = x2s.data_ptr(), dy2s.data_ptr(), B, H, H, 128, 128, 1, 1
+    d2.splits = _lib.check(lib.dmc_conv_wgrad_splits(C.byref(d2)), "splits")
+    partial2 = torch.empty((d2.splits, 128, 1, 128), device="cuda")
+    d2.partial, d2.dw, d2.accumulate = partial2.data_ptr(), full.data_ptr(), 0
+    d2.dw_cout, d2.dw_cin, d2.dw_cin_total, d2.dw_ci0 = 128, 128, 384, 256
+    _lib.check(lib.dmc_conv_wgrad(C.byref(d2), _lib.stream_ptr()), "wgrad window 2")
+    torch.cuda.synchronize()
+    assert rel_l2(full[:, 256:], ref2) < 1e-5 and torch.isnan(full[:, :256]).all()
