@@ -2,7 +2,7 @@
 """Why final DDIM-50 images cannot pin an implementation when the weights are random-init (CPU, oracle only):
 the fp32 run with eps perturbed by a tiny relative amount per step ends far from the unperturbed run.
 
-    python tools/chaos_probe.py        # prints final max-abs / relative L2 for eps perturbations 1e-4, 1e-3, 6e-3
+    python tests/chaos_probe.py        # prints final max-abs / relative L2 for eps perturbations 1e-4, 1e-3, 6e-3
 Measured here: 1e-4 -> 1.74 / 0.46, 1e-3 -> 1.95 / 0.67, 6e-3 -> 1.99 / 0.91 (images clamp to [-1, 1])."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

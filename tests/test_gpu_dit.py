@@ -314,7 +314,7 @@ def test_dit_sampling_loops_graph_equals_launch_loop(kind):
 def test_dit_ddim50_teacher_forced_along_reference_trajectory(golden):
     """from the reference's own state before step s (fp32 CPU DDIM-50 run of the CIFAR DiT), one native step lands within
     8e-2 max-abs / 3e-2 relative L2 (measured: 9.3e-3 max-abs) of the reference's state after step s; the free-running final images are only recorded (random-init
-    weights make the sampler chaotic, see tests/test_gpu_unet.py and tools/chaos_probe.py)"""
+    weights make the sampler chaotic, see tests/test_gpu_unet.py and tests/chaos_probe.py)"""
     from diffusion_models_collection_b200.diffusion import DDIM
 
     g = golden["samples"]

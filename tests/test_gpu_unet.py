@@ -205,7 +205,7 @@ def test_full_size_batch_chunking_and_sharding_property():
 # ---- whole DDIM-50 runs vs the reference's own sample() / sample_with_cfg() (fp32 CPU, same x_T) ----------------------
 # With random-init weights the DDIM map is chaotic (1 / sqrt(alpha_bar_999) = 157 at the first steps, then a clamp): the
 # fp32 reference itself, with eps perturbed by 1e-4 relative per step, ends 1.74 max-abs / 0.46 relative L2 away from its
-# unperturbed run (tools/chaos_probe.py).  A bound on the FINAL images therefore says nothing about an implementation;
+# unperturbed run (tests/chaos_probe.py).  A bound on the FINAL images therefore says nothing about an implementation;
 # the meaningful end-to-end statement is teacher forcing along the reference's own trajectory: from the reference's
 # state before step s, one native step lands within TOL_STEP_MAXABS of the reference's state after step s, for early,
 # middle and last steps.  (The loop logic itself -- timestep order, coefficient rows, CFG, thresholding, the CUDA graph --

@@ -1,5 +1,5 @@
 """Per-parameter gradient error of the native UNet training step against autograd through the fp32 oracle (GPU box tool).
-   python tools/train_debug.py [B] [num_classes|none]"""
+   python tests/train_grad_report.py [B] [num_classes|none]"""
 import sys
 
 import torch
