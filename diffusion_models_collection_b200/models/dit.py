@@ -54,6 +54,13 @@ class DiT(nn.Module):
         self._packed_version = None
         self._init_parameters()
 
+    def __getstate__(self):
+        """copy.deepcopy(model) / torch.save(model): launch plans and packed operands are caches bound to native handles and
+        device pointers -- a copy starts without them and rebuilds them on its first forward"""
+        st = self.__dict__.copy()
+        st.update(_plans={}, _packed=None, _packed_version=None)
+        return st
+
     def _init_parameters(self):
         """models/dit.py:233-247: Xavier-uniform linears with zero bias, pos-emb N(0, 0.02^2), zero-init adaLN and
         final layer; conv patch embed and label table keep PyTorch defaults."""

@@ -387,6 +387,14 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------------------------------------
     # weight packing (one-time / on parameter change; plain torch ops -- not on the hot path)
     # ------------------------------------------------------------------------------------------------
+    def __getstate__(self):
+        """copy.deepcopy(model) / torch.save(model): the launch plans, training engines and packed operands are caches bound to
+        native handles and device pointers -- a copy starts without them and rebuilds them on its first forward"""
+        st = self.__dict__.copy()
+        st.update(_plans={}, _train_engines={}, _plist=None, _packed=None, _packed_version=None, _packed_ids=None,
+                  _grad_allreduce=None)
+        return st
+
     def parameters(self, recurse: bool = True):
         """nn.Module.parameters() walks the module tree (one small container per dotted-name component: ~1.5 ms for the 357
         tensors); the trainer calls it several times per step (optimizer, clip_grad_norm_), so the flat list is cached."""

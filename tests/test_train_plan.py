@@ -169,3 +169,28 @@ def test_native_gradient_allreduce_world_2_gloo():
         mp.spawn(_native_allreduce_worker, args=(world, 29655, out), nprocs=world, join=True)
         assert all(out[r][0] for r in range(world))
         assert torch.equal(out[0][1], out[1][1])  # parameters were broadcast from rank 0
+
+
+def test_models_deepcopy_and_pickle_without_their_native_caches():
+    """EMA helpers deep-copy the model (torch.optim.swa_utils.AveragedModel does) and torch.save(model) pickles it: plans, engines
+    and packed operands hold native handles / device pointers and must not travel; the copy rebuilds them on its first forward"""
+    import copy
+    import io
+
+    from diffusion_models_collection_b200 import synth
+    from diffusion_models_collection_b200.models.dit import DiT
+
+    net = _net(10)
+    net._plans, net._packed = {"k": object()}, {"stale": 1}
+    twin = copy.deepcopy(net)
+    assert twin._plans == {} and twin._train_engines == {} and twin._packed is None and twin._plist is None
+    assert net._plans != {}  # the original keeps its caches
+    assert [k for k in twin.state_dict()] == [k for k in net.state_dict()]
+    assert all(torch.equal(a, b) and a is not b for a, b in zip(net.parameters(), twin.parameters()))
+    net._plans, net._packed = {}, None
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    assert len(torch.load(buf, weights_only=False).state_dict()) == 357
+    dit = DiT(**synth.CIFAR_DIT, num_classes=None)
+    assert copy.deepcopy(dit)._plans == {}
