@@ -17,6 +17,8 @@ for k in conv3x3 conv_kernel_variants conv_split fused_output_head conv1x1 short
 done
 run unet tests/test_gpu_unet.py
 run dit tests/test_gpu_dit.py
+run train_kernels tests/test_gpu_train.py
+run train_step tests/test_gpu_train_step.py
 if [ "$1" != "nobench" ]; then
   timeout 900 python bench.py --batch ${BENCH_BATCH:-1024} --steps 1 --warmup 3 --ops-out $OUT/ops.json > $OUT/bench.log 2>&1
   echo "bench exit $? :: $(tail -c 300 $OUT/bench.log)" >> $OUT/summary.txt
