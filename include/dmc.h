@@ -104,14 +104,18 @@ DMC_API int dmc_q_sample(const float* x0, const float* noise, const int64_t* t, 
                  const float* sqrt_1m_acp, float* x_t, int32_t B, int32_t n_per_sample, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Training step building blocks (the full step is not wired yet)
+ * Training step building blocks.  models/unet_train.py assembles them into the UNet training step:
+ * forward plan with kept activations, then per layer the entry points below, in reverse order of the forward ops.
  * ---------------------------------------------------------------------------------------------- */
 
 /* Weight gradient of a 3x3 (padding 1) or 1x1 convolution, the backward of nn.Conv2d w.r.t. its weight
  * (models/unet.py:37,54,58,81,82,106,116 under autograd):
  *   dw[co, ci, r, s] (+)= sum_{n,h,w} dy[n, h, w, co] * x[n, h*stride + r - pad, w*stride + s - pad, ci]
  * tcgen05 GEMM over K = output pixels with both operands MN-major straight from the NHWC tensors; the pixels are cut into
- * `splits` slices whose partial sums are added in index order (deterministic).
+ * `splits` slices whose partial sums are added in index order (deterministic).  Two kernels behind one entry point: stride 1,
+ * rows of 8..64 pixels, >= 64 pixels per image and Cin % 128 == 0 take the row-slab kernel (128 co x 128 ci x the three
+ * vertical taps of one column shift per CTA, one TMA box of BH + 2 rows for the three taps); everything else (4x4 maps,
+ * stride 2, Cin % 128 == 64) the 128 co x 64 ci x 5-tap kernel.
  * (The input gradient needs no new kernel: it is dmc_plan_add_conv over dy with the weights packed transposed and
  * tap-flipped.) */
 typedef struct {
