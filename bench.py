@@ -405,7 +405,13 @@ def run_train_workload(args, rank, local_rank, world):
         model = (torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb, gradient_as_bucket_view=bucket_view)
                  if world > 1 else net)
     ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
-    opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
+    fused_opt = os.environ.get("DMC_FUSED_OPT", "0") == "1"  # native clip + AdamW + EMA in two launches (optim.FusedAdamW)
+    if fused_opt:
+        from diffusion_models_collection_b200.optim import FusedAdamW
+
+        opt = FusedAdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, max_grad_norm=1.0, ema_params=ema, ema_decay=0.9999)
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4, fused=True)
     B = args.batch
     g = torch.Generator().manual_seed(42 + rank)
     nbuf = 4  # rotating host batches (the DataLoader's pinned buffers)
@@ -421,6 +427,10 @@ def run_train_workload(args, rank, local_rank, world):
         t = torch.randint(0, 1000, (B,), device=dev).long()
         loss = ddpm.p_losses(model, images, t, labels, loss_type="l2")
         loss.backward()
+        if fused_opt:
+            opt.step()
+            opt.zero_grad()
+            return loss.item() if read_loss else loss
         torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
         opt.step()
         opt.zero_grad()
@@ -484,6 +494,7 @@ def run_train_workload(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},
             "gpu_launches": int((info["forward_launches"] + info["backward_launches"]) * args.steps),
             "loss": loss_now, "host_enqueue_ms_per_step": host_ms}
+    line["config"]["optimizer"] = "FusedAdamW (native clip + AdamW + EMA)" if fused_opt else "torch fused AdamW + foreach clip / EMA"
     line["config"]["ddp_bucket_mb"] = bucket_mb if world > 1 else None
     line["config"]["ddp_gradient_as_bucket_view"] = bucket_view if world > 1 else None
     pk = peaks()

@@ -114,6 +114,19 @@ def pack_table(items, device):
     return host.to(device), len(items)
 
 
+class OptItem(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("n", C.c_int64)]
+
+
+class OptChunk(C.Structure):
+    _fields_ = [("item", C.c_int32), ("pad_", C.c_int32), ("start", C.c_int64)]
+
+
+class AdamWDesc(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("lr", "beta1", "beta2", "eps", "weight_decay", "bias_correction1", "bias_correction2",
+                                         "max_norm", "ema_decay")]
+
+
 class HeadDesc(C.Structure):
     _fields_ = [("src", vp), ("stats", vp), ("stats_slots", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("C", C.c_int32), ("Cout", C.c_int32), ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float),
@@ -158,6 +171,8 @@ SYMBOLS = {
     "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "dmc_dilate2x": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_pack_weights": (C.c_int, [vp, C.c_int32, vp]),
+    "dmc_opt_grad_norm": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp]),
+    "dmc_opt_adamw_step": (C.c_int, [vp, vp, C.c_int32, C.POINTER(AdamWDesc), vp, vp]),
     "dmc_add_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp]),
     "dmc_block_sum2x2": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dmc_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

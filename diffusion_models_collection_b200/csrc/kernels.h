@@ -55,6 +55,8 @@ int launch_dilate2x(const void* src, void* dst, int B, int h, int w, int C, cuda
 int launch_attention_backward_mma(const dmc_attn_bwd_desc& d, cudaStream_t st);
 int launch_pack_weights(const dmc_pack_item* items_dev, int n, cudaStream_t st);
 long long gn_backward_scratch_floats(const dmc_gn_bwd_desc& d);
+int launch_opt_grad_norm(const dmc_opt_item* items, const dmc_opt_chunk* chunks, int n_chunks, float* partial, float* norm, cudaStream_t st);
+int launch_opt_adamw(const dmc_opt_item* items, const dmc_opt_chunk* chunks, int n_chunks, const dmc_adamw_desc& h, const float* norm, cudaStream_t st);
 int launch_add_bf16(void* dst, const void* src, size_t n, int accumulate, cudaStream_t st);
 int launch_block_sum2x2(const void* dhigh, void* dlow, int B, int H, int W, int C, int accumulate, cudaStream_t st);
 int launch_nchw_to_nhwc_pad(const float* src, void* dst, int B, int Cs, int HW, int Cd, cudaStream_t st);

@@ -182,6 +182,15 @@ int64_t dmc_gn_backward_scratch(const dmc_gn_bwd_desc* d) {
   if (!d) return -1;
   return gn_backward_scratch_floats(*d);
 }
+int dmc_opt_grad_norm(const dmc_opt_item* items_dev, const dmc_opt_chunk* chunks_dev, int32_t n_chunks, float* partial_dev,
+                      float* norm_dev, void* stream) {
+  return launch_opt_grad_norm(items_dev, chunks_dev, n_chunks, partial_dev, norm_dev, static_cast<cudaStream_t>(stream));
+}
+int dmc_opt_adamw_step(const dmc_opt_item* items_dev, const dmc_opt_chunk* chunks_dev, int32_t n_chunks, const dmc_adamw_desc* h,
+                       const float* norm_dev, void* stream) {
+  DMC_REQUIRE(h != nullptr, "dmc_opt_adamw_step: null hyper-parameters");
+  return launch_opt_adamw(items_dev, chunks_dev, n_chunks, *h, norm_dev, static_cast<cudaStream_t>(stream));
+}
 int dmc_add_bf16(void* dst, const void* src, int64_t n, int32_t accumulate, void* stream) {
   DMC_REQUIRE(n > 0, "dmc_add_bf16: n=%lld", static_cast<long long>(n));
   return launch_add_bf16(dst, src, static_cast<size_t>(n), accumulate, static_cast<cudaStream_t>(stream));

@@ -208,6 +208,35 @@ DMC_API int dmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, in
 DMC_API int dmc_conv_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t Hin, int32_t Win,
                            int32_t Cin, int32_t Cout, int32_t stride, int32_t accumulate, void* stream);
 
+/* Multi-tensor optimizer step (utils/trainer.py:256-262: clip_grad_norm_(1.0), AdamW.step(), EMA update) for ALL parameters in two
+ * launches.  `items_dev` (one per tensor) and `chunks_dev` (one per 16384-element chunk of a tensor: the work list) live in
+ * DEVICE memory. */
+typedef struct {
+  float* p;        /* parameter */
+  const float* g;  /* its gradient */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  float* ema;      /* EMA copy of the parameter, or NULL */
+  int64_t n;       /* elements */
+} dmc_opt_item;
+typedef struct {
+  int32_t item;
+  int32_t pad_;
+  int64_t start;   /* first element of the chunk */
+} dmc_opt_chunk;
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias_correction1, bias_correction2; /* 1 - beta^step, computed by the host */
+  float max_norm;   /* > 0: gradients are scaled by min(1, max_norm / (norm + 1e-6)) as clip_grad_norm_ does; <= 0: no clipping */
+  float ema_decay;  /* > 0: ema = decay * ema + (1 - decay) * new parameter for items with an ema pointer */
+} dmc_adamw_desc;
+/* norm_dev[0] = l2 norm over all gradients; partial_dev: fp32 [n_chunks] scratch (chunk sums added in index order) */
+DMC_API int dmc_opt_grad_norm(const dmc_opt_item* items_dev, const dmc_opt_chunk* chunks_dev, int32_t n_chunks, float* partial_dev,
+                      float* norm_dev, void* stream);
+/* AdamW with decoupled weight decay (torch.optim.AdamW semantics) on the clipped gradient; norm_dev may be NULL when max_norm <= 0 */
+DMC_API int dmc_opt_adamw_step(const dmc_opt_item* items_dev, const dmc_opt_chunk* chunks_dev, int32_t n_chunks,
+                       const dmc_adamw_desc* h, const float* norm_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Denoiser forward as a "plan": an ordered list of kernel launches with all pointers, shapes and TMA
  * descriptors resolved once per (model, batch size, workspace).  One dmc_plan_run() == one

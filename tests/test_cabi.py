@@ -56,7 +56,7 @@ def test_struct_layouts_match_the_c_compiler():
         "dmc_cond_desc": _lib.CondDesc, "dmc_stem_desc": _lib.StemDesc, "dmc_gn_stats_desc": _lib.GnStatsDesc,
         "dmc_gn_apply_desc": _lib.GnApplyDesc, "dmc_conv_desc": _lib.ConvDesc, "dmc_attn_desc": _lib.AttnDesc,
         "dmc_upsample_desc": _lib.UpsampleDesc, "dmc_step_desc": _lib.StepDesc, "dmc_dit_cond_desc": _lib.DitCondDesc,
-        "dmc_patch_embed_desc": _lib.PatchEmbedDesc, "dmc_ln_mod_desc": _lib.LnModDesc, "dmc_head_desc": _lib.HeadDesc, "dmc_wgrad_desc": _lib.WgradDesc, "dmc_gn_bwd_desc": _lib.GnBwdDesc, "dmc_pack_item": _lib.PackItem,
+        "dmc_patch_embed_desc": _lib.PatchEmbedDesc, "dmc_ln_mod_desc": _lib.LnModDesc, "dmc_head_desc": _lib.HeadDesc, "dmc_wgrad_desc": _lib.WgradDesc, "dmc_gn_bwd_desc": _lib.GnBwdDesc, "dmc_pack_item": _lib.PackItem, "dmc_opt_item": _lib.OptItem, "dmc_opt_chunk": _lib.OptChunk, "dmc_adamw_desc": _lib.AdamWDesc,
         "dmc_attn_bwd_desc": _lib.AttnBwdDesc,
     }
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
