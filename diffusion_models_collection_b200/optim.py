@@ -31,6 +31,7 @@ class FusedAdamW(torch.optim.Optimizer):
                  ema_decay=0.9999):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("FusedAdamW: invalid hyper-parameter")
+        self._tables = None
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
         self.ema_decay = float(ema_decay)
@@ -79,6 +80,18 @@ class FusedAdamW(torch.optim.Optimizer):
                                partial=torch.empty(max(len(chunks), 1), dtype=torch.float32, device=device), group=g))
         self._tables = dict(device=device, groups=groups,
                             norms=torch.zeros(len(groups) + 1, dtype=torch.float32, device=device))
+
+    def load_state_dict(self, state_dict):
+        """(torch.optim.AdamW checkpoints load too: same state keys.)  Loaded moments are new tensors: rebuild the pointer tables."""
+        super().load_state_dict(state_dict)
+        for st in self.state.values():  # torch's fused AdamW keeps `step` on the device: ours is a host counter
+            if "step" in st:
+                st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32)
+        self._tables = None
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._tables = None
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -194,3 +194,31 @@ def test_models_deepcopy_and_pickle_without_their_native_caches():
     assert len(torch.load(buf, weights_only=False).state_dict()) == 357
     dit = DiT(**synth.CIFAR_DIT, num_classes=None)
     assert copy.deepcopy(dit)._plans == {}
+
+
+def test_fused_adamw_host_side_contract():
+    """FusedAdamW without a device: torch.optim.AdamW hyper-parameters / state keys, torch AdamW checkpoints load (and reset the
+    pointer tables), EMA pairing is checked, and step() refuses to run without the CUDA path"""
+    from diffusion_models_collection_b200.optim import FusedAdamW
+
+    ps = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 3))]
+    opt = FusedAdamW(ps, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    assert opt.param_groups[0]["betas"] == (0.9, 0.999) and opt.param_groups[0]["weight_decay"] == 0.1
+    ref_ps = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 3))]
+    ref = torch.optim.AdamW(ref_ps, lr=5e-4)
+    for p in ref_ps:
+        p.grad = torch.ones_like(p)
+    ref.step()
+    opt._tables = "stale"
+    opt.load_state_dict(ref.state_dict())
+    assert opt._tables is None and opt.param_groups[0]["lr"] == 5e-4
+    assert set(opt.state[ps[0]]) == {"step", "exp_avg", "exp_avg_sq"} and float(opt.state[ps[0]]["step"]) == 1.0
+    assert not opt.state[ps[0]]["step"].is_cuda
+    with pytest.raises(ValueError):
+        FusedAdamW(ps, ema_params=[torch.zeros(4)])
+    with pytest.raises(ValueError):
+        FusedAdamW(ps, lr=-1.0)
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    with pytest.raises(_lib.DmcError):
+        opt.step()
