@@ -492,7 +492,7 @@ def run_train_workload(args, rank, local_rank, world):
                        "l2": "activations + gradients of one step are > 10x the 126 MB L2", "dropout": 0.1},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},
-            "gpu_launches": int((info["forward_launches"] + info["backward_launches"]) * args.steps),
+            "gpu_launches": int((info["forward_launches"] + info["backward_launches"] + (3 if fused_opt else 0)) * args.steps),
             "loss": loss_now, "host_enqueue_ms_per_step": host_ms}
     line["config"]["optimizer"] = "FusedAdamW (native clip + AdamW + EMA)" if fused_opt else "torch fused AdamW + foreach clip / EMA"
     line["config"]["ddp_bucket_mb"] = bucket_mb if world > 1 else None
