@@ -18,6 +18,9 @@ Fixtures written:
                      and the DDIM timestep subsets
   steps_golden.npz   single p_sample calls (DDIM eta 0 / 0.5, last step, DDPM t>0 / t==0), q_sample
   loops_golden.npz   whole sample() / sample_with_cfg() runs with a toy denoiser and recorded noise
+  train_golden.npz   loss and parameter gradients of the reference's own DDPM.p_losses(UNet, ...) + backward() (eval mode: dropout
+                     off) for two small batches: per-tensor l2 norm and sum for all 357 / 334 tensors, every 1-D tensor in full,
+                     256 fixed entries of every larger tensor -- the pin of the training step (BASELINE configs[4])
   samples_golden.npz FINAL images of whole DDIM-50 runs of the REAL CIFAR UNet / DiT through the reference's own
                      sample() / sample_with_cfg() (fp32 CPU, x_T recorded): the end-to-end pin of BASELINE configs 1 / 3 / 4
 """
@@ -38,7 +41,8 @@ REF = os.environ.get("DMC_REFERENCE_DIR", "/root/reference")
 
 from diffusion_models_collection_b200 import synth  # noqa: E402
 from oracle.sched_oracle import toy_model  # noqa: E402
-from tests.golden_cases import DIT_CASES, UNET_CASES, SMALL_UNET, case_inputs  # noqa: E402
+from tests.golden_cases import (DIT_CASES, UNET_CASES, SMALL_UNET, TRAIN_CASES, case_inputs, perturbed_state_dict,  # noqa: E402
+                                sample_index, train_inputs)
 
 
 def _load(name, rel):
@@ -254,6 +258,34 @@ def gen_loops():
         except ValueError:
             pass
     np.savez_compressed(os.path.join(HERE, "loops_golden.npz"), **out)
+
+
+def gen_train():
+    out = {}
+    for name, c in TRAIN_CASES.items():
+        net = ref_unet.UNet(**synth.CIFAR_UNET, num_classes=c["num_classes"]).eval()
+        net.load_state_dict(perturbed_state_dict(c["num_classes"]), strict=True)
+        ddpm = ref_ddpm.DDPM(num_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", device="cpu")
+        x0, t, y, noise = train_inputs(c)
+        loss = ddpm.p_losses(net, x0, t, y, noise=noise, loss_type="l2")
+        loss.backward()
+        out[name + "/loss"] = np.float64(loss.item())
+        names, norms, sums = [], [], []
+        for k, p in net.named_parameters():
+            g = p.grad
+            names.append(k)
+            norms.append(float(g.double().norm()))
+            sums.append(float(g.double().sum()))
+            flat = g.reshape(-1)
+            if g.dim() == 1:
+                out[f"{name}/full/{k}"] = flat.numpy().copy()
+            else:
+                out[f"{name}/sample/{k}"] = flat[torch.from_numpy(sample_index(flat.numel()))].numpy().copy()
+        out[name + "/names"] = np.array(names)
+        out[name + "/norms"] = np.array(norms)
+        out[name + "/sums"] = np.array(sums)
+        print("train", name, "loss", loss.item(), "params", len(names), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
+    np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@ Inputs are regenerated from seeds with the CPU generator; weights come from synt
 
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 # a second, smaller geometry: exercises 64/128/192-channel layers and a 2-level UNet
@@ -38,3 +39,36 @@ def case_inputs(c):
     t = torch.tensor(c["t"], dtype=torch.long)
     y = None if c["y"] is None else torch.tensor(c["y"], dtype=torch.long)
     return x, t, y
+
+
+# ---- training step (BASELINE configs[4]): tests/golden/train_golden.npz -------------------------------------------
+TRAIN_CASES = {"cond_b3": dict(num_classes=10, B=3, seed=7), "uncond_b2": dict(num_classes=None, B=2, seed=8)}
+
+
+def train_inputs(c):
+    """inputs of one training iteration (utils/trainer.py:221-251): images in [-1, 1], labels already shifted (0 = null), t, noise"""
+    g = torch.Generator().manual_seed(c["seed"])
+    B = c["B"]
+    x0 = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
+    t = torch.randint(0, 1000, (B,), generator=g)
+    y = torch.randint(0, 11, (B,), generator=g) if c["num_classes"] else None
+    if y is not None:
+        y[0] = 0  # one null label: the padding row of label_embed must get no gradient
+    noise = torch.randn(B, 3, 32, 32, generator=g)
+    return x0, t, y, noise
+
+
+def sample_index(numel, k=256):
+    """fixed pseudo-random entries of a flattened tensor (a multiplicative walk: reproducible without a generator)"""
+    return (np.arange(k, dtype=np.int64) * 2654435761 + 12345) % numel
+
+
+def perturbed_state_dict(num_classes):
+    from diffusion_models_collection_b200 import synth
+
+    sd = synth.make_unet_state_dict(None, num_classes, seed=42)
+    g = torch.Generator().manual_seed(99)
+    for k, v in sd.items():  # GroupNorm affines / biases off their trivial initial values
+        if v.dim() == 1:
+            v.add_(0.05 * torch.randn(v.shape, generator=g))
+    return sd

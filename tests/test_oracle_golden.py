@@ -163,3 +163,38 @@ def test_oracle_whole_ddim50_run_matches_reference_samples(golden):
     img = so.ddim_sample(model, tb, ts, torch.from_numpy(g["unet.uncond.ddim50.xT"]))
     ref = torch.from_numpy(g["unet.uncond.ddim50"])
     assert float((img - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["cond_b3", "uncond_b2"])
+def test_oracle_training_gradients_match_the_reference(golden, name):
+    """BASELINE configs[4]: loss and parameter gradients of autograd through the oracle restatement == the reference's own
+    DDPM.p_losses(UNet, ...).backward() (train_golden.npz: per-tensor norm and sum for every tensor, every 1-D tensor in full, 256
+    fixed entries of each larger one).  Pins the oracle's BACKWARD too -- e.g. the null row of label_embed (padding_idx=0,
+    models/unet.py:183) receives no gradient."""
+    from tests.golden_cases import TRAIN_CASES, perturbed_state_dict, sample_index, train_inputs
+
+    c, g = TRAIN_CASES[name], golden["train"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in perturbed_state_dict(c["num_classes"]).items()}
+    x0, t, y, noise = train_inputs(c)
+    tb = so.make_tables()
+    eps = model_oracle.unet_forward.__wrapped__(sd, synth.CIFAR_UNET, so.q_sample(tb, x0, t, noise), t, y, c["num_classes"])
+    loss = torch.nn.functional.mse_loss(noise, eps)
+    assert abs(loss.item() - float(g[name + "/loss"])) < 2e-6
+    names = [str(n) for n in g[name + "/names"]]
+    assert names == list(sd)  # same tensors, same order as the reference's named_parameters()
+    grads = torch.autograd.grad(loss, [sd[n] for n in names])
+    norms, sums = g[name + "/norms"], g[name + "/sums"]
+    total = float(np.sqrt((norms ** 2).sum()))
+    for i, (n, gr) in enumerate(zip(names, grads)):
+        assert abs(float(gr.double().norm()) - norms[i]) <= 2e-5 * norms[i] + 1e-7 * total, n
+        assert abs(float(gr.double().sum()) - sums[i]) <= 1e-4 * norms[i] * gr.numel() ** 0.5 + 1e-9, n
+        flat = gr.reshape(-1)
+        if gr.dim() == 1:
+            assert rel_l2(flat, g[f"{name}/full/{n}"]) < 2e-5, n
+        else:
+            want = g[f"{name}/sample/{n}"]
+            got = flat[torch.from_numpy(sample_index(flat.numel()))]
+            assert float((got - torch.from_numpy(want)).abs().max()) <= 2e-5 * float(np.abs(want).max()) + 1e-6 * norms[i] / gr.numel() ** 0.5, n
+    if c["num_classes"]:
+        row0 = g[f"{name}/sample/label_embed.weight"]  # (sampled entries; the full check is on the oracle side)
+        assert float(grads[names.index("label_embed.weight")][0].abs().max()) == 0.0 and row0 is not None
