@@ -11,8 +11,10 @@ N ranks (contiguous slices, no data-path collective; one NCCL all-gather of the 
 DDIM-50 sampling of the global batch.  `value` is images/s with x_T and the labels already resident in HBM; `e2e` is the
 same call fed from pinned HOST buffers (labels + x_T) with the images read back to the host inside the timed region.
 
-`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port: /root/reference is Python
-and does not exist on the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the REFERENCE ITSELF on the host cores: its own `DDIM.sample_with_cfg(UNet, ...)`, imported from
+oracle/_ref (the reference's sources packed by oracle/make_ref.py; /root/reference does not exist on the GPU box), on a
+bounded sample of the same workload (`--ref-batch` images per step, all 50 DDIM steps, no extrapolation), plus BASELINE
+configs[0] verbatim (`cpu_baseline_config1`: uncond DDIM-50, batch 16, default init under seed 42).
 """
 
 from __future__ import annotations
@@ -91,55 +93,95 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline: the reference's algorithm (oracle port, fp32, all host threads) on a bounded sample
+# CPU baseline: the REFERENCE ITSELF (oracle/_ref: its own sources, packed by oracle/make_ref.py) on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_images_per_sec(batch=8, sub_steps=4, cfg_scale=3.0, repeats=1):
-    """images/s of DDIM-50 + CFG on the host: runs `sub_steps` of the 50 DDIM steps (2 forwards each) on `batch` images
-    and scales the time by 50 / sub_steps (every step costs the same)."""
+_REF = {}
+
+
+def _reference():
+    """the reference's own classes (oracle/ref_loader.py: /root/reference in the build container, the archive
+    oracle/_ref/reference_src.zip on the GPU box)"""
+    if not _REF:
+        from oracle import ref_loader
+
+        _REF.update(ref_loader.import_reference())
+    return _REF
+
+
+def _set_seed(seed):
+    # utils/helpers.py:12-19 of the reference (set_seed), minus the CUDA / cudnn lines that do nothing on the host
+    import random
+
+    import numpy as np
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def cpu_reference_config1():
+    """BASELINE.json configs[0] verbatim, through the reference's own code: set_seed(42); UNet(**cifar10_unet model_params,
+    num_classes=None) default init, eval; DDIM(1000, 50, 1e-4, 0.02, 'linear', eta=0).sample(model, (16, 3, 32, 32)) --
+    all 50 steps, fp32, every host thread.  No extrapolation."""
     from diffusion_models_collection_b200 import synth
-    from oracle import model_oracle, sched_oracle as so
 
+    ref = _reference()
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = synth.CIFAR_UNET
-    sd = synth.make_unet_state_dict(cfg, 10, seed=42)
-    tb = so.make_tables()
-    ts = so.ddim_timesteps(1000, 50)[:sub_steps + 1]
+    _set_seed(42)
+    net = ref["UNet"](**synth.CIFAR_UNET, num_classes=None).eval()
+    d = ref["DDIM"](1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        img = d.sample(net, (16, 3, 32, 32))
+    dt = time.perf_counter() - t0
+    assert tuple(img.shape) == (16, 3, 32, 32) and bool(torch.isfinite(img).all())
+    return {"value": 16 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference", "seconds": dt,
+            "sample": "BASELINE.json configs[0] verbatim: the reference's own DDIM(50 steps).sample(UNet uncond, default init "
+                      f"under seed 42, (16, 3, 32, 32)), fp32 on the host, all 50 steps, no extrapolation ({ref['kind']})"}
+
+
+_CFG_NET = {}
+
+
+def cpu_reference_images_per_sec(batch=4):
+    """images/s of THIS bench's workload (cond UNet, DDIM-50, CFG 3.0, dynamic threshold 0.995) through the reference's own
+    DDIM.sample_with_cfg on `batch` images: all 50 steps, two UNet forwards each, fp32, every host thread -- a bounded
+    sample of the 4096-image step (per-image cost does not depend on the batch), not an extrapolation over steps."""
+    from diffusion_models_collection_b200 import synth
+
+    ref = _reference()
+    torch.set_num_threads(os.cpu_count() or 1)
+    if "net" not in _CFG_NET:
+        net = ref["UNet"](**synth.CIFAR_UNET, num_classes=10)
+        net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))  # the native arm's weights
+        _CFG_NET["net"] = net.eval()
+        _CFG_NET["ddim"] = ref["DDIM"](1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
     g = torch.Generator().manual_seed(42)
-    x = torch.randn(batch, 3, 32, 32, generator=g)
     y = torch.randint(0, 10, (batch,), generator=g) + 1
-
-    def model(xx, t, yy):
-        return model_oracle.unet_forward(sd, cfg, xx, t, yy, num_classes=10)
-
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        img = x
-        for i in range(sub_steps):
-            t_, tn_ = torch.full((batch,), int(ts[i])), torch.full((batch,), int(ts[i + 1]))
-            eps = so.cfg_combine(model(img, t_, y), model(img, t_, torch.zeros_like(y)), cfg_scale)
-            x0 = so.dynamic_threshold(so.ddim_x0(tb, img, eps, t_), 0.995)
-            img = so.ddim_step(tb, img, eps, t_, tn_, clip_denoised=False, x0_pred=x0)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    full = best * 50.0 / sub_steps
-    return batch / full, {"value": batch / full, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                          "sample": f"{batch} images x {sub_steps} of 50 DDIM steps (2 UNet forwards each, CFG 3.0, "
-                                    f"dynamic threshold), fp32 oracle port on the host, time scaled by 50/{sub_steps}"}
+    torch.manual_seed(42)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        img = _CFG_NET["ddim"].sample_with_cfg(_CFG_NET["net"], (batch, 3, 32, 32), y, cfg_scale=3.0)
+    dt = time.perf_counter() - t0
+    assert tuple(img.shape) == (batch, 3, 32, 32) and bool(torch.isfinite(img).all())
+    return batch / dt, {"value": batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                        "sample": f"{batch} images of the 4096-image step through the reference's own DDIM.sample_with_cfg (all 50 "
+                                  f"steps, 2 UNet forwards each, CFG 3.0, dynamic threshold 0.995), fp32 on the host ({ref['kind']})"}
 
 
 def cpu_reference_train_images_per_sec(batch=8, steps=1):
-    """images/s of the reference's training step on the host: autograd through the fp32 oracle restatement of the UNet
-    (eps-MSE loss of q_sample'd images, backward, clip_grad_norm_ 1.0, AdamW) on `batch` images, all host threads."""
+    """images/s of the reference's training step on the host through its OWN code: DDPM.p_losses(UNet cond, train mode, l2) ->
+    backward -> clip_grad_norm_(1.0) -> AdamW(lr 2e-4, wd 1e-4) (utils/trainer.py:221-262) on `batch` images, every host thread."""
     from diffusion_models_collection_b200 import synth
-    from oracle import model_oracle, sched_oracle as so
 
+    ref = _reference()
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = synth.CIFAR_UNET
-    sd = {k: v.clone().requires_grad_(True) for k, v in synth.make_unet_state_dict(cfg, 10, seed=42).items()}
-    params = list(sd.values())
-    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=1e-4)
-    tb = so.make_tables()
+    torch.manual_seed(42)
+    net = ref["UNet"](**synth.CIFAR_UNET, num_classes=10)
+    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    net.train()
+    ddpm = ref["DDPM"](1000, 1e-4, 0.02, "linear", device="cpu")
+    opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4)
     g = torch.Generator().manual_seed(42)
     x0 = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
     y = torch.randint(0, 10, (batch,), generator=g) + 1
@@ -147,18 +189,16 @@ def cpu_reference_train_images_per_sec(batch=8, steps=1):
     for _ in range(steps):
         t0 = time.perf_counter()
         t = torch.randint(0, 1000, (batch,), generator=g)
-        noise = torch.randn(batch, 3, 32, 32, generator=g)
-        eps = model_oracle.unet_forward.__wrapped__(sd, cfg, so.q_sample(tb, x0, t, noise), t, y, 10)
-        loss = torch.nn.functional.mse_loss(noise, eps)
+        loss = ddpm.p_losses(net, x0, t, y, loss_type="l2")
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
         opt.step()
         opt.zero_grad()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return batch / best, {"value": batch / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                          "sample": f"{steps} training step(s) of {batch} images (q_sample, UNet forward + autograd backward through the "
-                                    "fp32 oracle port, clip_grad_norm_, AdamW) on the host"}
+    return batch / best, {"value": batch / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                          "sample": f"{steps} training step(s) of {batch} images through the reference's own DDPM.p_losses + "
+                                    f"backward + clip_grad_norm_ + AdamW, fp32 on the host ({ref['kind']})"}
 
 
 def run_reference_arm(args, rank):
@@ -168,31 +208,34 @@ def run_reference_arm(args, rank):
         for _ in range(min(args.warmup, 1)):
             cpu_reference_train_images_per_sec(batch=2, steps=1)
         t0 = time.perf_counter()
-        v, cb = cpu_reference_train_images_per_sec(batch=args.ref_batch, steps=args.steps)
+        v, cb = cpu_reference_train_images_per_sec(batch=args.ref_batch * 2, steps=args.steps)
         wall = time.perf_counter() - t0
         print(json.dumps({"impl": "reference", "metric": "train_unet_cifar10_images_per_sec", "value": v, "unit": UNIT,
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "UNet cond CIFAR-10 training step (BASELINE.json configs[4]), reference algorithm on "
-                                                 "the host cores", "per_gpu_batch": args.ref_batch},
+                          "config": {"workload": "UNet cond CIFAR-10 training step (BASELINE.json configs[4]), the reference's own "
+                                                 "code on the host cores", "per_gpu_batch": args.ref_batch * 2},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
         return
+    # every step = the reference's own DDIM-50 + CFG sampler on `ref_batch` images of the 4096-image step (all 50 denoising steps)
     for _ in range(args.warmup):
-        cpu_reference_images_per_sec(batch=2, sub_steps=1)
-    vals, cb = [], None
+        cpu_reference_images_per_sec(batch=args.ref_batch)
+    cb = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
-        vals.append(v)
+        _, cb = cpu_reference_images_per_sec(batch=args.ref_batch)
     wall = time.perf_counter() - t0
-    v = sum(vals) / len(vals)
+    v = args.ref_batch * args.steps / wall
     cb["value"] = v
+    shard = (args.batch + args.gpus - 1) // args.gpus
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 0),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, shard),
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline_config1"] = cpu_reference_config1()
     print(json.dumps(line), flush=True)
 
 
@@ -218,8 +261,8 @@ def main():
     ap.add_argument("--model", default="unet", choices=["unet", "dit"],
                     help="unet: BASELINE configs[2] (the bench line); dit: configs[3] (DiT patch-2 DDIM-50 uncond, --batch 1024), "
                          "a side measurement, not the headline")
-    ap.add_argument("--ref-batch", type=int, default=8)
-    ap.add_argument("--ref-sub-steps", type=int, default=4)
+    ap.add_argument("--ref-batch", type=int, default=4,
+                    help="images per step of the CPU reference legs (every step runs all 50 DDIM steps on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-op timing table (JSON) here")
@@ -366,8 +409,11 @@ def main():
         line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out, cfg=not uncond, step_ms=ms / args.steps / sampler_steps,
                                         chunks=-(-nb // max(1, net.max_images_per_launch // (1 if uncond else 2))))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, cb = cpu_reference_images_per_sec(batch=args.ref_batch, sub_steps=args.ref_sub_steps)
+        # the reference itself on the host cores: this workload on a bounded sample, and BASELINE configs[0] verbatim
+        _, cb = cpu_reference_images_per_sec(batch=2 * args.ref_batch)
         line["cpu_baseline"] = cb
+        if not is_dit and not is_ddpm:
+            line["cpu_baseline_config1"] = cpu_reference_config1()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -514,7 +560,7 @@ def run_train_workload(args, rank, local_rank, world):
                             "tensor_ms": tms, "all_ops_ms": sum(o["ms"] for o in ops), "step_ms": ms / args.steps,
                             "by_kind_ms": {k: sum(o["ms"] for o in ops if o["kind"] == k) for k in sorted({o["kind"] for o in ops})}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, line["cpu_baseline"] = cpu_reference_train_images_per_sec(batch=args.ref_batch, steps=2)
+        _, line["cpu_baseline"] = cpu_reference_train_images_per_sec(batch=2 * args.ref_batch, steps=2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -258,10 +258,11 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 }
 
 int launch_attention_backward_mma(const dmc_attn_bwd_desc& d, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  int attr_dev = 0;
+  if (attr.need(&attr_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(AB_SMEM)));
-    attr = true;
+    attr.done(attr_dev);
   }
   attention_bwd_mma_kernel<<<d.B * d.heads, AB_THREADS, AB_SMEM, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(d.qkv), reinterpret_cast<const __nv_bfloat16*>(d.out),

@@ -639,15 +639,16 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
 void attention_release(AttnPrepared* p) { delete p; }
 
 int launch_attention_umma(const AttnPrepared* P, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev = 0;
+  if (attr_set.need(&attr_set_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
-    attr_set = true;
+    attr_set.done(attr_set_dev);
   }
   if (P->p.L > AT_MAXKEYS) {
     attention_long_kernel<<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace dmc {
 
 // ---------------------------------------------------------------------------------------------
@@ -33,6 +35,20 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+
+// One-time, PER-DEVICE initialisation flag (e.g. cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-device
+// function attribute): `need()` is true until `done()` has been called on the current device.  Lock-free; two host threads
+// racing both run the (idempotent) initialisation, and a second device of the same process is never skipped.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask[4] = {};
+  bool need(int* dev_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    *dev_out = dev;
+    return (mask[(dev >> 6) & 3].load(std::memory_order_acquire) & (1ull << (dev & 63))) == 0;
+  }
+  void done(int dev) { mask[(dev >> 6) & 3].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // small device utilities

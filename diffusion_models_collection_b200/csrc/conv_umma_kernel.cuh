@@ -714,10 +714,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <int BN, int MT, int CG, int VAR>
 static int launch_variant(const ConvPrepared* P, const ConvKParams& kp, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // the opt-in shared-memory limit is a per-device function attribute
+  int attr_dev = 0;
+  if (attr_set.need(&attr_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MT, CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_set.done(attr_dev);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

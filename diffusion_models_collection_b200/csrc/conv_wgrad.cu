@@ -409,10 +409,11 @@ static int launch_conv_wgrad_slab(const dmc_wgrad_desc& d, cudaStream_t st) {
   CUtensorMap tmX, tmDY;
   if (encode4d(&tmX, d.x, d.Cin, W, H, d.B, W, p.BH + 2 * p.halo, 1, 1) != 0) return -1;
   if (encode4d(&tmDY, d.dy, d.Cout, W, H, d.B, W, p.BH, 1, 1) != 0) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev = 0;
+  if (attr_set.need(&attr_set_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT));
-    attr_set = true;
+    attr_set.done(attr_set_dev);
   }
   const int grid = (d.Cout / 128) * (d.Cin / 128) * p.ndw * p.splits;
   const size_t smem = static_cast<size_t>(p.nst) * p.stage_bytes + 1024 + 256;
@@ -463,10 +464,11 @@ int launch_conv_wgrad(const dmc_wgrad_desc& d, cudaStream_t st) {
   CUtensorMap tmX, tmDY;
   if (encode4d(&tmX, d.x, d.Cin, d.Win, d.Hin, d.B, BW, BH, BNIMG, d.stride) != 0) return -1;
   if (encode4d(&tmDY, d.dy, d.Cout, Wo, Ho, d.B, BW, BH, BNIMG, 1) != 0) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev = 0;
+  if (attr_set.need(&attr_set_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT));
-    attr_set = true;
+    attr_set.done(attr_set_dev);
   }
   const int grid = (d.Cout / 128) * (d.Cin / 64) * p.tap_groups * p.splits;
   const size_t smem = static_cast<size_t>(p.nst) * p.stage_bytes + 1024 + 256;

@@ -693,10 +693,11 @@ bool head_fused_supported(const dmc_head_desc& d) {
 
 template <int C, int W>
 static int launch_head_t(const HeadArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev = 0;
+  if (attr_set.need(&attr_set_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(head_fused_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_set = true;
+    attr_set.done(attr_set_dev);
   }
   head_fused_kernel<C, W><<<grid, HEAD_THREADS, smem, st>>>(a);
   return 0;

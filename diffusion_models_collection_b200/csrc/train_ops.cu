@@ -491,10 +491,11 @@ int launch_attention_backward(const dmc_attn_bwd_desc& d, cudaStream_t st) {
     if (!(e && e[0] == '1')) return launch_attention_backward_mma(d, st);
   }
   const size_t smem = static_cast<size_t>(4) * d.L * hd * 2 + static_cast<size_t>(3) * d.L * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  int attr_dev = 0;
+  if (attr.need(&attr_dev)) {
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
+    attr.done(attr_dev);
   }
   const int threads = d.L >= 256 ? 256 : (d.L >= 128 ? 128 : 64);
   attention_bwd_kernel<64><<<dim3(d.heads, d.B), threads, smem, st>>>(

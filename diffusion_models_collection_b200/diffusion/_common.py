@@ -136,8 +136,16 @@ class DiffusionBase:
         B = img.shape[0]
         n = img.numel() // B
         S = int(t_seq.numel())
-        packed = getattr(model, "_packed", None)
-        key = (id(model), bool(ddpm), bool(cfg), tuple(img.shape), y is not None, float(g.cfg_scale), int(g.clip_mode),
+        # Refresh the packed bf16 operands BEFORE the cache lookup: a replay runs no Python of the model, so weights changed
+        # in place since the capture (optimizer step, EMA update, load_state_dict) would otherwise never be re-packed and
+        # the graph would keep sampling from the weights of the first call.  The full (non-training) refresh also rebuilds
+        # the Upsample phase weights a training step skips.  In-place re-packs keep plans and graphs valid; a storage
+        # change replaces model._packed and invalidates the entry below.
+        ensure = getattr(model, "_ensure_packed", None)
+        if callable(ensure):
+            with torch.cuda.device(img.device):
+                ensure(img.device)
+        key = (self._model_token(model), bool(ddpm), bool(cfg), tuple(img.shape), y is not None, float(g.cfg_scale), int(g.clip_mode),
                int(g.q_lo), int(g.q_hi), float(g.q_weight), bool(draw_noise), S, id(coef_seq), id(t_seq), str(img.device),
                self._noise_shard)
         ent = getattr(self, "_graph_cache", None)
@@ -184,6 +192,19 @@ class DiffusionBase:
         for _ in self._bar(range(S), desc, S):
             ent["graph"].replay()
         return ent["x"].clone()
+
+    @staticmethod
+    def _model_token(model):
+        """identity of a denoiser for the graph cache: a token object the model owns (created on first use and dropped with
+        the model), not id(model) -- CPython reuses ids after garbage collection, which could replay a stale graph"""
+        tok = getattr(model, "_dmc_graph_token", None)
+        if tok is None:
+            tok = object()
+            try:
+                object.__setattr__(model, "_dmc_graph_token", tok)
+            except Exception:  # a callable without a __dict__: fall back to the object itself (kept alive by the cache key)
+                return model
+        return tok
 
     @staticmethod
     def _uniform_t(model):

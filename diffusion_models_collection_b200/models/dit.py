@@ -58,7 +58,7 @@ class DiT(nn.Module):
         """copy.deepcopy(model) / torch.save(model): launch plans and packed operands are caches bound to native handles and
         device pointers -- a copy starts without them and rebuilds them on its first forward"""
         st = self.__dict__.copy()
-        st.update(_plans={}, _packed=None, _packed_version=None)
+        st.update(_plans={}, _packed=None, _packed_version=None, _dmc_graph_token=None)
         return st
 
     def _init_parameters(self):

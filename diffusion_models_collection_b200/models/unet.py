@@ -392,7 +392,7 @@ class UNet(nn.Module):
         native handles and device pointers -- a copy starts without them and rebuilds them on its first forward"""
         st = self.__dict__.copy()
         st.update(_plans={}, _train_engines={}, _plist=None, _packed=None, _packed_version=None, _packed_ids=None,
-                  _grad_allreduce=None)
+                  _grad_allreduce=None, _dmc_graph_token=None)
         return st
 
     def parameters(self, recurse: bool = True):
@@ -758,7 +758,9 @@ class UNet(nn.Module):
         if broadcast_parameters:  # what DDP does when it wraps the model: rank 0's parameters everywhere
             with torch.no_grad():
                 for p in self.parameters():
-                    dist.broadcast(p.data, src=dist.get_global_rank(group, 0), group=group)
+                    # p.detach() shares the version counter with p (p.data does not): ranks that packed their bf16
+                    # operands before the broadcast re-pack them on the next forward
+                    dist.broadcast(p.detach(), src=dist.get_global_rank(group, 0), group=group)
         self._grad_allreduce = group
         return self
 

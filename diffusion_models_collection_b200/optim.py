@@ -152,4 +152,16 @@ class FusedAdamW(torch.optim.Optimizer):
                 h.ema_decay = self.ema_decay if self._ema is not None else 0.0
                 _lib.check(lib.dmc_opt_adamw_step(t["items_dev"].data_ptr(), t["chunks_dev"].data_ptr(), t["n_chunks"], C.byref(h),
                                                   self.last_grad_norm.data_ptr() if clip else None, st_ptr), "dmc_opt_adamw_step")
+                # The kernel wrote the parameters (and EMA tensors) through raw device pointers, which autograd's version
+                # counters do not see.  The native UNet / DiT re-pack their bf16 GEMM operands when a parameter version
+                # changes (models/unet.py:_ensure_packed), so every tensor the launch touched is bumped here -- without it the
+                # forward would keep training on the weights packed before the first step.
+                touched = [p for p in t["params"] if p.grad is not None]
+                torch.autograd.graph.increment_version(touched)
+                if self._ema is not None:
+                    ema_of = t.get("ema_list")
+                    if ema_of is None:
+                        pairs = dict(zip([id(p) for g_ in self.param_groups for p in g_["params"]], self._ema))
+                        ema_of = t["ema_list"] = {id(p): pairs[id(p)] for p in t["params"] if id(p) in pairs}
+                    torch.autograd.graph.increment_version([ema_of[id(p)] for p in touched if id(p) in ema_of])
         return loss

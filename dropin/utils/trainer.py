@@ -10,8 +10,7 @@ import sys
 
 
 def _reference_dir():
-    cands = [os.environ.get("DMC_REFERENCE_DIR"), os.path.dirname(os.path.abspath(sys.argv[0])) if sys.argv and sys.argv[0] else None,
-             "/root/reference"]
+    cands = [os.environ.get("DMC_REFERENCE_DIR"), os.path.dirname(os.path.abspath(sys.argv[0])) if sys.argv and sys.argv[0] else None]
     for c in cands:
         if c and os.path.exists(os.path.join(c, "utils", "trainer.py")):
             return c

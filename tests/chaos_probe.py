@@ -1,33 +1,67 @@
 #!/usr/bin/env python
-"""Why final DDIM-50 images cannot pin an implementation when the weights are random-init (CPU, oracle only):
-the fp32 run with eps perturbed by a tiny relative amount per step ends far from the unperturbed run.
+"""How sensitive is a whole DDIM-50 run of a RANDOM-INIT UNet to the per-step eps error?  (CPU, the reference itself via
+oracle/ref_loader.py; ~1 minute.)  This settles the disagreement between SURVEY.md A.8 ("linear gain ~130x: 1e-5 -> 1.3e-3,
+1e-4 -> 1.3e-2 final max-abs") and the round-1 probe ("1e-4 -> 1.74"):
 
-    python tests/chaos_probe.py        # prints final max-abs / relative L2 for eps perturbations 1e-4, 1e-3, 6e-3
-Measured here: 1e-4 -> 1.74 / 0.46, 1e-3 -> 1.95 / 0.67, 6e-3 -> 1.99 / 0.91 (images clamp to [-1, 1])."""
-import os, sys
+    python tests/chaos_probe.py
+
+Every step the reference's eps gets i.i.d. Gaussian noise of relative L2 norm r; the final images are compared with the
+unperturbed run from the same x_T (B = 4).  Measured here (build container, torch 2.11 CPU fp32):
+
+    weights                                   r = 1e-5         1e-4           1e-3        (final max-abs / relative L2)
+    default init under seed 42 (configs[0])   1.94 / 0.59      2.00 / 0.76    1.98 / 1.00
+    synth.make_unet_state_dict(seed 42)       1.67 / 0.29      1.82 / 0.48    1.98 / 0.69
+
+i.e. with random-init weights the map x_T -> x_0 is chaotic for BOTH weight sets: the first steps divide by
+sqrt(alpha_bar_999) = 1/157 and clamp, and an eps perturbation of 1e-5 already moves single pixels across the whole [-1, 1]
+range after 50 steps.  SURVEY A.8's linear-gain table is not reproducible with the reference (no seed / weight set we tried
+shows it); consequence: a max-abs bound on FINAL free-running images cannot separate a correct implementation from a wrong one,
+in any precision mode -- fp32 on a machine with a different BLAS blocking already differs by O(1).  The tests therefore bound
+(a) every step teacher-forced along the reference's trajectory and (b) the free-running deviation after 1, 2, 3, 5, 10, 20 steps
+(tests/test_gpu_config1.py), where the growth is still below saturation, and only RECORD the deviation at step 50."""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
-import torch
-from diffusion_models_collection_b200 import synth
-from oracle import model_oracle, sched_oracle as so
+import torch  # noqa: E402
 
-g = np.load(os.path.join(ROOT, "tests", "golden", "samples_golden.npz"))
-sd = synth.make_unet_state_dict(None, None, seed=42)
-tb, ts = so.make_tables(), so.ddim_timesteps(1000, 50)
-xT, ref = torch.from_numpy(g["unet.uncond.ddim50.xT"]), torch.from_numpy(g["unet.uncond.ddim50"])
+from diffusion_models_collection_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
 
 
-def perturbed(rel):
-    def model(x, t, y=None):
-        e = model_oracle.unet_forward(sd, synth.CIFAR_UNET, x, t, y, num_classes=None)
-        n = torch.randn_like(e)
-        return e + rel * e.norm() / n.norm() * n
-    return model
+def run(ref, kind, B=4):
+    torch.manual_seed(42)
+    net = ref["UNet"](**synth.CIFAR_UNET, num_classes=None).eval()
+    if kind == "synth":
+        net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42))
+    d = ref["DDIM"](1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
+    xT = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    ts = d.inference_timesteps.tolist()
+
+    def sample(rel):
+        gen = torch.Generator().manual_seed(0)
+        x = xT.clone()
+        with torch.no_grad():
+            for i, t in enumerate(ts):
+                tb = torch.full((B,), t, dtype=torch.long)
+                tn = torch.full((B,), ts[i + 1] if i + 1 < len(ts) else -1, dtype=torch.long)
+                e = net(x, tb)
+                if rel:
+                    n = torch.randn(e.shape, generator=gen)
+                    e = e + rel * e.norm() / n.norm() * n
+                x = d.p_sample(net, x, tb, tn, eps=e)
+        return x
+
+    base = sample(0.0)
+    for rel in (1e-5, 1e-4, 1e-3):
+        img = sample(rel)
+        print(f"{kind:8s} eps perturbation {rel:g}: final max-abs {float((img - base).abs().max()):.3f}, "
+              f"relative L2 {float((img - base).norm() / base.norm()):.3f}", flush=True)
 
 
-torch.manual_seed(0)
-for rel in (1e-4, 1e-3, 6e-3):
-    img = so.ddim_sample(perturbed(rel), tb, ts, xT)
-    print(f"eps perturbation {rel:g}: final max-abs {float((img - ref).abs().max()):.3f}, "
-          f"relative L2 {float((img - ref).norm() / ref.norm()):.3f}")
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = ref_loader.import_reference()
+    for k in (sys.argv[1:] or ["default", "synth"]):
+        run(r, k)

@@ -21,6 +21,8 @@ Fixtures written:
   train_golden.npz   loss and parameter gradients of the reference's own DDPM.p_losses(UNet, ...) + backward() (eval mode: dropout
                      off) for two small batches: per-tensor l2 norm and sum for all 357 / 334 tensors, every 1-D tensor in full,
                      256 fixed entries of every larger tensor -- the pin of the training step (BASELINE configs[4])
+  config1_golden.npz BASELINE configs[0] verbatim (default init under seed 42, uncond DDIM-50, batch 16): x_T, the reference's
+                     state after 1 / 2 / 3 / 5 / 10 / 20 / 50 free-running steps, its first eps (a B = 16 whole-model golden)
   samples_golden.npz FINAL images of whole DDIM-50 runs of the REAL CIFAR UNet / DiT through the reference's own
                      sample() / sample_with_cfg() (fp32 CPU, x_T recorded): the end-to-end pin of BASELINE configs 1 / 3 / 4
 """
@@ -286,6 +288,40 @@ def gen_train():
         out[name + "/sums"] = np.array(sums)
         print("train", name, "loss", loss.item(), "params", len(names), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
     np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
+
+
+CONFIG1_HORIZONS = [1, 2, 3, 5, 10, 20, 50]  # states after this many free-running DDIM steps
+
+
+def gen_config1():
+    """BASELINE.json configs[0] VERBATIM through the reference: set_seed(42) (sample.py:90), UNet(**cifar10_unet model_params,
+    num_classes=None) with PyTorch's default init, DDIM(1000, 50, 1e-4, 0.02, 'linear', eta=0).sample(model, (16, 3, 32, 32)).
+    Stored: x_T, the reference's state after CONFIG1_HORIZONS free-running steps (the last one = the final images), its eps for
+    the first forward (a B = 16 whole-model golden), and per-tensor checksums of the default-init weights so that a test can prove
+    it rebuilt the same weights from the reference's constructor on another machine."""
+    import contextlib
+    import io
+    import random
+
+    random.seed(42)
+    np.random.seed(42)
+    torch.manual_seed(42)
+    net = ref_unet.UNet(**synth.CIFAR_UNET, num_classes=None).eval()
+    d50 = ref_ddim.DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
+    with NoiseRecorder() as rec, contextlib.redirect_stderr(io.StringIO()), torch.no_grad():
+        traj = d50.sample(net, (16, 3, 32, 32), return_all_timesteps=True)
+    xT = rec.draws[0]
+    out = {"xT": xT.numpy(), "horizons": np.array(CONFIG1_HORIZONS)}
+    for h in CONFIG1_HORIZONS:
+        out[f"after{h}"] = traj[h - 1].numpy()
+    with torch.no_grad():
+        out["eps0"] = net(xT, torch.full((16,), 999, dtype=torch.long)).numpy()
+    names = [k for k, _ in net.state_dict().items()]
+    out["weight_names"] = np.array(names)
+    out["weight_sums"] = np.array([float(v.double().sum()) for v in net.state_dict().values()])
+    out["weight_abs_sums"] = np.array([float(v.double().abs().sum()) for v in net.state_dict().values()])
+    np.savez_compressed(os.path.join(HERE, "config1_golden.npz"), **out)
+    print("config1", tuple(traj.shape), float(traj[-1].abs().max()), float(traj[-1].std()), "eps0 std", float(out["eps0"].std()))
 
 
 if __name__ == "__main__":

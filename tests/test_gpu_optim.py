@@ -61,3 +61,73 @@ def test_fused_adamw_refuses_cpu_tensors():
     p.grad = torch.ones(4)
     with pytest.raises(_lib.DmcError):
         FusedAdamW([p]).step()
+
+
+def test_fused_adamw_steps_reach_the_native_unet_forward():
+    """FusedAdamW writes parameters through raw device pointers; the native UNet re-packs its bf16 GEMM operands when a
+    parameter VERSION changes -- so the optimizer must bump the versions, or the forward keeps training on the weights packed
+    before the first step (round-1 advisor finding).  Three steps of UNet + FusedAdamW against UNet + clip_grad_norm_ +
+    torch.optim.AdamW + the trainer's EMA loop on the same batches: same losses, same weights, and the packed bf16 weights
+    follow the fp32 masters."""
+    from diffusion_models_collection_b200.diffusion import DDPM
+    from diffusion_models_collection_b200.models import UNet
+    from tests.golden_cases import SMALL_UNET
+
+    def make():
+        net = UNet(**SMALL_UNET, num_classes=10, )
+        net.load_state_dict(synth.make_unet_state_dict(SMALL_UNET, 10, seed=4))
+        net.dropout = 0.0
+        return net.cuda().train()
+
+    from diffusion_models_collection_b200 import synth
+
+    a, b = make(), make()
+    ema_a = [p.detach().clone() for p in a.parameters()]
+    ema_b = [p.detach().clone() for p in b.parameters()]
+    opt_a = FusedAdamW(a.parameters(), lr=1e-2, weight_decay=1e-4, max_grad_norm=1.0, ema_params=ema_a, ema_decay=0.9)
+    opt_b = torch.optim.AdamW(b.parameters(), lr=1e-2, weight_decay=1e-4)
+    ddpm = DDPM(1000, device=torch.device("cuda"))
+    g = torch.Generator().manual_seed(5)
+    losses = []
+    for step in range(3):
+        x0 = (torch.rand(8, 3, 32, 32, generator=g) * 2 - 1).cuda()
+        t = torch.randint(0, 1000, (8,), generator=g).cuda()
+        y = torch.randint(0, 11, (8,), generator=g).cuda()
+        nz = torch.randn(8, 3, 32, 32, generator=g).cuda()
+        ver_before = [p._version for p in a.parameters()]
+        la = ddpm.p_losses(a, x0, t, y, noise=nz)
+        la.backward()
+        opt_a.step()
+        opt_a.zero_grad()
+        lb = ddpm.p_losses(b, x0, t, y, noise=nz)
+        lb.backward()
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt_b.step()
+        opt_b.zero_grad()
+        for e, q in zip(ema_b, b.parameters()):
+            e.mul_(0.9).add_(q.detach(), alpha=0.1)
+        assert all(p._version > v for p, v in zip(a.parameters(), ver_before))
+        losses.append((float(la), float(lb)))
+    # lr 1e-2 moves the weights far: a forward that ignored the updates would show the step-0 loss three times
+    assert abs(losses[0][0] - losses[0][1]) < 1e-6
+    assert abs(losses[2][0] - losses[0][0]) > 1e-3
+    for la, lb in losses:
+        assert abs(la - lb) <= 2e-2 * abs(lb), losses
+    # (two bf16 pipelines fed weights that differ in the last fp32 bits: AdamW's m / sqrt(v) amplifies that for near-zero
+    # gradients, hence the loose element-wise bound; 3 steps at lr 1e-2 move every weight by up to 3e-2)
+    num = sum(float((p - q).pow(2).sum()) for p, q in zip(a.parameters(), b.parameters()))
+    den = sum(float((q - r).pow(2).sum()) for q, r in zip(b.parameters(), make().parameters()))
+    assert num < 1e-3 * den, (num, den)  # distance between the two runs << distance travelled
+    for e, f in zip(ema_a, ema_b):
+        assert torch.allclose(e, f, rtol=1e-2, atol=3e-3)
+    # the EMA tensors were bumped too: an EMA model fed through ema_params re-packs as well
+    assert all(e._version > 0 for e in ema_a)
+    # packed operands == current masters (eval forward of `a` equals a freshly built model with a's weights)
+    x = torch.randn(2, 3, 32, 32, generator=g).cuda()
+    tt = torch.full((2,), 500).cuda()
+    yy = torch.tensor([1, 2]).cuda()
+    fresh = UNet(**SMALL_UNET, num_classes=10)
+    fresh.load_state_dict(a.state_dict())
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        assert torch.equal(a.eval()(x, tt, yy), fresh(x, tt, yy))

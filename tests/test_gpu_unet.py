@@ -183,6 +183,48 @@ def test_cuda_graph_loop_is_bit_identical_to_the_launch_loop(kind, monkeypatch):
     assert torch.equal(outs[0][0], outs[2][0])
 
 
+@pytest.mark.parametrize("model_kind", ["unet", "dit"])
+def test_cached_graph_loop_samples_from_the_current_weights(model_kind):
+    """a replayed sampling graph runs none of the model's Python, so weights changed in place since the capture (optimizer step,
+    EMA update, load_state_dict -- the reference trainer samples its EMA model every N epochs) must be re-packed BEFORE the
+    replay (round-1 advisor finding): sample, change the weights in place, sample again with the same sampler object and
+    require the result of the launch-by-launch loop on the new weights"""
+    from diffusion_models_collection_b200.diffusion import DDIM
+
+    if model_kind == "unet":
+        net = build_unet(SMALL_UNET, 10, 4)
+    else:
+        from diffusion_models_collection_b200.models import DiT
+
+        net = DiT(**synth.CIFAR_DIT, num_classes=10)
+        net.load_state_dict(synth.make_dit_state_dict(None, 10, seed=7))
+        net = net.cuda().eval()
+    y = torch.tensor([1, 10, 3, 5]).cuda()
+    d = DDIM(1000, 4, device="cuda")
+    d.progress = False
+    xT = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    first = d.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT)
+    cache = d._graph_cache
+    assert cache is not None
+    with torch.no_grad():
+        for n_, p in net.named_parameters():  # in place: same storage, new values (what optimizer / EMA updates do)
+            if p.dim() > 1:
+                p.mul_(1.05)
+    second = d.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT)
+    d2 = DDIM(1000, 4, device="cuda")
+    d2.progress = False
+    d2.use_cuda_graph = False
+    want = d2.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT)
+    assert not torch.equal(first, second)
+    assert torch.equal(second, want)
+    if model_kind == "unet":  # values-only change: the plan, its TMA descriptors and the captured graph all survived
+        assert d._graph_cache is cache
+    # load_state_dict (copy_ into the same storage) is seen as well
+    net.load_state_dict({k: v * 0.97 for k, v in net.state_dict().items()})
+    third = d.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT)
+    assert torch.equal(third, d2.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT))
+
+
 def test_full_size_batch_chunking_and_sharding_property():
     """BASELINE configs[2] scale (thousands of images, several 2048-image launches per step): an image's trajectory does
     not depend on which chunk / shard it is denoised in -- rows of the big run equal the same rows sampled alone"""

@@ -2,6 +2,8 @@
 (tests/golden/make_golden.py).  fp32 CPU vs fp32 CPU of the same torch build => tight tolerances;
 integer work (timesteps, label clamp / null token) is bit-exact."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -198,3 +200,31 @@ def test_oracle_training_gradients_match_the_reference(golden, name):
     if c["num_classes"]:
         row0 = g[f"{name}/sample/label_embed.weight"]  # (sampled entries; the full check is on the oracle side)
         assert float(grads[names.index("label_embed.weight")][0].abs().max()) == 0.0 and row0 is not None
+
+
+def test_config1_b16_oracle_matches_reference_golden():
+    """BASELINE configs[0] at its own batch size: the restatement's eps for the 16 images of the reference's first DDIM step, with
+    the default-init weights rebuilt by the reference's constructor under seed 42 (checksums stored next to the golden)"""
+    import random
+
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference not available")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_golden.npz"))
+    ref = ref_loader.import_reference()
+    random.seed(42)
+    np.random.seed(42)
+    torch.manual_seed(42)
+    sd = ref["UNet"](**synth.CIFAR_UNET, num_classes=None).state_dict()
+    assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["weight_sums"])
+    x = torch.from_numpy(g["xT"])
+    eps = model_oracle.unet_forward(sd, synth.CIFAR_UNET, x, torch.full((16,), 999, dtype=torch.long), None, num_classes=None)
+    ref_eps = torch.from_numpy(g["eps0"])
+    err = float((eps - ref_eps).norm() / ref_eps.norm())
+    assert err < 2e-6, err
+    # and one free-running step of the oracle's sampler lands on the reference's state after step 1
+    tb = so.make_tables()
+    ts = so.ddim_timesteps(1000, 50)
+    x1 = so.ddim_step(tb, x, eps, torch.full((16,), int(ts[0])), torch.full((16,), int(ts[1])))
+    assert float((x1 - torch.from_numpy(g["after1"])).abs().max()) < 1e-5
