@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.setdefault("TQDM_DISABLE", "1")  # the reference's samplers draw tqdm bars on stderr
+
 import torch  # noqa: E402
 
 METRIC = "ddim50_unet_cifar10_images_per_sec"
@@ -218,15 +220,22 @@ def run_reference_arm(args, rank):
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
         return
-    # every step = the reference's own DDIM-50 + CFG sampler on `ref_batch` images of the 4096-image step (all 50 denoising steps)
-    for _ in range(args.warmup):
-        cpu_reference_images_per_sec(batch=args.ref_batch)
+    # every step = the reference's own DDIM-50 + CFG sampler on `rb` images of the 4096-image step (all 50 denoising steps);
+    # rb = --ref-batch, halved until the K + W steps fit ~200 s of host time (measured on the first run)
+    rb = max(1, args.ref_batch)
+    t0 = time.perf_counter()
+    cpu_reference_images_per_sec(batch=rb)  # warm-up 1 (always: it sizes the sample)
+    t_one = time.perf_counter() - t0
+    while rb > 1 and (args.steps + max(args.warmup, 1) - 1) * t_one > 200.0:
+        rb, t_one = rb // 2, t_one / 2
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_reference_images_per_sec(batch=rb)
     cb = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, cb = cpu_reference_images_per_sec(batch=args.ref_batch)
+        _, cb = cpu_reference_images_per_sec(batch=rb)
     wall = time.perf_counter() - t0
-    v = args.ref_batch * args.steps / wall
+    v = rb * args.steps / wall
     cb["value"] = v
     shard = (args.batch + args.gpus - 1) // args.gpus
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -253,7 +262,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="global batch (images per step); default 4096 (256 for ddpm1000)")
-    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "dit_ddim50", "dit64_ddim50", "train"],
+    ap.add_argument("--workload", default=None, choices=["ddim50_cfg", "ddpm1000", "eval_ddpm1000_cfg", "dit_ddim50", "dit64_ddim50", "train"],
                     help="ddim50_cfg: BASELINE configs[2], the bench line (default); ddpm1000: configs[1] (uncond UNet, DDPM "
                          "1000 steps, batch 256); dit_ddim50: configs[3] (same as --model dit).  The last two are side "
                          "measurements recorded under profiles/, not the headline metric")
@@ -270,7 +279,8 @@ def main():
     if args.workload is None:
         args.workload = "dit_ddim50" if args.model == "dit" else "ddim50_cfg"
     if args.batch is None:
-        args.batch = 256 if args.workload in ("ddpm1000", "dit64_ddim50") else (128 if args.workload == "train" else 4096)
+        args.batch = 256 if args.workload in ("ddpm1000", "dit64_ddim50") else (
+            128 if args.workload == "train" else (512 if args.workload == "eval_ddpm1000_cfg" else 4096))
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -307,14 +317,15 @@ def main():
     is_dit = args.workload in ("dit_ddim50", "dit64_ddim50")
     dit64 = args.workload == "dit64_ddim50"
     img = 64 if dit64 else 32
-    is_ddpm = args.workload == "ddpm1000"
-    uncond = is_dit or is_ddpm
+    is_eval = args.workload == "eval_ddpm1000_cfg"  # evaluate.py:201-219: DDPM-1000 + CFG at the published batch 512
+    is_ddpm = args.workload == "ddpm1000" or is_eval
+    uncond = is_dit or (is_ddpm and not is_eval)
     sampler_steps = 1000 if is_ddpm else 50
     if is_dit:
         dcfg = dict(synth.CIFAR_DIT, img_size=(img, img))
         net = DiT(**dcfg, num_classes=None)
         net.load_state_dict(synth.make_dit_state_dict(dcfg, None, seed=42))
-    elif is_ddpm:
+    elif is_ddpm and not is_eval:
         net = UNet(**synth.CIFAR_UNET, num_classes=None)
         net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42))
     else:
@@ -389,7 +400,8 @@ def main():
             "gpu_launches": int(launches)}
     pk = peaks()
     # 2 forwards per DDIM step (cond + uncond) for the CFG UNet workload, 1 for the unconditional DiT one
-    flops_step = (50 * (62.855e9 if dit64 else 12.107e9) * B) if is_dit else ((1000 * 12.632e9 * B) if is_ddpm else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B))
+    flops_step = (50 * (62.855e9 if dit64 else 12.107e9) * B) if is_dit else (
+        (2 * 1000 * FLOPS_PER_IMAGE_FORWARD * B) if is_eval else ((1000 * 12.632e9 * B) if is_ddpm else (2 * 50 * FLOPS_PER_IMAGE_FORWARD * B)))
     line["model_flops_utilization"] = {"achieved_tflops": flops_step * args.steps / (ms / 1e3) / 1e12 / world,
                                        "peak_tflops": pk["bf16_tflops_sustained"], "peak_source": pk["_source"]}
 
@@ -405,6 +417,12 @@ def main():
                                       "(BASELINE.json configs[1]); side measurement, not the headline metric")
         line["config"]["sampler"] = "ddpm1000"
         line["config"]["cfg_scale"] = None
+    if is_eval:
+        line["metric"] = "ddpm1000_cfg_unet_cifar10_images_per_sec"
+        line["config"]["workload"] = ("UNet cond (10+1 null) CIFAR-10 32x32, DDPM 1000 steps + CFG 3.0 + dynamic threshold, batch 512 per "
+                                      "call: the generation loop of the reference's evaluate.py:201-219 at its published batch size "
+                                      "(docs/cifar10_runs.md:129); side measurement, not the headline metric")
+        line["config"]["cfg_scale"] = 3.0
     if rank == 0 and not args.no_roofline:
         line["roofline"] = roofline_leg(net, dev, nb, pk, args.ops_out, cfg=not uncond, step_ms=ms / args.steps / sampler_steps,
                                         chunks=-(-nb // max(1, net.max_images_per_launch // (1 if uncond else 2))))

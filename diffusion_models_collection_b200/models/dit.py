@@ -108,6 +108,7 @@ class DiT(nn.Module):
         if self._packed is not None and self._packed_version == ver:
             return self._packed
         sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in self.state_dict().items()}
+        sd = self._canonical_state(sd)
         hs, p, c = self.hidden_size, self.patch_size, self.in_channels
         W, Bv = {}, {}
         w_all, b_all = [], []
@@ -146,6 +147,10 @@ class DiT(nn.Module):
             pl.destroy()
         self._plans = {}
         return self._packed
+
+    def _canonical_state(self, sd):
+        """fp32 device copies of the parameters under the DiT key names the packer / plan read (DiM maps its own names here)"""
+        return sd
 
     def _get_plan(self, device, nimg, x_batch, has_y, uniform_t):
         if self.precision not in ("bf16", "bf16x3"):
@@ -340,6 +345,10 @@ class _DiTPlan:
             if split:
                 a.qkv_lo, a.out_lo = self.lo[id(self.qkv)].data_ptr(), self.lo[id(self.ao)].data_ptr()
             a.impl = int(os.environ.get("DMC_DEBUG_ATTN_IMPL", "0"))
+            if hs // heads != 64:  # the tcgen05 kernel is head-dim 64; 32 runs on the CUDA-core flash kernel (attention.cu)
+                if hs // heads != 32:
+                    raise _lib.DmcError(f"native attention supports head dims 64 and 32 (hidden {hs} / {heads} heads = {hs // heads})")
+                a.impl = 1
             add(lib.dmc_plan_add_attention, a, b + ".attention")
             gemm(self.ao, hs, b + ".out", hs, b + ".out_proj", gate_col=base + 2 * hs)
             ln(base + 3 * hs, base + 4 * hs, b + ".norm2")

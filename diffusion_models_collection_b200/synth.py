@@ -188,3 +188,52 @@ def make_dit_state_dict(cfg=None, num_classes=None, seed=0, null_row_zero=True):
     sd["final_layer.adaLN_modulation.1.weight"] = 0.02 * torch.randn(2 * hs, hs, generator=g)
     sd["final_layer.adaLN_modulation.1.bias"] = 0.02 * torch.randn(2 * hs, generator=g)
     return sd
+
+
+CIFAR_DIM = dict(img_size=(32, 32), patch_size=2, in_channels=3, hidden_size=512, depth=4, state_size=16, mlp_ratio=4.0, dropout=0.1)
+
+
+def make_dim_state_dict(cfg=None, num_classes=None, seed=0, null_row_zero=True):
+    """fp32 CPU state_dict with the keys of the reference DiM as it is built WITHOUT mamba_ssm (models/dim.py:103-117: the
+    nn.MultiheadAttention variant); zero-init tensors re-randomised, LayerNorm affines off their trivial 1 / 0."""
+    cfg = dict(CIFAR_DIM if cfg is None else cfg)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    sd = OrderedDict()
+    hs, p, c = cfg["hidden_size"], cfg["patch_size"], cfg["in_channels"]
+    img = cfg["img_size"]
+    ih, iw = (img, img) if isinstance(img, int) else img
+    hid = int(hs * cfg["mlp_ratio"])
+    sd["pos_embed"] = 0.02 * torch.randn(1, (ih // p) * (iw // p), hs, generator=g)
+    _conv(g, sd, "x_embedder.proj", hs, c, p)
+    _linear(g, sd, "t_embedder.mlp.0", hs, 256)
+    _linear(g, sd, "t_embedder.mlp.2", hs, hs)
+    if num_classes is not None:
+        w = torch.randn(num_classes + 1, hs, generator=g)
+        if null_row_zero:
+            w[0].zero_()
+        sd["y_embedder.embedding_table.weight"] = w
+
+    def norm(name):
+        sd[name + ".weight"] = 1.0 + 0.2 * torch.randn(hs, generator=g)
+        sd[name + ".bias"] = 0.1 * torch.randn(hs, generator=g)
+
+    for i in range(cfg["depth"]):
+        m, f = f"blocks.{i}.mamba_block", f"blocks.{i}.ff_block"
+        norm(m + ".norm")
+        sd[m + ".mamba.in_proj_weight"] = (torch.rand(3 * hs, hs, generator=g) * 2 - 1) / math.sqrt(hs)
+        sd[m + ".mamba.in_proj_bias"] = 0.05 * torch.randn(3 * hs, generator=g)
+        _linear(g, sd, m + ".mamba.out_proj", hs, hs)
+        sd[m + ".adaLN_modulation.1.weight"] = 0.02 * torch.randn(3 * hs, hs, generator=g)
+        sd[m + ".adaLN_modulation.1.bias"] = 0.02 * torch.randn(3 * hs, generator=g)
+        norm(f + ".norm")
+        _linear(g, sd, f + ".mlp.0", hid, hs)
+        _linear(g, sd, f + ".mlp.3", hs, hid)
+        sd[f + ".adaLN_modulation.1.weight"] = 0.02 * torch.randn(3 * hs, hs, generator=g)
+        sd[f + ".adaLN_modulation.1.bias"] = 0.02 * torch.randn(3 * hs, generator=g)
+    norm("final_layer.norm_final")
+    sd["final_layer.linear.weight"] = 0.05 * torch.randn(p * p * c, hs, generator=g)
+    sd["final_layer.linear.bias"] = 0.02 * torch.randn(p * p * c, generator=g)
+    sd["final_layer.adaLN_modulation.1.weight"] = 0.02 * torch.randn(2 * hs, hs, generator=g)
+    sd["final_layer.adaLN_modulation.1.bias"] = 0.02 * torch.randn(2 * hs, generator=g)
+    return sd

@@ -158,3 +158,48 @@ def dit_forward(sd, cfg, x, t, y=None, num_classes=None):
     h = h.reshape(B, hh, ww, p, p, C)
     h = torch.einsum("nhwpqc->nchpwq", h)
     return h.reshape(B, C, hh * p, ww * p)
+
+
+@torch.no_grad()
+def dim_forward(sd, cfg, x, t, y=None, num_classes=None):
+    """eps = DiM(x, t, y) in fp32, eval mode, for the variant the reference runs without mamba_ssm (models/dim.py:103-117:
+    nn.MultiheadAttention with 8 heads in place of Mamba).  Follows models/dim.py:119-141 (MambaBlock.forward), :153-164
+    (FeedForward.forward), :188-193 (FinalLayer.forward), :306-340 (unpatchify, DiM.forward); the LayerNorms are affine."""
+    hs, nh, p = cfg["hidden_size"], 8, cfg["patch_size"]
+    B, C, H, W = x.shape
+    hh, ww = H // p, W // p
+    hd = hs // nh
+
+    def ln(v, name):
+        return F.layer_norm(v, (hs,), sd[name + ".weight"], sd[name + ".bias"], eps=1e-6)
+
+    tok = F.conv2d(x, sd["x_embedder.proj.weight"], sd["x_embedder.proj.bias"], stride=p)
+    tok = tok.flatten(2).transpose(1, 2) + sd["pos_embed"]
+    c = F.linear(_dit_time_embedding(t), sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])
+    c = F.linear(F.silu(c), sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"])
+    if num_classes is not None and y is not None:
+        c = c + F.embedding(torch.clamp(y, 0, num_classes), sd["y_embedder.embedding_table.weight"])
+    sc = F.silu(c)
+    for i in range(cfg["depth"]):
+        m, f = f"blocks.{i}.mamba_block", f"blocks.{i}.ff_block"
+        shift, scale, gate = F.linear(sc, sd[m + ".adaLN_modulation.1.weight"], sd[m + ".adaLN_modulation.1.bias"]).chunk(3, dim=-1)
+        h = ln(tok, m + ".norm") * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+        q, k, v = F.linear(h, sd[m + ".mamba.in_proj_weight"], sd[m + ".mamba.in_proj_bias"]).chunk(3, dim=-1)
+        q = q.reshape(B, -1, nh, hd).transpose(1, 2)
+        k = k.reshape(B, -1, nh, hd).transpose(1, 2)
+        v = v.reshape(B, -1, nh, hd).transpose(1, 2)
+        a = torch.softmax(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+        h = torch.matmul(a, v).transpose(1, 2).reshape(B, -1, hs)
+        h = F.linear(h, sd[m + ".mamba.out_proj.weight"], sd[m + ".mamba.out_proj.bias"])
+        tok = tok + gate.unsqueeze(1) * h
+        shift, scale, gate = F.linear(sc, sd[f + ".adaLN_modulation.1.weight"], sd[f + ".adaLN_modulation.1.bias"]).chunk(3, dim=-1)
+        h = ln(tok, f + ".norm") * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+        h = F.gelu(F.linear(h, sd[f + ".mlp.0.weight"], sd[f + ".mlp.0.bias"]))
+        h = F.linear(h, sd[f + ".mlp.3.weight"], sd[f + ".mlp.3.bias"])
+        tok = tok + gate.unsqueeze(1) * h
+    shift, scale = F.linear(sc, sd["final_layer.adaLN_modulation.1.weight"], sd["final_layer.adaLN_modulation.1.bias"]).chunk(2, dim=-1)
+    h = ln(tok, "final_layer.norm_final") * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+    h = F.linear(h, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
+    h = h.reshape(B, hh, ww, p, p, C)
+    h = torch.einsum("nhwpqc->nchpwq", h)
+    return h.reshape(B, C, hh * p, ww * p)

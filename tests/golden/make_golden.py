@@ -156,6 +156,26 @@ def gen_dit():
     np.savez_compressed(os.path.join(HERE, "dit_golden.npz"), **out)
 
 
+def gen_dim():
+    """eps = DiM(x, t, y) of the reference's own DiM class as built in this container (mamba_ssm absent: models/dim.py:103-117
+    picks nn.MultiheadAttention)"""
+    from tests.golden_cases import DIM_CASES
+
+    ref_dim = _load("_ref_dim", "models/dim.py")
+    assert not ref_dim.MAMBA_AVAILABLE
+    out = {}
+    for name, c in DIM_CASES.items():
+        cfg = dict(synth.CIFAR_DIM, hidden_size=c["hidden"], depth=c["depth"])
+        net = ref_dim.DiM(**cfg, num_classes=c["num_classes"]).eval()
+        net.load_state_dict(synth.make_dim_state_dict(cfg, c["num_classes"], seed=c["wseed"]), strict=True)
+        x, t, y = case_inputs(c)
+        with torch.no_grad():
+            eps = net(x, t, y)
+        out[name] = eps.numpy()
+        print("dim", name, tuple(eps.shape), float(eps.std()))
+    np.savez_compressed(os.path.join(HERE, "dim_golden.npz"), **out)
+
+
 TABLE_NAMES = ["betas", "alphas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
                "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas", "sqrt_recipm1_alphas_cumprod",
                "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]

@@ -32,6 +32,14 @@ DIT_CASES = {
 }
 
 
+# DiM as the reference builds it without mamba_ssm (nn.MultiheadAttention, 8 heads): hidden 512 -> head dim 64 (tcgen05
+# attention), hidden 256 -> head dim 32 (CUDA-core flash kernel)
+DIM_CASES = {
+    "cond_h512": dict(wseed=8, num_classes=10, xseed=23, B=3, t=[999, 0, 347], y=[0, 10, 4], hidden=512, depth=4),
+    "uncond_h256": dict(wseed=9, num_classes=None, xseed=24, B=2, t=[500, 20], y=None, hidden=256, depth=2),
+}
+
+
 def case_inputs(c):
     g = torch.Generator(device="cpu")
     g.manual_seed(int(c["xseed"]))
