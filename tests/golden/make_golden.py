@@ -314,11 +314,13 @@ CONFIG1_HORIZONS = [1, 2, 3, 5, 10, 20, 50]  # states after this many free-runni
 
 
 def gen_config1():
-    """BASELINE.json configs[0] VERBATIM through the reference: set_seed(42) (sample.py:90), UNet(**cifar10_unet model_params,
-    num_classes=None) with PyTorch's default init, DDIM(1000, 50, 1e-4, 0.02, 'linear', eta=0).sample(model, (16, 3, 32, 32)).
+    """BASELINE.json configs[0] through the reference: set_seed(42) (sample.py:90), UNet(**cifar10_unet model_params,
+    num_classes=None), DDIM(1000, 50, 1e-4, 0.02, 'linear', eta=0).sample(model, (16, 3, 32, 32)).  One departure from the
+    verbatim config: the weights are synth.make_unet_state_dict(seed 42) instead of PyTorch's default init -- nn.init's
+    un-seeded-generator path is not bit-reproducible across CPU models (measured: the GPU box's host draws other values than the
+    build container for the same seed), the explicit-generator draws of synth.py are, and 148 MB of weights are no fixture.
     Stored: x_T, the reference's state after CONFIG1_HORIZONS free-running steps (the last one = the final images), its eps for
-    the first forward (a B = 16 whole-model golden), and per-tensor checksums of the default-init weights so that a test can prove
-    it rebuilt the same weights from the reference's constructor on another machine."""
+    the first forward (a B = 16 whole-model golden), and per-tensor checksums of the weights."""
     import contextlib
     import io
     import random
@@ -327,6 +329,7 @@ def gen_config1():
     np.random.seed(42)
     torch.manual_seed(42)
     net = ref_unet.UNet(**synth.CIFAR_UNET, num_classes=None).eval()
+    net.load_state_dict(synth.make_unet_state_dict(None, None, seed=42), strict=True)
     d50 = ref_ddim.DDIM(1000, 50, 1e-4, 0.02, "linear", eta=0.0, device="cpu")
     with NoiseRecorder() as rec, contextlib.redirect_stderr(io.StringIO()), torch.no_grad():
         traj = d50.sample(net, (16, 3, 32, 32), return_all_timesteps=True)

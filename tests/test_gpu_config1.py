@@ -1,7 +1,7 @@
-"""GPU: BASELINE.json configs[0] -- the reference's own CPU-runnable case (uncond UNet, default init under seed 42, DDIM-50,
-batch 16) -- replayed on the native path against tests/golden/config1_golden.npz (written from the live reference by
-tests/golden/make_golden.py config1).  The weights are rebuilt on this machine by the reference's own constructor (from
-oracle/_ref) and proven identical through the stored per-tensor checksums.
+"""GPU: BASELINE.json configs[0] -- the reference's own CPU-runnable case (uncond UNet, DDIM-50, batch 16, seed 42) -- replayed
+on the native path against tests/golden/config1_golden.npz (written from the live reference by tests/golden/make_golden.py
+config1).  Weights: synth.make_unet_state_dict(seed 42), proven identical to the golden run's through stored per-tensor
+checksums (PyTorch's default init is not bit-reproducible across host CPU models, see make_golden.gen_config1).
 
 * whole-model eps at B = 16 (the batch size of configs[0]): bf16 <= 2e-2, split-bf16 ("bf16x3") <= 1e-3 relative L2;
 * FREE-RUNNING DDIM from the reference's x_T: deviation from the reference's own state after 1, 2, 3, 5, 10, 20 and 50 steps.
@@ -29,22 +29,12 @@ FREE_RUN_GATES_BF16 = {1: 5e-2}
 
 
 def _reference_weights(g):
-    from oracle import ref_loader
-
-    if not ref_loader.available():
-        pytest.skip("reference not available (no checkout, no oracle/_ref archive)")
-    import random
-
-    ref = ref_loader.import_reference()
-    random.seed(42)
-    np.random.seed(42)
-    torch.manual_seed(42)
-    sd = ref["UNet"](**synth.CIFAR_UNET, num_classes=None).state_dict()
+    sd = synth.make_unet_state_dict(None, None, seed=42)
     sums = np.array([float(v.double().sum()) for v in sd.values()])
     asums = np.array([float(v.double().abs().sum()) for v in sd.values()])
     assert list(sd) == list(g["weight_names"])
     assert np.array_equal(sums, g["weight_sums"]) and np.array_equal(asums, g["weight_abs_sums"]), \
-        "the reference's default init under seed 42 did not reproduce the weights the golden run used"
+        "synth.make_unet_state_dict(seed 42) did not reproduce the weights the golden run used"
     return sd
 
 

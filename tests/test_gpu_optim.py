@@ -5,6 +5,7 @@ norm's sum, fused multiply-adds)."""
 import pytest
 import torch
 
+from diffusion_models_collection_b200 import synth
 from diffusion_models_collection_b200.optim import FusedAdamW
 
 pytestmark = pytest.mark.gpu
@@ -71,15 +72,13 @@ def test_fused_adamw_steps_reach_the_native_unet_forward():
     follow the fp32 masters."""
     from diffusion_models_collection_b200.diffusion import DDPM
     from diffusion_models_collection_b200.models import UNet
-    from tests.golden_cases import SMALL_UNET
+    SMALL_UNET = synth.CIFAR_UNET  # (the training engine needs channel counts that are multiples of 128)
 
     def make():
         net = UNet(**SMALL_UNET, num_classes=10, )
         net.load_state_dict(synth.make_unet_state_dict(SMALL_UNET, 10, seed=4))
         net.dropout = 0.0
         return net.cuda().train()
-
-    from diffusion_models_collection_b200 import synth
 
     a, b = make(), make()
     ema_a = [p.detach().clone() for p in a.parameters()]
@@ -90,10 +89,10 @@ def test_fused_adamw_steps_reach_the_native_unet_forward():
     g = torch.Generator().manual_seed(5)
     losses = []
     for step in range(3):
-        x0 = (torch.rand(8, 3, 32, 32, generator=g) * 2 - 1).cuda()
-        t = torch.randint(0, 1000, (8,), generator=g).cuda()
-        y = torch.randint(0, 11, (8,), generator=g).cuda()
-        nz = torch.randn(8, 3, 32, 32, generator=g).cuda()
+        x0 = (torch.rand(4, 3, 32, 32, generator=g) * 2 - 1).cuda()
+        t = torch.randint(0, 1000, (4,), generator=g).cuda()
+        y = torch.randint(0, 11, (4,), generator=g).cuda()
+        nz = torch.randn(4, 3, 32, 32, generator=g).cuda()
         ver_before = [p._version for p in a.parameters()]
         la = ddpm.p_losses(a, x0, t, y, noise=nz)
         la.backward()

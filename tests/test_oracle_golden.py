@@ -203,20 +203,10 @@ def test_oracle_training_gradients_match_the_reference(golden, name):
 
 
 def test_config1_b16_oracle_matches_reference_golden():
-    """BASELINE configs[0] at its own batch size: the restatement's eps for the 16 images of the reference's first DDIM step, with
-    the default-init weights rebuilt by the reference's constructor under seed 42 (checksums stored next to the golden)"""
-    import random
-
-    from oracle import ref_loader
-
-    if not ref_loader.available():
-        pytest.skip("reference not available")
+    """BASELINE configs[0] at its own batch size: the restatement's eps for the 16 images of the reference's first DDIM step (synth
+    weights seed 42, checksums stored next to the golden)"""
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_golden.npz"))
-    ref = ref_loader.import_reference()
-    random.seed(42)
-    np.random.seed(42)
-    torch.manual_seed(42)
-    sd = ref["UNet"](**synth.CIFAR_UNET, num_classes=None).state_dict()
+    sd = synth.make_unet_state_dict(None, None, seed=42)
     assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["weight_sums"])
     x = torch.from_numpy(g["xT"])
     eps = model_oracle.unet_forward(sd, synth.CIFAR_UNET, x, torch.full((16,), 999, dtype=torch.long), None, num_classes=None)
