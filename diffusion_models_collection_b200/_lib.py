@@ -66,7 +66,10 @@ class ConvDesc(C.Structure):
                 ("Ktot", C.c_int32), ("bias", vp), ("cond", vp), ("cond_stride", C.c_int32), ("residual", vp),
                 ("out_bf16", vp), ("out_f32_nchw", vp), ("stats", vp), ("stats_slots", C.c_int32), ("impl", C.c_int32),
                 ("act", C.c_int32), ("gate", vp), ("gate_stride", C.c_int32), ("residual_f32", vp), ("out_f32_nhwc", vp),
-                ("out_lo", vp), ("residual_lo", vp), ("unpatch_p", C.c_int32)]
+                ("out_lo", vp), ("residual_lo", vp), ("unpatch_p", C.c_int32),
+                ("gn_nver", C.c_int32), ("gn_out", vp * 2), ("gn_pitch", C.c_int32 * 2), ("gn_coff", C.c_int32 * 2),
+                ("gn_gamma", vp * 2), ("gn_beta", vp * 2), ("gn_gsize", C.c_int32 * 2), ("gn_silu", C.c_int32 * 2),
+                ("gn_eps", C.c_float), ("gn_counters", vp)]
 
 
 class DitCondDesc(C.Structure):
@@ -203,6 +206,7 @@ SYMBOLS = {
     "dmc_plan_add_ln_modulate": (C.c_int, [vp, C.POINTER(LnModDesc)]),
     "dmc_plan_add_head": (C.c_int, [vp, C.POINTER(HeadDesc)]),
     "dmc_head_supported": (C.c_int, [C.POINTER(HeadDesc)]),
+    "dmc_conv_gn_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),

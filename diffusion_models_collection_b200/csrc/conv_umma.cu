@@ -50,24 +50,61 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // MT * BN (the A tile is reused by BN channels, the B tile by MT * 128 pixels): prefer 256 TMEM columns per
 // accumulator when that still yields at least one tile per SM.
 struct TileCfg { int bn, mt, cg; };
-static TileCfg pick_cfg(int cout_pad, int m_tiles) {
+
+// Fused GroupNorm epilogue: can tile configuration `c` run it for an output of P pixels per image, `cout` channels and
+// statistics groups of at most `max_gsz` channels?  Every group must lie inside one n tile; an image spanning several CTAs
+// needs whole CTA groups per image and all of them in one wave of the persistent grid.
+static bool gn_cfg_ok(const TileCfg& c, int cout, int P, int max_gsz) {
+  if (c.bn < 64 || cout % c.bn != 0 || c.bn % max_gsz != 0) return false;
+  const int rows = TILE_M * c.mt;
+  if (P <= rows) return rows % P == 0 && (P == 16 || P % 32 == 0);
+  if (P % rows != 0) return false;
+  const int ctas = P / rows;
+  if (ctas % c.cg != 0) return false;
+  return (ctas / c.cg) * (cout / c.bn) <= num_sms() / c.cg;
+}
+
+static TileCfg pick_cfg(int cout_pad, int m_tiles, int gn_P = 0, int gn_max_gsz = 0) {
   const int sms = num_sms();
   // DMC_CONV_CG (debug / tests): "1" never pairs SMs, "2" pairs them whenever the channel count allows
   const char* e = getenv("DMC_CONV_CG");
   const bool allow_pairs = !(e && e[0] == '1');
   const bool force_pairs = e && e[0] == '2';
   const TileCfg cands[7] = {{256, 1, 2}, {128, 2, 2}, {256, 1, 1}, {128, 2, 1}, {128, 1, 1}, {64, 1, 1}, {32, 1, 1}};
+  auto ok = [&](const TileCfg& c) { return gn_P == 0 || gn_cfg_ok(c, cout_pad, gn_P, gn_max_gsz); };
   if (force_pairs)
     for (int i = 0; i < 2; ++i)
-      if (cout_pad % cands[i].bn == 0) return cands[i];
+      if (cout_pad % cands[i].bn == 0 && ok(cands[i])) return cands[i];
   for (const TileCfg& c : cands) {
-    if (cout_pad % c.bn != 0 || (c.cg == 2 && !allow_pairs)) continue;
+    if (cout_pad % c.bn != 0 || (c.cg == 2 && !allow_pairs) || !ok(c)) continue;
     const long long ctas = static_cast<long long>((m_tiles + c.mt * c.cg - 1) / (c.mt * c.cg)) * (cout_pad / c.bn) * c.cg;
     if (ctas >= sms) return c;
   }
   for (int i = 6; i >= 2; --i)
-    if (cout_pad % cands[i].bn == 0) return cands[i];
+    if (cout_pad % cands[i].bn == 0 && ok(cands[i])) return cands[i];
+  if (gn_P != 0) return {0, 0, 0};  // no configuration can fuse the GroupNorm of this output
   return {32, 1, 1};
+}
+
+// 128-pixel M tiles of a [B, Hout, Wout] output (box BW x BH x BNIMG, see conv_prepare); 0 when the shape does not tile
+static int conv_m_tiles(int B, int Hout, int Wout, int* tiles_w_out) {
+  const int BW = std::min(Wout, TILE_M);
+  if (BW <= 0 || TILE_M % BW != 0 || Wout % BW != 0) return 0;
+  const int BH = std::min(Hout, TILE_M / BW);
+  if (BH <= 0 || (TILE_M / BW) % BH != 0 || Hout % BH != 0) return 0;
+  const int BNIMG = TILE_M / (BW * BH);
+  if (tiles_w_out) *tiles_w_out = Wout / BW;
+  return ((B + BNIMG - 1) / BNIMG) * (Wout / BW) * (Hout / BH);
+}
+
+bool conv_gn_supported(int B, int Hout, int Wout, int Cout, int max_gsz) {
+  if (B <= 0 || Hout <= 0 || Wout <= 0 || Cout % 32 != 0 || !(max_gsz == 16 || max_gsz == 32 || max_gsz == 64)) return false;
+  int tiles_w = 0;
+  const int m_tiles = conv_m_tiles(B, Hout, Wout, &tiles_w);
+  if (m_tiles == 0 || tiles_w != 1) return false;
+  const int P = Hout * Wout;
+  if (!(P == 16 || (P >= 32 && P % 32 == 0))) return false;
+  return pick_cfg(Cout, m_tiles, P, max_gsz).bn != 0;
 }
 
 int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
@@ -76,7 +113,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   DMC_REQUIRE(d.up_phase >= -1 && d.up_phase <= 3, "conv: up_phase=%d", d.up_phase);
   DMC_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0, "conv: empty input");
   DMC_REQUIRE(d.Hin % d.stride == 0 && d.Win % d.stride == 0, "conv: odd spatial size with stride 2");
-  DMC_REQUIRE(d.weight && (d.out_bf16 || d.out_f32_nchw || d.out_f32_nhwc), "conv: null weight/output");
+  DMC_REQUIRE(d.weight && (d.out_bf16 || d.out_f32_nchw || d.out_f32_nhwc || d.gn_nver > 0), "conv: null weight/output");
   DMC_REQUIRE(d.Cout_pad % 32 == 0 && d.Cout <= d.Cout_pad, "conv: Cout_pad=%d must be a multiple of 32", d.Cout_pad);
   if (d.out_bf16 || d.out_f32_nhwc)
     DMC_REQUIRE(d.Cout % 32 == 0, "conv: NHWC output needs Cout %% 32 == 0 (got %d)", d.Cout);
@@ -87,7 +124,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
               "conv: unpatch_p=%d needs an fp32 NCHW output and Cout = p*p*channels", d.unpatch_p);
   if (d.out_f32_nchw) DMC_REQUIRE(!d.gate && !d.residual_f32 && !d.out_f32_nhwc && d.act == 0,
                                   "conv: the fp32 NCHW head takes bias only");
-  if (d.stats) DMC_REQUIRE(d.out_bf16 != nullptr, "conv: stats need a bf16 output");
+  if (d.stats) DMC_REQUIRE(d.out_bf16 != nullptr || d.gn_nver > 0, "conv: stats need a bf16 output");
 
   ConvPrepared* P = new (std::nothrow) ConvPrepared();
   DMC_REQUIRE(P != nullptr, "conv: out of host memory");
@@ -148,7 +185,33 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     DMC_REQUIRE(false, "conv: Ktot=%d does not match the sources (%d)", d.Ktot, kb * KB);
   }
 
-  const TileCfg tc = pick_cfg(d.Cout_pad, kp.num_m_tiles);
+  // ---- fused GroupNorm request (dmc_conv_desc.gn_*) ----
+  const bool gn = d.gn_nver != 0;
+  const int gn_P = Hout * Wout;
+  int gn_max_gsz = 0, gn_min_gsz = 64;
+  if (gn) {
+    bool okv = d.gn_nver >= 1 && d.gn_nver <= 2 && d.stats != nullptr && d.out_f32_nchw == nullptr && !d.act && !d.gate &&
+               !d.residual_f32 && !d.out_f32_nhwc && !d.out_lo && !d.residual_lo && d.up_phase < 0 && d.Cout == d.Cout_pad &&
+               kp.tiles_w == 1 && d.unpatch_p == 0;
+    for (int v = 0; okv && v < d.gn_nver; ++v) {
+      const int gs = d.gn_gsize[v];
+      okv = d.gn_out[v] && d.gn_gamma[v] && d.gn_beta[v] && (gs == 16 || gs == 32 || gs == 64) && d.Cout % gs == 0 &&
+            d.gn_coff[v] >= 0 && d.gn_coff[v] % gs == 0 && d.gn_pitch[v] >= d.gn_coff[v] + d.Cout && d.gn_pitch[v] % 8 == 0;
+      gn_max_gsz = std::max(gn_max_gsz, gs);
+      gn_min_gsz = std::min(gn_min_gsz, gs);
+    }
+    if (!okv) {
+      delete P;
+      DMC_REQUIRE(false, "conv: bad fused-GroupNorm request (needs a plain UNet convolution with stats, 1-2 versions, group "
+                         "sizes 16/32/64 that divide Cout and the slice offset)");
+    }
+  }
+  const TileCfg tc = pick_cfg(d.Cout_pad, kp.num_m_tiles, gn ? gn_P : 0, gn_max_gsz);
+  if (tc.bn == 0) {
+    delete P;
+    DMC_REQUIRE(false, "conv: no tile configuration fuses the GroupNorm of a %d-pixel, %d-channel output (group size %d)", gn_P,
+                d.Cout, gn_max_gsz);
+  }
   const int BN = tc.bn;
   P->BN = BN;
   P->MT = tc.mt;
@@ -160,6 +223,28 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     cuuint32_t box[2] = {KB, static_cast<cuuint32_t>(BN / tc.cg)};
     cuuint32_t estr[2] = {1, 1};
     if (encode_map(&P->tmB, d.weight, 2, dims, strides, box, estr) != 0) { delete P; return -1; }
+  }
+  kp.gn_nver = 0;
+  int gn_tab_bytes = 0;
+  if (gn) {
+    const int rows = TILE_M * tc.mt;
+    kp.gn_nver = d.gn_nver;
+    kp.gn_P = gn_P;
+    kp.gn_imgs = gn_P <= rows ? rows / gn_P : 1;
+    kp.gn_ctas_per_img = gn_P <= rows ? 1 : gn_P / rows;
+    kp.gn_tab_groups = BN / gn_min_gsz;
+    kp.gn_eps = d.gn_eps;
+    kp.gn_counters = d.gn_counters;
+    for (int v = 0; v < d.gn_nver; ++v) {
+      kp.gn_out[v] = reinterpret_cast<__nv_bfloat16*>(d.gn_out[v]);
+      kp.gn_pitch[v] = d.gn_pitch[v]; kp.gn_coff[v] = d.gn_coff[v]; kp.gn_gsize[v] = d.gn_gsize[v]; kp.gn_silu[v] = d.gn_silu[v];
+      kp.gn_gamma[v] = d.gn_gamma[v]; kp.gn_beta[v] = d.gn_beta[v];
+    }
+    gn_tab_bytes = 2 /*accumulator stages*/ * 2 /*versions*/ * kp.gn_imgs * kp.gn_tab_groups * 8;
+    if (kp.gn_ctas_per_img > 1 && d.gn_counters == nullptr) {
+      delete P;
+      DMC_REQUIRE(false, "conv: fused GroupNorm of a %d-pixel image spans %d CTAs: gn_counters is required", gn_P, kp.gn_ctas_per_img);
+    }
   }
   // ---- kernel variant selection (every switch has an environment override for A/B measurements and tests) ----
   const bool split = d.out_lo != nullptr || d.residual_lo != nullptr;  // split-bf16 (hi, lo) output / residual pairs
@@ -191,6 +276,10 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     kp.bres = 1;
     kp.b_region_bytes = kp.num_kb * b_tile;
   }
+  if (gn && kp.bres && kp.gn_ctas_per_img > 1 && kp.num_n_tiles > 1) {  // the resident-weight schedule splits an image's n tiles
+    kp.bres = 0;
+    kp.b_region_bytes = 0;
+  }
   // (2) row slabs for the 3x3 segment 0: one box serves the three vertical taps
   kp.slab = 0;
   kp.slab_bytes = 0;
@@ -218,6 +307,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   //     longer K loops lose more from the 32 KB it takes out of the operand ring (+4 % .. +19 % at 36-48 K blocks).
   P->tmOut = P->tmB;
   P->tmRes = P->tmB;
+  P->tmV[0] = P->tmV[1] = P->tmB;
   kp.tma_store = 0;
   kp.res_tma = 0;
   kp.store_bufs = 1;
@@ -228,7 +318,10 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     const bool f32 = epi == 3;
     const int boxc = f32 ? 32 : 64;
     void* optr = f32 ? static_cast<void*>(d.out_f32_nhwc) : d.out_bf16;
-    if (want && epi != 2 && epi != 4 && !split && optr != nullptr && d.Cout % boxc == 0 && BN >= 128) {
+    if (gn && optr == nullptr) optr = d.gn_out[0];  // no raw output: tmOut is a placeholder, never stored through
+    bool gn_ts_ok = true;
+    for (int v = 0; v < d.gn_nver; ++v) gn_ts_ok = gn_ts_ok && d.gn_pitch[v] % 8 == 0 && d.gn_coff[v] % 8 == 0;
+    if (want && epi != 2 && epi != 4 && !split && optr != nullptr && d.Cout % boxc == 0 && BN >= 128 && gn_ts_ok) {
       const int qbw = std::min(BW, 32), qbh = std::min(BH, 32 / qbw), qbn = 32 / (qbw * qbh);
       const int os = kp.oscale;
       const size_t es = f32 ? 4 : 2;
@@ -242,13 +335,22 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
       cuuint32_t estr[4] = {1, 1, 1, 1};
       const char* base = reinterpret_cast<const char*>(optr) +
                          (static_cast<size_t>(kp.ooff_h) * kp.out_W + kp.ooff_w) * d.Cout * es;
-      if (encode_map(&P->tmOut, base, 4, dims, strides, box, estr, dt) != 0) { delete P; return -1; }
+      if (d.out_bf16 != nullptr || !gn) {
+        if (encode_map(&P->tmOut, base, 4, dims, strides, box, estr, dt) != 0) { delete P; return -1; }
+      }
+      for (int v = 0; v < d.gn_nver; ++v) {  // the normalised versions: channel slices of [B, Hout, Wout, pitch] tensors
+        const cuuint64_t pc = static_cast<cuuint64_t>(d.gn_pitch[v]);
+        cuuint64_t vdims[4] = {pc, static_cast<cuuint64_t>(Wout), static_cast<cuuint64_t>(Hout), static_cast<cuuint64_t>(d.B)};
+        cuuint64_t vstr[3] = {pc * 2, static_cast<cuuint64_t>(Wout) * pc * 2, static_cast<cuuint64_t>(Hout) * Wout * pc * 2};
+        if (encode_map(&P->tmV[v], d.gn_out[v], 4, vdims, vstr, box, estr) != 0) { delete P; return -1; }
+      }
+      if (gn && d.out_bf16 == nullptr) P->tmOut = P->tmV[0];
       kp.tma_store = 1;
       kp.qbw = qbw;
       kp.qbh = qbh;
       // the residual (same shape as the output) comes in as boxes too: coalesced and asynchronous
       const void* rptr = f32 ? static_cast<const void*>(d.residual_f32) : d.residual;
-      if (rptr != nullptr && os == 1 && env_flag("DMC_CONV_RES_TMA", 1)) {
+      if (rptr != nullptr && os == 1 && env_flag("DMC_CONV_RES_TMA", 1) && (!gn || d.out_bf16 != nullptr)) {
         if (rptr == optr) P->tmRes = P->tmOut;
         else if (encode_map(&P->tmRes, rptr, 4, dims, strides, box, estr, dt) != 0) { delete P; return -1; }
         kp.res_tma = 1;
@@ -258,7 +360,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   {
     auto plan = [&](int bufs, int* nst) {
       const int store_bytes = kp.tma_store ? bufs * (EPI_THREADS / 32) * 4096 : 0;
-      const int fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + store_bytes + kp.b_region_bytes;
+      const int fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + gn_tab_bytes + store_bytes + kp.b_region_bytes;
       *nst = std::min(std::min(MAX_NST, env_flag("DMC_CONV_NST", MAX_NST)), (SMEM_LIMIT - fixed) / kp.stage_bytes);
       return fixed;
     };
@@ -279,7 +381,8 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     }
     P->smem = static_cast<size_t>(fixed) + static_cast<size_t>(kp.nst) * kp.stage_bytes;
   }
-  P->var = (kp.slab ? VAR_SLAB : 0) | (kp.bres ? VAR_BRES : 0) | (kp.tma_store ? VAR_TS : 0) | (epi << VAR_EPI_SHIFT);
+  P->var = (kp.slab ? VAR_SLAB : 0) | (kp.bres ? VAR_BRES : 0) | (kp.tma_store ? VAR_TS : 0) | (epi << VAR_EPI_SHIFT) |
+           (gn ? VAR_GN : 0);
   kp.Cout = d.Cout;
   kp.bias = d.bias; kp.cond = d.cond; kp.cond_stride = d.cond_stride;
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
@@ -307,7 +410,14 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   {
     const int mtg = tc.mt * tc.cg;
     const int group_tiles = ((kp.num_m_tiles + mtg - 1) / mtg) * kp.num_n_tiles;
-    P->grid = tc.cg * std::min(group_tiles, num_sms() / tc.cg);
+    int groups = std::min(group_tiles, num_sms() / tc.cg);
+    if (gn && kp.gn_ctas_per_img > 1) {
+      // the CTA groups that hold the pieces of one image (all its n tiles) must run in the same iteration of the tile loop:
+      // the grid is a whole number of such units (group_tiles = images x unit by construction)
+      const int unit = (kp.gn_ctas_per_img / tc.cg) * kp.num_n_tiles;
+      groups = groups / unit * unit;
+    }
+    P->grid = tc.cg * groups;
   }
   *out = P;
   return 0;

@@ -57,6 +57,18 @@ struct ConvKParams {
   int nst, stage_bytes, a_bytes, b_region_bytes;
   int bres;                   // weights of the whole K extent stay resident (short-K GEMMs: 1x1 convs, transformer linears)
   int slab, slab_bytes;       // 3x3 segment 0 is loaded as row slabs shared by the three vertical taps
+  // fused GroupNorm(+SiLU) of the output (VAR_GN): see dmc_conv_desc.gn_*
+  int gn_nver;                // normalised versions written by the epilogue (1 or 2)
+  int gn_P;                   // output pixels per image
+  int gn_imgs;                // images (or the one partial image) in this CTA's table: P <= 128 * MT ? 128 * MT / P : 1
+  int gn_ctas_per_img;        // CTAs holding pieces of one image (1: the shared-memory barrier is the only hand-shake)
+  int gn_tab_groups;          // table columns per version (BN / smallest group size)
+  int* gn_counters;           // [image * num_n_tiles + n_tile][arrived, done]
+  float gn_eps;
+  __nv_bfloat16* gn_out[2];
+  int gn_pitch[2], gn_coff[2], gn_gsize[2], gn_silu[2];
+  const float* gn_gamma[2];
+  const float* gn_beta[2];
 };
 
 constexpr int MAX_NST = 8;
@@ -68,6 +80,7 @@ struct ConvPrepared {
   CUtensorMap tmB;
   CUtensorMap tmOut;
   CUtensorMap tmRes;
+  CUtensorMap tmV[2];  // fused-GroupNorm versions (TMA-store epilogue)
   ConvKParams kp;
   int BN, MT, CG;
   int var;  // kernel variant (VAR_* bits)
@@ -156,19 +169,23 @@ __device__ __forceinline__ void reduce8(const float (&v)[8], bool full, int lane
 //                2: model head (bias, fp32 NCHW out, optional unpatchify)
 //                3: transformer linear on the fp32 residual stream (bias, gate, fp32 residual, fp32 NHWC out)
 //                4: UNet convolution in split-bf16 mode: like 0, the residual and the output are (hi, lo) bf16 pairs
-constexpr int VAR_SLAB = 1, VAR_BRES = 2, VAR_TS = 4, VAR_EPI_SHIFT = 3;
+//   bit 6 GN     EPI 0 only: GroupNorm(+SiLU) of the output fused into the epilogue (two passes over the tile in tensor memory)
+constexpr int VAR_SLAB = 1, VAR_BRES = 2, VAR_TS = 4, VAR_EPI_SHIFT = 3, VAR_GN = 64;
+constexpr int GN_TAB_OFFSET = 512;  // the mean / rstd table follows the barrier block
 
 template <int BN, int MT, int CG, int VAR>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ ConvKParams p) {
+                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmV0,
+                 const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BN, MT, CG>;
   constexpr bool SLAB = (VAR & VAR_SLAB) != 0;
   constexpr bool BRES = (VAR & VAR_BRES) != 0;
   constexpr bool TS = (VAR & VAR_TS) != 0 && Cfg::TMA_STORE;
-  constexpr int EPI = VAR >> VAR_EPI_SHIFT;
+  constexpr int EPI = (VAR >> VAR_EPI_SHIFT) & 7;
+  constexpr bool GN = (VAR & VAR_GN) != 0 && EPI == 0;
   constexpr bool UNET = EPI == 0 || EPI == 4;  // bias + conditioning + bf16 residual + GroupNorm partial sums
   constexpr int MTG = MT * CG;  // 128-pixel tiles per CTA-group tile
   constexpr int B_TILE = Cfg::B_STAGE_BYTES;
@@ -214,6 +231,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (TS) tma_prefetch_desc(&tmOut);
     if (TS && p.res_tma) tma_prefetch_desc(&tmRes);
+    if (GN && TS) {
+      tma_prefetch_desc(&tmV0);
+      if (p.gn_nver > 1) tma_prefetch_desc(&tmV1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -432,6 +453,310 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS +
                              (MT == 2 ? grp * BN : 0) + col0;
+      if constexpr (GN) {
+        // ======================= fused GroupNorm(+SiLU) of the output: two passes over the tile =======================
+        // pass 1  finish the tile (bias, conditioning, residual), write the raw output (if anything reads it) and the
+        //         GroupNorm partial sums of this warp's rows, and park the finished fp32 values back in tensor memory;
+        // sync    every warp holding a piece of the same image has written its partial sums (shared-memory barrier inside
+        //         the CTA; a self-resetting global counter when the image spans CTAs -- all CTAs of a persistent grid are
+        //         co-resident and the tile schedule puts the pieces of one image in the same iteration);
+        // table   the 8 epilogue warps reduce the partial sums (slot order: bit-reproducible, batch-invariant, the same
+        //         order as gn_apply_kernel) to mean / rstd per (image, group, version) in shared memory;
+        // pass 2  re-read the tile from tensor memory and write each normalised version (channel slice of its tensor).
+        const int C8 = p.Cout >> 3;
+        const bool full = ppi >= 32;
+        const bool raw = p.out != nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          const int cg = n_tile * BN + col0 + c0;
+          const bool box_start = TS && raw && (c0 % BOXC) == 0;
+          const bool box_end = TS && raw && ((c0 + 32) % BOXC) == 0;
+          const uint32_t bi = (TS && p.store_bufs == 2) ? (boxi & 1u) : 0u;
+          uint8_t* stg = my_stage + bi * 4096u;
+          uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
+          const bool res_tma = TS && raw && p.res_tma != 0;
+          if (box_start) {
+            if (lane == 0) {
+              if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (res_tma) {
+                mbar_expect_tx(rb, 4096);
+                tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+              }
+            }
+            __syncwarp();
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          float add[32];
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) add[j] = 0.f;
+          }
+          if (p.cond != nullptr && valid) {
+            const float4* c4 = reinterpret_cast<const float4*>(p.cond + static_cast<size_t>(n) * p.cond_stride + cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(c4 + j);
+              add[4 * j] += b.x; add[4 * j + 1] += b.y; add[4 * j + 2] += b.z; add[4 * j + 3] += b.w;
+            }
+          }
+          uint4 res[4];
+          const bool has_res = p.residual != nullptr && valid;
+          if (has_res && !res_tma) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = __ldg(r4 + j);
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + add[j];
+          if (res_tma) {
+            if (box_start) {
+              mbar_wait(rb, (rphase >> bi) & 1u);
+              rphase ^= 1u << bi;
+            }
+            const uint8_t* rowp = stg + lane * 128;
+            const int half = (c0 >> 5) & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4));
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(w[k]);
+                v[8 * j + 2 * k] += f.x;
+                v[8 * j + 2 * k + 1] += f.y;
+              }
+            }
+          } else if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(w[k]);
+                v[8 * j + 2 * k] += f.x;
+                v[8 * j + 2 * k + 1] += f.y;
+              }
+            }
+          }
+          // ---- raw output ----
+          if (raw) {
+            if (TS) {
+              uint8_t* rowp = stg + lane * 128;
+              const int half = (c0 >> 5) & 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = u;
+              }
+              if (box_end) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&tmOut, stg, cg + 32 - BOXC, sw0, sh0, sn0);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++boxi;
+              }
+            } else if (valid) {
+              uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                o4[j] = u;
+              }
+            }
+          }
+          // ---- GroupNorm partial sums of this warp's rows (same slots as the stand-alone consumers read) ----
+          {
+            float sv[8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float s_ = 0.f, ss_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s_ += v[8 * b + j];
+                ss_ = fmaf(v[8 * b + j], v[8 * b + j], ss_);
+              }
+              sv[b] = valid ? s_ : 0.f;
+              sv[4 + b] = valid ? ss_ : 0.f;
+            }
+            float tot;
+            int idx;
+            reduce8(sv, full, lane, tot, idx);
+            const bool writer = full ? ((lane & 3) == 0) : ((lane & 1) == 0);
+            if (writer && valid) {
+              const int wpi = ppi >> 5;
+              const int slot = p.stats_slot_base + (full ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
+              float* dst = p.stats + ((static_cast<size_t>(n) * p.stats_slots + slot) * C8 + ((cg >> 3) + (idx & 3))) * 2;
+              dst[idx >> 2] = tot;
+            }
+          }
+          // ---- park the finished values in tensor memory for pass 2 ----
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+          tmem_st_32x32(taddr + c0, r);
+        }
+        tmem_st_wait();
+        // ---- sync: every partial sum of the image(s) of this tile is in global memory ----
+        __threadfence();
+        if (p.gn_ctas_per_img > 1) {
+          __syncwarp();
+          if (lane == 0 && valid) {  // (BNIMG == 1 here: the whole warp belongs to image n)
+            int* cnt = p.gn_counters + 2 * (static_cast<size_t>(n) * p.num_n_tiles + n_tile);
+            const int expected = (EPI_THREADS / 32) * p.gn_ctas_per_img;
+            atomicAdd(cnt, 1);
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(cnt) < expected) {
+              __nanosleep(64);
+              if (++spins > (1u << 22)) {
+                printf("dmc: GroupNorm image counter timed out (block %d warp %d image %d)\n", (int)blockIdx.x, warp, n);
+                __trap();
+              }
+            }
+            // self-resetting: the last warp to get past the wait clears both words for the next launch
+            if (atomicAdd(cnt + 1, 1) == expected - 1) {
+              cnt[0] = 0;
+              cnt[1] = 0;
+            }
+          }
+          __syncwarp();
+        }
+        named_bar_sync(1, EPI_THREADS);
+        // ---- table: mean / rstd per (version, image of this tile, group) ----
+        float2* tab = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + GN_TAB_OFFSET) +
+                      acc * (2 * p.gn_imgs * p.gn_tab_groups);
+        {
+          const int n_first = ((ct * MTG + rank * MT) * TILE_M) / p.gn_P;  // first image of this CTA's rows
+          for (int ver = 0; ver < p.gn_nver; ++ver) {
+            const int gsz = p.gn_gsize[ver], ng = BN / gsz, nb = gsz >> 3;
+            for (int e = warp - 4; e < p.gn_imgs * ng; e += EPI_THREADS / 32) {
+              const int il = e / ng, g = e % ng;
+              const int n_e = n_first + il;
+              float s_ = 0.f, ss_ = 0.f;
+              if (n_e < p.B) {
+                const float2* base = reinterpret_cast<const float2*>(p.stats) +
+                                     static_cast<size_t>(n_e) * p.stats_slots * C8 + ((n_tile * BN + g * gsz) >> 3);
+                for (int i2 = lane; i2 < nb * p.stats_slots; i2 += 32) {
+                  const float2 t2 = __ldcg(base + static_cast<size_t>(i2 / nb) * C8 + i2 % nb);
+                  s_ += t2.x;
+                  ss_ += t2.y;
+                }
+              }
+#pragma unroll
+              for (int o = 16; o; o >>= 1) {
+                s_ += __shfl_xor_sync(0xFFFFFFFFu, s_, o);
+                ss_ += __shfl_xor_sync(0xFFFFFFFFu, ss_, o);
+              }
+              if (lane == 0) {
+                const float inv_cnt = 1.0f / (static_cast<float>(gsz) * static_cast<float>(p.gn_P));
+                const float mean = s_ * inv_cnt;
+                const float var = fmaxf(ss_ * inv_cnt - mean * mean, 0.f);
+                tab[(ver * p.gn_imgs + il) * p.gn_tab_groups + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+              }
+            }
+          }
+        }
+        named_bar_sync(1, EPI_THREADS);
+        // ---- pass 2: the normalised versions ----
+        const int il_row = p.gn_imgs > 1 ? (((MT == 2 ? grp : 0) * TILE_M + row) / p.gn_P) : 0;
+#pragma unroll 1
+        for (int ver = 0; ver < p.gn_nver; ++ver) {
+          const int gsz = p.gn_gsize[ver];
+          const float fold = p.gn_silu[ver] ? 0.5f : 1.0f;  // SiLU(y) = h + h tanh(h), h = y / 2: folded into scale / shift
+          const bool silu = p.gn_silu[ver] != 0;
+          const float2* trow = tab + (ver * p.gn_imgs + il_row) * p.gn_tab_groups;
+          const float* gam = p.gn_gamma[ver];
+          const float* bet = p.gn_beta[ver];
+          __nv_bfloat16* vout = p.gn_out[ver];
+          const int vpitch = p.gn_pitch[ver], vcoff = p.gn_coff[ver];
+          const CUtensorMap* tmv = ver == 0 ? &tmV0 : &tmV1;
+#pragma unroll 1
+          for (int c0 = 0; c0 < COLS; c0 += 32) {
+            const int cl = col0 + c0;  // first channel of this chunk inside the n tile
+            const int cg = n_tile * BN + cl;
+            const bool box_start = TS && (c0 % BOXC) == 0;
+            const bool box_end = TS && ((c0 + 32) % BOXC) == 0;
+            const uint32_t bi = (TS && p.store_bufs == 2) ? (boxi & 1u) : 0u;
+            uint8_t* stg = my_stage + bi * 4096u;
+            if (box_start) {
+              if (lane == 0) {
+                if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              __syncwarp();
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0, r);
+            const float2 m0 = trow[cl / gsz], m1 = trow[(cl + 16) / gsz];
+            float sc[32], sh[32];
+            {
+              const float4* g4 = reinterpret_cast<const float4*>(gam + cg);
+              const float4* b4 = reinterpret_cast<const float4*>(bet + cg);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 gv = __ldg(g4 + j), bv = __ldg(b4 + j);
+                const float2 m = j < 4 ? m0 : m1;
+                const float a0 = m.y * gv.x, a1 = m.y * gv.y, a2 = m.y * gv.z, a3 = m.y * gv.w;
+                sc[4 * j] = fold * a0; sc[4 * j + 1] = fold * a1; sc[4 * j + 2] = fold * a2; sc[4 * j + 3] = fold * a3;
+                sh[4 * j] = fold * (bv.x - m.x * a0); sh[4 * j + 1] = fold * (bv.y - m.x * a1);
+                sh[4 * j + 2] = fold * (bv.z - m.x * a2); sh[4 * j + 3] = fold * (bv.w - m.x * a3);
+              }
+            }
+            tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y0 = fmaf(__uint_as_float(r[2 * j]), sc[2 * j], sh[2 * j]);
+              float y1 = fmaf(__uint_as_float(r[2 * j + 1]), sc[2 * j + 1], sh[2 * j + 1]);
+              if (silu) {
+                y0 = silu_from_half(y0);
+                y1 = silu_from_half(y1);
+              }
+              o[j] = pack_bf16x2(y0, y1);
+            }
+            if (TS) {
+              uint8_t* rowp = stg + lane * 128;
+              const int half = (c0 >> 5) & 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) =
+                    make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              if (box_end) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(tmv, stg, vcoff + cg + 32 - BOXC, sw0, sh0, sn0);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++boxi;
+              }
+            } else if (valid) {
+              uint4* o4 = reinterpret_cast<uint4*>(vout + pix * vpitch + vcoff + cg);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+          }
+        }
+      } else
       if (!idle) {
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS; c0 += 32) {
@@ -734,7 +1059,7 @@ static int launch_variant(const ConvPrepared* P, const ConvKParams& kp, cudaStre
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DMC_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MT, CG, VAR>, P->tmA[0], P->tmA[1], P->tmA[2], P->tmS, P->tmB,
-                                 P->tmOut, P->tmRes, kp));
+                                 P->tmOut, P->tmRes, P->tmV[0], P->tmV[1], kp));
   return 0;
 }
 
@@ -760,9 +1085,22 @@ static int launch_tile_cfg(const ConvPrepared* P, const ConvKParams& kp, cudaStr
 #undef DMC_V
     default: break;
   }
+  if constexpr (BN >= 64) {  // fused GroupNorm epilogue (plain UNet convolutions only)
+    switch (P->var) {
+#define DMC_V(v) case (v): return launch_variant<BN, MT, CG, (v)>(P, kp, st)
+      DMC_V(VAR_GN);
+      DMC_V(VAR_GN | VAR_SLAB);
+      DMC_V(VAR_GN | VAR_BRES);
+#undef DMC_V
+      default: break;
+    }
+  }
   if constexpr (TSOK) {
     switch (P->var) {
 #define DMC_V(v) case (v): return launch_variant<BN, MT, CG, (v)>(P, kp, st)
+      DMC_V(VAR_GN | VAR_TS);
+      DMC_V(VAR_GN | VAR_TS | VAR_SLAB);
+      DMC_V(VAR_GN | VAR_TS | VAR_BRES);
       DMC_V(VAR_TS);
       DMC_V(VAR_TS | VAR_SLAB);
       DMC_V(VAR_TS | VAR_BRES);

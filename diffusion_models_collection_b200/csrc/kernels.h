@@ -46,6 +46,7 @@ struct ConvPrepared;
 int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out);
 void conv_release(ConvPrepared* p);
 int launch_conv(const dmc_conv_desc& d, const ConvPrepared* p, cudaStream_t st);
+bool conv_gn_supported(int B, int Hout, int Wout, int Cout, int max_gsz);
 // train_ops.cu : non-GEMM backward kernels
 uint32_t dropout_threshold(float p);
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st);

@@ -385,6 +385,8 @@ int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d) {
   for (int s = 0; s < d->nsrc; ++s) in_bytes += 2.0 * d->B * d->Hin * d->Win * d->src_c[s];
   op.bytes = in_bytes + 2.0 * static_cast<double>(d->Cout_pad) * d->Ktot + opix * d->Cout * (d->out_bf16 ? 2.0 : 4.0) +
              (d->residual ? 2.0 * opix * d->Cout : 0.0) + (d->residual_f32 ? 4.0 * opix * d->Cout : 0.0);
+  if (d->gn_nver > 0)  // fused GroupNorm: each normalised version is written once; the raw output only if requested
+    op.bytes += 2.0 * opix * d->Cout * (d->gn_nver - (d->out_bf16 ? 0 : 1));
   return push(p, op);
 }
 
@@ -431,6 +433,10 @@ int dmc_plan_add_ln_modulate(dmc_plan* p, const dmc_ln_mod_desc* d) {
   op.ln_mod = *d;
   op.bytes = 6.0 * d->B * static_cast<double>(d->L) * d->C;  // fp32 in, bf16 out
   return push(p, op);
+}
+
+int dmc_conv_gn_supported(int32_t B, int32_t Hout, int32_t Wout, int32_t Cout, int32_t max_gsize) {
+  return conv_gn_supported(B, Hout, Wout, Cout, max_gsize) ? 1 : 0;
 }
 
 int dmc_head_supported(const dmc_head_desc* d) { return (d != nullptr && head_fused_supported(*d)) ? 1 : 0; }

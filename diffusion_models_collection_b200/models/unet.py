@@ -99,13 +99,16 @@ class _Arena:
 
 
 class _Act:
-    """A bf16 NHWC activation [B, H, W, C] living in the plan workspace."""
+    """A bf16 NHWC activation [B, H, W, C] living in the plan workspace.  Offsets are assigned AFTER the op list is final
+    (_PlanBuilder._assign_memory): a tensor lives from the first op that touches it to the last one."""
 
-    __slots__ = ("blk", "lo", "C", "H", "W", "stats", "slots")
+    __slots__ = ("blk", "lo", "C", "H", "W", "stats", "slots", "nbytes", "split", "raw")
 
-    def __init__(self, blk, Cc, H, W, lo=None):
-        self.blk, self.lo, self.C, self.H, self.W = blk, lo, Cc, H, W  # lo: low parts in split-bf16 mode
+    def __init__(self, nbytes, Cc, H, W, split=False):
+        self.blk, self.lo, self.C, self.H, self.W = None, None, Cc, H, W  # lo: low parts in split-bf16 mode
         self.stats, self.slots = None, 0  # GroupNorm partial sums [B, slots, C/8, 2] fp32 (workspace block)
+        self.nbytes, self.split = nbytes, split
+        self.raw = True  # False: nothing reads the tensor itself (only its fused normalised versions): not stored
 
 
 class _PlanBuilder:
@@ -123,29 +126,135 @@ class _PlanBuilder:
 
     # -- workspace ---------------------------------------------------------------------------------
     def act(self, Cc, H, W):
-        n = self.B * H * W * Cc * 2
-        return _Act(self.arena.alloc(n), Cc, H, W, self.arena.alloc(n) if self.split else None)
+        return _Act(self.B * H * W * Cc * 2, Cc, H, W, self.split)
 
     def free(self, a: _Act):
-        if self.keep:
-            return
-        self.arena.release(a.blk)
-        if a.lo is not None:
-            self.arena.release(a.lo)
-        if a.stats is not None:
-            self.arena.release(a.stats)
+        """(lifetimes are derived from the final op list in _assign_memory; kept as a no-op marker of the topology)"""
 
     def _alloc_stats(self, a: _Act, slots):
         a.slots = slots
-        a.stats = self.arena.alloc(self.B * slots * (a.C // 8) * 2 * 4)
 
     def stats_of(self, a: _Act):
         """GroupNorm partial sums of `a`: written by the producing conv's epilogue when it has one, else by a
         stand-alone pass (stem output; every tensor when the CUDA-core debug conv is selected)."""
-        if a.stats is None:
+        if a.slots == 0:
             self._alloc_stats(a, (a.H * a.W + 127) // 128)
             self.ops.append(("gn_stats", dict(src=a)))
         return a
+
+    # -- op list post-passes -----------------------------------------------------------------------------
+    @staticmethod
+    def _touched(kind, o):
+        """activations an op reads or writes"""
+        if kind in ("stem", "gn_stats", "head"):
+            return [o.get("out") or o.get("src")]
+        if kind == "gn_apply":
+            return list(o["srcs"]) + [o["out"]]
+        if kind == "conv":
+            t = list(o["srcs"])
+            if o["residual"] is not None:
+                t.append(o["residual"])
+            if o["out"] is not None:
+                t.append(o["out"])
+            t += [v["dst"] for v in o.get("gn", ())]
+            return t
+        if kind == "attention":
+            return [o["qkv"], o["out"]]
+        if kind == "upsample":
+            return [o["src"], o["out"]]
+        return []
+
+    def _fuse_groupnorm(self):
+        """Moves GroupNorm(+SiLU) passes into the epilogue of the convolution that produces their input (north_star:
+        "GroupNorm+SiLU ... fused into the conv prologue/epilogue"; models/unet.py:35-36,51-52,80,238-239).  A gn_apply op
+        disappears when EVERY source is the output of one tcgen05 convolution whose tile geometry can complete the statistics
+        in its epilogue (dmc_conv_gn_supported), no statistics group straddles two sources of a concat (models/unet.py:284) and
+        the producer has fewer than two fused versions already; that convolution then writes the normalised tensor (its channel
+        slice of the concat) itself.  What stays a stand-alone pass: inputs produced by the stem, by the four Upsample phase
+        convolutions (four launches write one tensor) and the 384-channel concats whose 48-channel groups straddle."""
+        lib = _lib.load()
+        producer = {}
+        writers = {}
+        for i, (kind, o) in enumerate(self.ops):
+            if kind == "conv" and o["out"] is not None:
+                writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 1
+                producer[id(o["out"])] = i
+            elif kind in ("stem", "upsample", "attention", "gn_apply"):
+                writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 99
+        drop = set()
+        for gi, (kind, g) in enumerate(self.ops):
+            if kind != "gn_apply" or g["drop_p"] > 0:
+                continue
+            ct = sum(s_.C for s_ in g["srcs"])
+            gsz = ct // 8
+            if gsz not in (16, 32, 64):
+                continue
+            plan, off, ok = [], 0, True
+            for s_ in g["srcs"]:
+                pi = producer.get(id(s_))
+                if pi is None or writers.get(id(s_)) != 1 or off % gsz or s_.C % gsz:
+                    ok = False
+                    break
+                po = self.ops[pi][1]
+                pend = sum(1 for q_ in plan if q_[0] is po)
+                if (po["out_nchw"] or po["up_phase"] >= 0 or not po["want_stats"] or len(po.get("gn", ())) + pend >= 2 or
+                        not lib.dmc_conv_gn_supported(self.B, s_.H, s_.W, s_.C, max([gsz] + [v["gsize"] for v in po.get("gn", ())]))):
+                    ok = False
+                    break
+                plan.append((po, off, s_))
+                off += s_.C
+            if not ok:
+                continue
+            for po, off, s_ in plan:
+                po.setdefault("gn", []).append(dict(dst=g["out"], coff=off, prefix=g["prefix"], gsize=gsz, silu=g["silu"]))
+            drop.add(gi)
+        if not drop:
+            return
+        self.ops = [op for i, op in enumerate(self.ops) if i not in drop]
+        # a raw output nothing reads any more (e.g. conv1 of a ResidualBlock: only its normalised version is consumed) is not stored
+        read = set()
+        for kind, o in self.ops:
+            if kind == "conv":
+                read.update(id(s_) for s_ in o["srcs"])
+                if o["residual"] is not None:
+                    read.add(id(o["residual"]))
+            elif kind == "gn_apply":
+                read.update(id(s_) for s_ in o["srcs"])
+            elif kind in ("gn_stats", "head", "upsample"):
+                read.add(id(o["src"]))
+            elif kind == "attention":
+                read.add(id(o["qkv"]))
+        for kind, o in self.ops:
+            if kind == "conv" and o.get("gn") and o["out"] is not None and id(o["out"]) not in read:
+                o["out"].raw = False
+
+    def _assign_memory(self):
+        """workspace offsets from lifetimes: every activation (with its statistics block) is allocated right before the first op
+        that touches it and released right after the last one (stream order makes reuse safe); training plans keep everything"""
+        first, last, acts = {}, {}, {}
+        for i, (kind, o) in enumerate(self.ops):
+            for a in self._touched(kind, o):
+                first.setdefault(id(a), i)
+                last[id(a)] = i
+                acts[id(a)] = a
+        begin, end = {}, {}
+        for k, a in acts.items():
+            begin.setdefault(first[k], []).append(a)
+            end.setdefault(last[k], []).append(a)
+        for i in range(len(self.ops)):
+            for a in begin.get(i, ()):
+                if a.raw:
+                    a.blk = self.arena.alloc(a.nbytes)
+                    if a.split:
+                        a.lo = self.arena.alloc(a.nbytes)
+                if a.slots:
+                    a.stats = self.arena.alloc(self.B * a.slots * (a.C // 8) * 2 * 4)
+            if self.keep:
+                continue
+            for a in end.get(i, ()):
+                for blk in (a.blk, a.lo, a.stats):
+                    if blk is not None:
+                        self.arena.release(blk)
 
     # -- layers --------------------------------------------------------------------------------------
     def gn_apply(self, srcs, prefix, silu):
@@ -164,7 +273,7 @@ class _PlanBuilder:
             Ho, Wo = 2 * H, 2 * W
         if out is None and not out_nchw:
             out = self.act(Cout, Ho, Wo)
-        if out is not None and want_stats and self.conv_impl == 0 and out.stats is None:
+        if out is not None and want_stats and self.conv_impl == 0 and out.slots == 0:
             ppi = (H // stride) * (W // stride)  # iteration pixels per image: one slot per 32-pixel epilogue warp
             self._alloc_stats(out, max(1, ppi // 32) * (4 if up_phase >= 0 else 1))
         parts = ["hi"] * len(srcs)
@@ -283,6 +392,9 @@ class _PlanBuilder:
             self.conv([a], [9], "output.2", net.out_channels, H, W, bias="output.2", out_nchw=True, want_stats=False)
             self.free(a)
         self.ncols = col
+        if self.net.fuse_groupnorm and not (self.split or self.keep or self.conv_impl != 0):
+            self._fuse_groupnorm()
+        self._assign_memory()
         return self
 
 
@@ -295,6 +407,9 @@ class UNet(nn.Module):
     # output GroupNorm + SiLU + conv as one mma.sync kernel: opt-in -- measured 0.725 ms against 0.20 + 0.53 ms for the
     # two-kernel path at 2048 images (legacy mma.sync issues ~1 per 80 clk per SM sub-partition on sm_100a), no gain
     fuse_head = os.environ.get("DMC_FUSED_HEAD", "0") != "0"
+    # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
+    # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
+    fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
 
     def __init__(self, image_size: Tuple[int, int] = (32, 32), in_channels=3, model_channels=128, out_channels=3,
                  num_res_blocks=2, attention_resolutions=(16, 8), dropout=0.1, channel_mult=(1, 2, 2, 2),
@@ -855,6 +970,8 @@ class _UNetPlan:
             return idx
 
         self.stem_idx = self.cond_idx = self.head_idx = -1
+        self.gn_counters = []
+        self.fused_gn = sum(len(o.get("gn", ())) for kind, o in b.ops if kind == "conv")  # normalised versions written by convs
         for kind, o in b.ops:
             self.op_index.append(len(self.op_names))
             if kind == "cond":
@@ -918,11 +1035,22 @@ class _UNetPlan:
                 d.residual_lo = ap_lo(o["residual"]) if o["residual"] is not None else None
                 if o["out_nchw"]:
                     d.out_f32_nchw = self.eps.data_ptr()
-                else:
+                elif o["out"].raw:
                     d.out_bf16, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 d.impl = conv_impl
                 if conv_impl == 0 and o["out"] is not None and o["out"].stats is not None and o["want_stats"]:
                     d.stats, d.stats_slots = wsp + o["out"].stats[0], o["out"].slots
+                gn = o.get("gn", ())
+                if gn:  # GroupNorm(+SiLU) of this output, applied by this convolution's epilogue for its consumer(s)
+                    d.gn_nver, d.gn_eps = len(gn), 1e-5
+                    for vi, v in enumerate(gn):
+                        d.gn_out[vi], d.gn_pitch[vi], d.gn_coff[vi] = ap(v["dst"]), v["dst"].C, v["coff"]
+                        d.gn_gamma[vi] = sd[v["prefix"] + ".weight"].data_ptr() + 4 * v["coff"]
+                        d.gn_beta[vi] = sd[v["prefix"] + ".bias"].data_ptr() + 4 * v["coff"]
+                        d.gn_gsize[vi], d.gn_silu[vi] = v["gsize"], v["silu"]
+                    cnt = torch.zeros(2 * nimg * max(1, o["Cout"] // 64), dtype=torch.int32, device=device)
+                    self.gn_counters.append(cnt)  # self-resetting image counters (images that span several CTAs)
+                    d.gn_counters = cnt.data_ptr()
                 idx = add(lib.dmc_plan_add_conv, d, o["wname"])
                 if o["out_nchw"]:
                     self.head_idx = idx

@@ -394,8 +394,31 @@ typedef struct {
   int32_t unpatch_p;          /* > 0 with out_f32_nchw: columns are (pi, qi, c) of a p x p patch and pixel (i, j) of image n
                                  scatters to out[n, c, i*p + pi, j*p + qi] -- DiT.unpatchify (models/dit.py:249-261);
                                  Cout = p * p * channels */
+  /* --- GroupNorm(+SiLU) of the OUTPUT fused into this convolution's epilogue (models/unet.py:35-36,51-52,80,238-239: the
+   * normalisation the NEXT layer applies to this tensor).  The epilogue keeps the finished fp32 tile in tensor memory, writes
+   * the GroupNorm partial sums of the output (`stats`, required), waits until every CTA holding a piece of the same image has
+   * done so (shared-memory barrier inside a CTA, a self-resetting counter in `gn_counters` across CTAs), reduces them to
+   * mean / rstd in slot order (bit-reproducible, batch-invariant) and writes up to two normalised versions
+   *     gn_out[v][n, pixel, gn_coff[v] + c] = act_v((x - mean_g) * rstd_g * gn_gamma[v][c] + gn_beta[v][c])
+   * straight from the fp32 accumulator.  A version may be a channel slice of a wider tensor (the torch.cat of
+   * models/unet.py:284 is then free): gn_pitch[v] is that tensor's channel count, gn_gsize[v] the channels per statistics group
+   * (C_total / 8 of the consumer's GroupNorm; groups must not straddle this tensor).  out_bf16 may be NULL when nothing reads
+   * the raw output.  Supported when dmc_conv_gn_supported() says so. --- */
+  int32_t gn_nver;            /* 0 (no fused GroupNorm), 1 or 2 */
+  void* gn_out[2];            /* bf16 NHWC [B, Hout, Wout, gn_pitch[v]] */
+  int32_t gn_pitch[2];
+  int32_t gn_coff[2];         /* first channel of this tensor inside gn_out[v] */
+  const float* gn_gamma[2];   /* [Cout]: the consumer GroupNorm's weight / bias rows of THIS tensor's channels */
+  const float* gn_beta[2];
+  int32_t gn_gsize[2];        /* 16, 32 or 64 */
+  int32_t gn_silu[2];
+  float gn_eps;
+  int32_t* gn_counters;       /* int32 [2 * B * (Cout / 32)] zeroed once by the caller (only touched when an image spans CTAs) */
 } dmc_conv_desc;
 DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
+/* 1 when some tile configuration of the tcgen05 kernel can fuse the GroupNorm of a [B, Hout, Wout, Cout] output whose largest
+ * statistics group has max_gsize channels (pure geometry: no pointers, no device), else 0 (use dmc_plan_add_gn_apply) */
+DMC_API int dmc_conv_gn_supported(int32_t B, int32_t Hout, int32_t Wout, int32_t Cout, int32_t max_gsize);
 
 /* Output head, fused: GroupNorm(groups, C) + SiLU + 3x3 convolution C -> Cout (<= 8) + bias, written as the fp32 NCHW
  * model output (models/unet.py:237-241,287-292).  One read of the activation; replaces a gn_apply + a padded-N conv. */

@@ -361,6 +361,41 @@ def test_split_bf16_mode_cfg_sampling_and_batch_invariance():
     assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("case", ["cond_labels", "small_cond"])
+def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(golden, case, monkeypatch):
+    """the default plan applies GroupNorm(+SiLU) in the epilogue of the producing convolution (50 of the 56 passes of the CIFAR
+    UNet); DMC_FUSE_GN=0 / UNet.fuse_groupnorm=False keeps every stand-alone gn_apply pass.  Both are within the bf16 gate of
+    the reference golden, and the fused plan is at least as close (it normalises the fp32 accumulator, not its bf16 rounding)."""
+    from diffusion_models_collection_b200.models import UNet
+
+    c = UNET_CASES[case]
+    cfg = SMALL_UNET if c.get("small") else synth.CIFAR_UNET
+    x, t, y = case_inputs(c)
+    net = build_unet(cfg, c["num_classes"], c["wseed"])
+    assert net.fuse_groupnorm
+    with torch.no_grad():
+        a = net(x.cuda(), t.cuda(), y.cuda())
+    names_a = net.plan_info(x.shape[0]).op_names
+    monkeypatch.setattr(UNet, "fuse_groupnorm", False)
+    net2 = build_unet(cfg, c["num_classes"], c["wseed"])
+    with torch.no_grad():
+        b = net2(x.cuda(), t.cuda(), y.cuda())
+    names_b = net2.plan_info(x.shape[0]).op_names
+    n_gn = lambda names: sum(1 for n_ in names if n_.endswith((".conv1.0", ".conv2.0", ".norm", "output.0")))  # noqa: E731
+    assert n_gn(names_a) < n_gn(names_b)
+    if not c.get("small"):
+        assert n_gn(names_b) == 56 and n_gn(names_a) == 6
+        assert net.plan_info(x.shape[0]).fused_gn == 57
+    ref = torch.from_numpy(golden["unet"][case])
+    ea, eb = rel_l2(a, ref), rel_l2(b, ref)
+    print(f"{case}: eps rel-L2 fused {ea:.3e} unfused {eb:.3e}; fused vs unfused {rel_l2(a, b):.3e}")
+    import os
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/eps_errors.txt", "a") as fh:
+            fh.write(f"gn_fused_{case} {ea:.4e} (unfused {eb:.4e})\n")
+    assert ea < TOL_EPS_BF16 and eb < TOL_EPS_BF16 and rel_l2(a, b) < 1.5e-2
+
+
 def test_fused_head_path_matches_two_kernel_path(monkeypatch):
     """the opt-in fused output head (GroupNorm + SiLU + conv3x3 in one kernel) vs the default gn_apply + conv path"""
     from diffusion_models_collection_b200.models import UNet
