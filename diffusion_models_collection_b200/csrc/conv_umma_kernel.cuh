@@ -455,34 +455,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                              (MT == 2 ? grp * BN : 0) + col0;
       if constexpr (GN) {
         // ======================= fused GroupNorm(+SiLU) of the output: two passes over the tile =======================
-        // pass 1  finish the tile (bias, conditioning, residual), write the raw output (if anything reads it) and the
-        //         GroupNorm partial sums of this warp's rows, and park the finished fp32 values back in tensor memory;
-        // sync    every warp holding a piece of the same image has written its partial sums (shared-memory barrier inside
-        //         the CTA; a self-resetting global counter when the image spans CTAs -- all CTAs of a persistent grid are
-        //         co-resident and the tile schedule puts the pieces of one image in the same iteration);
+        // pass 1  finish the tile (bias, conditioning, residual), write the GroupNorm partial sums of this warp's rows and
+        //         park the finished fp32 values back in tensor memory -- NO bulk stores yet: the hand-shake below must
+        //         not wait behind a tile's worth of output traffic;
+        // sync    every warp holding a piece of the same image has written its partial sums: a named barrier inside the
+        //         CTA; a release-add / acquire-poll on a self-resetting global counter when the image spans CTAs (all
+        //         CTAs of a persistent grid are co-resident; the tile schedule puts the pieces of one image in the same
+        //         iteration);
         // table   the 8 epilogue warps reduce the partial sums (slot order: bit-reproducible, batch-invariant, the same
         //         order as gn_apply_kernel) to mean / rstd per (image, group, version) in shared memory;
-        // pass 2  re-read the tile from tensor memory and write each normalised version (channel slice of its tensor).
+        // pass 2  re-read the tile from tensor memory: the raw output (when something reads it) and each normalised
+        //         version (a channel slice of its tensor).
         const int C8 = p.Cout >> 3;
         const bool full = ppi >= 32;
         const bool raw = p.out != nullptr;
+        const bool res_tma = TS && p.res_tma != 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS; c0 += 32) {
           const int cg = n_tile * BN + col0 + c0;
-          const bool box_start = TS && raw && (c0 % BOXC) == 0;
-          const bool box_end = TS && raw && ((c0 + 32) % BOXC) == 0;
+          const bool box_start = res_tma && (c0 % BOXC) == 0;
           const uint32_t bi = (TS && p.store_bufs == 2) ? (boxi & 1u) : 0u;
           uint8_t* stg = my_stage + bi * 4096u;
           uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
-          const bool res_tma = TS && raw && p.res_tma != 0;
-          if (box_start) {
+          if (box_start) {  // residual box: coalesced, asynchronous, lands in a staging buffer no TMA store is reading
             if (lane == 0) {
               if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
               else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              if (res_tma) {
-                mbar_expect_tx(rb, 4096);
-                tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
-              }
+              mbar_expect_tx(rb, 4096);
+              tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
             }
             __syncwarp();
           }
@@ -537,6 +537,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 v[8 * j + 2 * k + 1] += f.y;
               }
             }
+            if (((c0 + 32) % BOXC) == 0) ++boxi;  // this residual box is consumed: the next one takes the other buffer
           } else if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -546,42 +547,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const float2 f = unpack_bf16x2(w[k]);
                 v[8 * j + 2 * k] += f.x;
                 v[8 * j + 2 * k + 1] += f.y;
-              }
-            }
-          }
-          // ---- raw output ----
-          if (raw) {
-            if (TS) {
-              uint8_t* rowp = stg + lane * 128;
-              const int half = (c0 >> 5) & 1;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = u;
-              }
-              if (box_end) {
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  tma_store_4d(&tmOut, stg, cg + 32 - BOXC, sw0, sh0, sn0);
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                ++boxi;
-              }
-            } else if (valid) {
-              uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cg);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                o4[j] = u;
               }
             }
           }
@@ -607,7 +572,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const int wpi = ppi >> 5;
               const int slot = p.stats_slot_base + (full ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
               float* dst = p.stats + ((static_cast<size_t>(n) * p.stats_slots + slot) * C8 + ((cg >> 3) + (idx & 3))) * 2;
-              dst[idx >> 2] = tot;
+              __stcg(dst + (idx >> 2), tot);
             }
           }
           // ---- park the finished values in tensor memory for pass 2 ----
@@ -617,16 +582,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         tmem_st_wait();
         // ---- sync: every partial sum of the image(s) of this tile is in global memory ----
-        __threadfence();
         if (p.gn_ctas_per_img > 1) {
           __syncwarp();
           if (lane == 0 && valid) {  // (BNIMG == 1 here: the whole warp belongs to image n)
             int* cnt = p.gn_counters + 2 * (static_cast<size_t>(n) * p.num_n_tiles + n_tile);
             const int expected = (EPI_THREADS / 32) * p.gn_ctas_per_img;
-            atomicAdd(cnt, 1);
+            // release: the partial sums of all lanes (ordered before this by __syncwarp) are visible to whoever sees the count
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
             uint32_t spins = 0;
             while (ld_acquire_gpu(cnt) < expected) {
-              __nanosleep(64);
+              __nanosleep(20);
               if (++spins > (1u << 22)) {
                 printf("dmc: GroupNorm image counter timed out (block %d warp %d image %d)\n", (int)blockIdx.x, warp, n);
                 __trap();
@@ -676,19 +641,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         named_bar_sync(1, EPI_THREADS);
-        // ---- pass 2: the normalised versions ----
+        // ---- pass 2: the raw output (ver == -1) and the normalised versions ----
         const int il_row = p.gn_imgs > 1 ? (((MT == 2 ? grp : 0) * TILE_M + row) / p.gn_P) : 0;
 #pragma unroll 1
-        for (int ver = 0; ver < p.gn_nver; ++ver) {
-          const int gsz = p.gn_gsize[ver];
-          const float fold = p.gn_silu[ver] ? 0.5f : 1.0f;  // SiLU(y) = h + h tanh(h), h = y / 2: folded into scale / shift
-          const bool silu = p.gn_silu[ver] != 0;
-          const float2* trow = tab + (ver * p.gn_imgs + il_row) * p.gn_tab_groups;
-          const float* gam = p.gn_gamma[ver];
-          const float* bet = p.gn_beta[ver];
-          __nv_bfloat16* vout = p.gn_out[ver];
-          const int vpitch = p.gn_pitch[ver], vcoff = p.gn_coff[ver];
-          const CUtensorMap* tmv = ver == 0 ? &tmV0 : &tmV1;
+        for (int ver = raw ? -1 : 0; ver < p.gn_nver; ++ver) {
+          const int vi = ver < 0 ? 0 : ver;
+          const int gsz = p.gn_gsize[vi];
+          const bool norm = ver >= 0;
+          const bool silu = norm && p.gn_silu[vi] != 0;
+          const float fold = silu ? 0.5f : 1.0f;  // SiLU(y) = h + h tanh(h), h = y / 2: folded into scale / shift
+          const float2* trow = tab + (vi * p.gn_imgs + il_row) * p.gn_tab_groups;
+          const float* gam = p.gn_gamma[vi];
+          const float* bet = p.gn_beta[vi];
+          __nv_bfloat16* vout = norm ? p.gn_out[vi] : p.out;
+          const int vpitch = norm ? p.gn_pitch[vi] : p.Cout, vcoff = norm ? p.gn_coff[vi] : 0;
+          const CUtensorMap* tmv = !norm ? &tmOut : (ver == 0 ? &tmV0 : &tmV1);
 #pragma unroll 1
           for (int c0 = 0; c0 < COLS; c0 += 32) {
             const int cl = col0 + c0;  // first channel of this chunk inside the n tile
@@ -706,9 +673,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             uint32_t r[32];
             tmem_ld_32x32(taddr + c0, r);
-            const float2 m0 = trow[cl / gsz], m1 = trow[(cl + 16) / gsz];
-            float sc[32], sh[32];
-            {
+            uint32_t o[16];
+            if (norm) {
+              const float2 m0 = trow[cl / gsz], m1 = trow[(cl + 16) / gsz];
+              float sc[32], sh[32];
               const float4* g4 = reinterpret_cast<const float4*>(gam + cg);
               const float4* b4 = reinterpret_cast<const float4*>(bet + cg);
 #pragma unroll
@@ -720,18 +688,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 sh[4 * j] = fold * (bv.x - m.x * a0); sh[4 * j + 1] = fold * (bv.y - m.x * a1);
                 sh[4 * j + 2] = fold * (bv.z - m.x * a2); sh[4 * j + 3] = fold * (bv.w - m.x * a3);
               }
-            }
-            tmem_ld_wait();
-            uint32_t o[16];
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float y0 = fmaf(__uint_as_float(r[2 * j]), sc[2 * j], sh[2 * j]);
-              float y1 = fmaf(__uint_as_float(r[2 * j + 1]), sc[2 * j + 1], sh[2 * j + 1]);
-              if (silu) {
-                y0 = silu_from_half(y0);
-                y1 = silu_from_half(y1);
+              for (int j = 0; j < 16; ++j) {
+                float y0 = fmaf(__uint_as_float(r[2 * j]), sc[2 * j], sh[2 * j]);
+                float y1 = fmaf(__uint_as_float(r[2 * j + 1]), sc[2 * j + 1], sh[2 * j + 1]);
+                if (silu) {
+                  y0 = silu_from_half(y0);
+                  y1 = silu_from_half(y1);
+                }
+                o[j] = pack_bf16x2(y0, y1);
               }
-              o[j] = pack_bf16x2(y0, y1);
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
             }
             if (TS) {
               uint8_t* rowp = stg + lane * 128;

@@ -197,6 +197,10 @@ class _PlanBuilder:
                     break
                 po = self.ops[pi][1]
                 pend = sum(1 for q_ in plan if q_[0] is po)
+                kblocks = sum(t_ * a_.C for t_, a_ in zip(po["taps"], po["srcs"])) // 64
+                if kblocks < self.net.fuse_gn_min_kblocks:  # short K loop: the two-pass epilogue would outlast the tile's MMAs
+                    ok = False
+                    break
                 if (po["out_nchw"] or po["up_phase"] >= 0 or not po["want_stats"] or len(po.get("gn", ())) + pend >= 2 or
                         not lib.dmc_conv_gn_supported(self.B, s_.H, s_.W, s_.C, max([gsz] + [v["gsize"] for v in po.get("gn", ())]))):
                     ok = False
@@ -410,6 +414,9 @@ class UNet(nn.Module):
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
+    # ... only into convolutions whose K loop has at least this many 64-element blocks: the epilogue of tile k (two passes +
+    # the statistics hand-shake) overlaps the MMAs of tile k+1, which a 1x1 convolution (4 - 8 blocks) finishes long before
+    fuse_gn_min_kblocks = int(os.environ.get("DMC_FUSE_GN_MIN_KB", "16"))
 
     def __init__(self, image_size: Tuple[int, int] = (32, 32), in_channels=3, model_channels=128, out_channels=3,
                  num_res_blocks=2, attention_resolutions=(16, 8), dropout=0.1, channel_mult=(1, 2, 2, 2),

@@ -341,8 +341,9 @@ def gen_config1():
         out["eps0"] = net(xT, torch.full((16,), 999, dtype=torch.long)).numpy()
     names = [k for k, _ in net.state_dict().items()]
     out["weight_names"] = np.array(names)
-    out["weight_sums"] = np.array([float(v.double().sum()) for v in net.state_dict().values()])
-    out["weight_abs_sums"] = np.array([float(v.double().abs().sum()) for v in net.state_dict().values()])
+    # exact, order-independent checksums (integer sums of the fp32 bit patterns): a floating-point .sum() depends on the SIMD
+    # width of the host CPU and differed between the build container and the GPU box for IDENTICAL weights
+    out["weight_isums"] = np.array([int(v.contiguous().view(torch.int32).to(torch.int64).sum()) for v in net.state_dict().values()])
     np.savez_compressed(os.path.join(HERE, "config1_golden.npz"), **out)
     print("config1", tuple(traj.shape), float(traj[-1].abs().max()), float(traj[-1].std()), "eps0 std", float(out["eps0"].std()))
 

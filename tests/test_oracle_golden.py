@@ -207,7 +207,8 @@ def test_config1_b16_oracle_matches_reference_golden():
     weights seed 42, checksums stored next to the golden)"""
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_golden.npz"))
     sd = synth.make_unet_state_dict(None, None, seed=42)
-    assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["weight_sums"])
+    assert np.array_equal(np.array([int(v.contiguous().view(torch.int32).to(torch.int64).sum()) for v in sd.values()]),
+                          g["weight_isums"])
     x = torch.from_numpy(g["xT"])
     eps = model_oracle.unet_forward(sd, synth.CIFAR_UNET, x, torch.full((16,), 999, dtype=torch.long), None, num_classes=None)
     ref_eps = torch.from_numpy(g["eps0"])
