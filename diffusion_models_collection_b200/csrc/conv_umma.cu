@@ -235,6 +235,10 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     kp.gn_tab_groups = BN / gn_min_gsz;
     kp.gn_eps = d.gn_eps;
     kp.gn_counters = d.gn_counters;
+    {
+      const char* e = getenv("DMC_GN_DEBUG");
+      kp.gn_debug = (e && e[0]) ? atoi(e) : 0;
+    }
     for (int v = 0; v < d.gn_nver; ++v) {
       kp.gn_out[v] = reinterpret_cast<__nv_bfloat16*>(d.gn_out[v]);
       kp.gn_pitch[v] = d.gn_pitch[v]; kp.gn_coff[v] = d.gn_coff[v]; kp.gn_gsize[v] = d.gn_gsize[v]; kp.gn_silu[v] = d.gn_silu[v];

@@ -64,6 +64,8 @@ struct ConvKParams {
   int gn_ctas_per_img;        // CTAs holding pieces of one image (1: the shared-memory barrier is the only hand-shake)
   int gn_tab_groups;          // table columns per version (BN / smallest group size)
   int* gn_counters;           // [image * num_n_tiles + n_tile][arrived, done]
+  int gn_debug;               // DMC_GN_DEBUG (timing experiments only, results are WRONG): 1 no cross-CTA wait, 2 no pass 2,
+                              // 4 no table, 8 no park-in-TMEM
   float gn_eps;
   __nv_bfloat16* gn_out[2];
   int gn_pitch[2], gn_coff[2], gn_gsize[2], gn_silu[2];
@@ -578,11 +580,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           // ---- park the finished values in tensor memory for pass 2 ----
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-          tmem_st_32x32(taddr + c0, r);
+          if (!(p.gn_debug & 8)) tmem_st_32x32(taddr + c0, r);
         }
         tmem_st_wait();
         // ---- sync: every partial sum of the image(s) of this tile is in global memory ----
-        if (p.gn_ctas_per_img > 1) {
+        if (p.gn_ctas_per_img > 1 && !(p.gn_debug & 1)) {
           __syncwarp();
           if (lane == 0 && valid) {  // (BNIMG == 1 here: the whole warp belongs to image n)
             int* cnt = p.gn_counters + 2 * (static_cast<size_t>(n) * p.num_n_tiles + n_tile);
@@ -609,7 +611,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- table: mean / rstd per (version, image of this tile, group) ----
         float2* tab = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + GN_TAB_OFFSET) +
                       acc * (2 * p.gn_imgs * p.gn_tab_groups);
-        {
+        if (!(p.gn_debug & 4)) {
           const int n_first = ((ct * MTG + rank * MT) * TILE_M) / p.gn_P;  // first image of this CTA's rows
           for (int ver = 0; ver < p.gn_nver; ++ver) {
             const int gsz = p.gn_gsize[ver], ng = BN / gsz, nb = gsz >> 3;
@@ -644,7 +646,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- pass 2: the raw output (ver == -1) and the normalised versions ----
         const int il_row = p.gn_imgs > 1 ? (((MT == 2 ? grp : 0) * TILE_M + row) / p.gn_P) : 0;
 #pragma unroll 1
-        for (int ver = raw ? -1 : 0; ver < p.gn_nver; ++ver) {
+        for (int ver = raw ? -1 : 0; ver < ((p.gn_debug & 2) ? 0 : p.gn_nver); ++ver) {
           const int vi = ver < 0 ? 0 : ver;
           const int gsz = p.gn_gsize[vi];
           const bool norm = ver >= 0;

@@ -23,9 +23,14 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# max-abs deviation of the free-running state after h steps, fp32-accuracy mode: 3x the values measured on B200 (round 2)
-FREE_RUN_GATES_X3 = {1: 3e-4, 2: 1e-3, 3: 3e-3}
-FREE_RUN_GATES_BF16 = {1: 5e-2}
+# max-abs deviation (16 x 3072 values) of the free-running state from the reference's own state after h steps: gates = 3x the
+# values measured on B200 (round 2, profiles/r02_eps_errors_run3.txt):
+#   split-bf16 ("bf16x3", per-step eps error 1.6e-5):  h = 1: 3.0e-5, 2: 5.9e-5, 3: 9.8e-5, 5: 3.7e-4, 10: 4.3e-3, 20: 0.37, 50: 1.93
+#   bf16 (per-step eps error 6.2e-3):                  h = 1: 1.0e-2, 2: 2.2e-2, 3: 4.3e-2, 5: 0.12,   10: 1.34,   20: 2.8,  50: 2.0
+# The deviation grows ~10x every 5 steps whatever the precision: beyond ~15 steps it has saturated at the clamp range, exactly
+# like the reference against itself (tests/chaos_probe.py).  Horizons past the gated ones are recorded, not asserted.
+FREE_RUN_GATES_X3 = {1: 1e-4, 2: 2e-4, 3: 3e-4, 5: 1.2e-3, 10: 1.3e-2}
+FREE_RUN_GATES_BF16 = {1: 3e-2, 2: 7e-2, 3: 1.3e-1, 5: 3.6e-1}
 
 
 def _reference_weights(g):
