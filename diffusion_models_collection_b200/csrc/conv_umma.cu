@@ -244,7 +244,8 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
       kp.gn_pitch[v] = d.gn_pitch[v]; kp.gn_coff[v] = d.gn_coff[v]; kp.gn_gsize[v] = d.gn_gsize[v]; kp.gn_silu[v] = d.gn_silu[v];
       kp.gn_gamma[v] = d.gn_gamma[v]; kp.gn_beta[v] = d.gn_beta[v];
     }
-    gn_tab_bytes = 2 /*accumulator stages*/ * 2 /*versions*/ * kp.gn_imgs * kp.gn_tab_groups * 8;
+    gn_tab_bytes = 2 /*versions*/ * kp.gn_imgs * kp.gn_tab_groups * 8;
+    kp.gn_sc_smem = 0;
     if (kp.gn_ctas_per_img > 1 && d.gn_counters == nullptr) {
       delete P;
       DMC_REQUIRE(false, "conv: fused GroupNorm of a %d-pixel image spans %d CTAs: gn_counters is required", gn_P, kp.gn_ctas_per_img);
@@ -370,6 +371,20 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     };
     int nst1 = 0, nst2 = 0;
     int fixed = plan(1, &nst1);
+    if (gn && kp.gn_imgs == 1 && env_flag("DMC_GN_SC_SMEM", 1)) {
+      // per-channel (scale, shift) of the tile's image in shared memory, computed once per tile instead of once per thread --
+      // when it costs no ring stage
+      const int sc_bytes = 2 * BN * 8;
+      gn_tab_bytes += sc_bytes;
+      int nst_sc = 0;
+      const int fixed_sc = plan(1, &nst_sc);
+      if (nst_sc == nst1) {
+        kp.gn_sc_smem = 1;
+        fixed = fixed_sc;
+      } else {
+        gn_tab_bytes -= sc_bytes;
+      }
+    }
     kp.nst = nst1;
     if (kp.tma_store && env_flag("DMC_CONV_STORE_BUFS", 2) == 2) {  // a second staging buffer per warp, if the ring can spare it
       const int fixed2 = plan(2, &nst2);

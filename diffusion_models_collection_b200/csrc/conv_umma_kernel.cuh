@@ -63,6 +63,7 @@ struct ConvKParams {
   int gn_imgs;                // images (or the one partial image) in this CTA's table: P <= 128 * MT ? 128 * MT / P : 1
   int gn_ctas_per_img;        // CTAs holding pieces of one image (1: the shared-memory barrier is the only hand-shake)
   int gn_tab_groups;          // table columns per version (BN / smallest group size)
+  int gn_sc_smem;             // per-channel scale / shift of the tile's image precomputed once per tile in shared memory
   int* gn_counters;           // [image * num_n_tiles + n_tile][arrived, done]
   int gn_debug;               // DMC_GN_DEBUG (timing experiments only, results are WRONG): 1 no cross-CTA wait, 2 no pass 2,
                               // 4 no table, 8 no park-in-TMEM
@@ -475,16 +476,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS; c0 += 32) {
           const int cg = n_tile * BN + col0 + c0;
-          const bool box_start = res_tma && (c0 % BOXC) == 0;
+          // with the TMA-store epilogue the raw output leaves in pass 1 (bulk-async stores do not delay the hand-shake below);
+          // per-thread stores would, so without it the raw output is written in pass 2
+          const bool raw1 = TS && raw;
+          const bool box_start = (res_tma || raw1) && (c0 % BOXC) == 0;
+          const bool box_end = (res_tma || raw1) && ((c0 + 32) % BOXC) == 0;
           const uint32_t bi = (TS && p.store_bufs == 2) ? (boxi & 1u) : 0u;
           uint8_t* stg = my_stage + bi * 4096u;
           uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
-          if (box_start) {  // residual box: coalesced, asynchronous, lands in a staging buffer no TMA store is reading
+          if (box_start) {  // the staging buffer is free once the TMA store issued from it has read it out of shared memory
             if (lane == 0) {
               if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
               else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              mbar_expect_tx(rb, 4096);
-              tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+              if (res_tma) {  // residual box: coalesced, asynchronous
+                mbar_expect_tx(rb, 4096);
+                tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+              }
             }
             __syncwarp();
           }
@@ -539,7 +546,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 v[8 * j + 2 * k + 1] += f.y;
               }
             }
-            if (((c0 + 32) % BOXC) == 0) ++boxi;  // this residual box is consumed: the next one takes the other buffer
           } else if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -551,6 +557,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 v[8 * j + 2 * k + 1] += f.y;
               }
             }
+          }
+          if (raw1) {  // ---- raw output through the staging buffer (the residual box, if any, has been consumed above) ----
+            uint8_t* rowp = stg + lane * 128;
+            const int half = (c0 >> 5) & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = u;
+            }
+          }
+          if (box_end) {
+            if (raw1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, stg, cg + 32 - BOXC, sw0, sh0, sn0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+            ++boxi;
           }
           // ---- GroupNorm partial sums of this warp's rows (same slots as the stand-alone consumers read) ----
           {
@@ -609,12 +639,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         named_bar_sync(1, EPI_THREADS);
         // ---- table: mean / rstd per (version, image of this tile, group) ----
-        float2* tab = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + GN_TAB_OFFSET) +
-                      acc * (2 * p.gn_imgs * p.gn_tab_groups);
+        // (one buffer is enough: a warp reaches this tile's barrier only after it has finished pass 2 of the previous tile)
+        float2* tab = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + GN_TAB_OFFSET);
+        float2* scsh = tab + 2 * p.gn_imgs * p.gn_tab_groups;  // [version][BN] (scale, shift), when p.gn_sc_smem
         if (!(p.gn_debug & 4)) {
           const int n_first = ((ct * MTG + rank * MT) * TILE_M) / p.gn_P;  // first image of this CTA's rows
           for (int ver = 0; ver < p.gn_nver; ++ver) {
             const int gsz = p.gn_gsize[ver], ng = BN / gsz, nb = gsz >> 3;
+            const float fold = p.gn_silu[ver] ? 0.5f : 1.0f;
             for (int e = warp - 4; e < p.gn_imgs * ng; e += EPI_THREADS / 32) {
               const int il = e / ng, g = e % ng;
               const int n_e = n_first + il;
@@ -629,15 +661,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
               }
 #pragma unroll
-              for (int o = 16; o; o >>= 1) {
+              for (int o = 16; o; o >>= 1) {  // butterfly: every lane ends with the totals
                 s_ += __shfl_xor_sync(0xFFFFFFFFu, s_, o);
                 ss_ += __shfl_xor_sync(0xFFFFFFFFu, ss_, o);
               }
-              if (lane == 0) {
-                const float inv_cnt = 1.0f / (static_cast<float>(gsz) * static_cast<float>(p.gn_P));
-                const float mean = s_ * inv_cnt;
-                const float var = fmaxf(ss_ * inv_cnt - mean * mean, 0.f);
-                tab[(ver * p.gn_imgs + il) * p.gn_tab_groups + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+              const float inv_cnt = 1.0f / (static_cast<float>(gsz) * static_cast<float>(p.gn_P));
+              const float mean = s_ * inv_cnt;
+              const float var = fmaxf(ss_ * inv_cnt - mean * mean, 0.f);
+              const float rstd = rsqrtf(var + p.gn_eps);
+              if (lane == 0) tab[(ver * p.gn_imgs + il) * p.gn_tab_groups + g] = make_float2(mean, rstd);
+              if (p.gn_sc_smem) {  // (one image per tile) the channels of this group: scale / shift with the SiLU 1/2 folded in
+                for (int c = lane; c < gsz; c += 32) {
+                  const int cl = g * gsz + c;
+                  const float a = rstd * __ldg(p.gn_gamma[ver] + n_tile * BN + cl);
+                  scsh[ver * BN + cl] = make_float2(fold * a, fold * (__ldg(p.gn_beta[ver] + n_tile * BN + cl) - mean * a));
+                }
               }
             }
           }
@@ -646,7 +684,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- pass 2: the raw output (ver == -1) and the normalised versions ----
         const int il_row = p.gn_imgs > 1 ? (((MT == 2 ? grp : 0) * TILE_M + row) / p.gn_P) : 0;
 #pragma unroll 1
-        for (int ver = raw ? -1 : 0; ver < ((p.gn_debug & 2) ? 0 : p.gn_nver); ++ver) {
+        for (int ver = (raw && !TS) ? -1 : 0; ver < ((p.gn_debug & 2) ? 0 : p.gn_nver); ++ver) {
           const int vi = ver < 0 ? 0 : ver;
           const int gsz = p.gn_gsize[vi];
           const bool norm = ver >= 0;
@@ -676,7 +714,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t r[32];
             tmem_ld_32x32(taddr + c0, r);
             uint32_t o[16];
-            if (norm) {
+            if (norm && p.gn_sc_smem) {
+              const float4* t4 = reinterpret_cast<const float4*>(scsh + vi * BN + cl);  // (sc, sh) pairs: broadcast reads
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 t = t4[j];
+                float y0 = fmaf(__uint_as_float(r[2 * j]), t.x, t.y);
+                float y1 = fmaf(__uint_as_float(r[2 * j + 1]), t.z, t.w);
+                if (silu) {
+                  y0 = silu_from_half(y0);
+                  y1 = silu_from_half(y1);
+                }
+                o[j] = pack_bf16x2(y0, y1);
+              }
+            } else if (norm) {
               const float2 m0 = trow[cl / gsz], m1 = trow[(cl + 16) / gsz];
               float sc[32], sh[32];
               const float4* g4 = reinterpret_cast<const float4*>(gam + cg);
