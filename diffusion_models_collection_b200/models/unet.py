@@ -181,6 +181,19 @@ class _PlanBuilder:
                 producer[id(o["out"])] = i
             elif kind in ("stem", "upsample", "attention", "gn_apply"):
                 writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 99
+        readers = {}  # how many ops read each tensor
+        for kind, o in self.ops:
+            rd = []
+            if kind == "conv":
+                rd = list(o["srcs"]) + ([o["residual"]] if o["residual"] is not None else [])
+            elif kind == "gn_apply":
+                rd = list(o["srcs"])
+            elif kind in ("head", "upsample"):
+                rd = [o["src"]]
+            elif kind == "attention":
+                rd = [o["qkv"]]
+            for a_ in rd:
+                readers[id(a_)] = readers.get(id(a_), 0) + 1
         drop = set()
         for gi, (kind, g) in enumerate(self.ops):
             if kind != "gn_apply" or g["drop_p"] > 0:
@@ -199,6 +212,11 @@ class _PlanBuilder:
                 pend = sum(1 for q_ in plan if q_[0] is po)
                 kblocks = sum(t_ * a_.C for t_, a_ in zip(po["taps"], po["srcs"])) // 64
                 if kblocks < self.net.fuse_gn_min_kblocks:  # short K loop: the two-pass epilogue would outlast the tile's MMAs
+                    ok = False
+                    break
+                if self.net.fuse_gn_scope == "conv1" and (readers.get(id(s_), 0) != 1 or po["residual"] is not None):
+                    # measured (profiles/r02_conv_gn_micro_*): an epilogue that ALSO writes the raw tensor (residual / skip /
+                    # shortcut readers) costs more than the stand-alone pass it replaces; conv1 -> conv2.0 pairs do not
                     ok = False
                     break
                 if (po["out_nchw"] or po["up_phase"] >= 0 or not po["want_stats"] or len(po.get("gn", ())) + pend >= 2 or
@@ -416,7 +434,10 @@ class UNet(nn.Module):
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
     # ... only into convolutions whose K loop has at least this many 64-element blocks: the epilogue of tile k (two passes +
     # the statistics hand-shake) overlaps the MMAs of tile k+1, which a 1x1 convolution (4 - 8 blocks) finishes long before
-    fuse_gn_min_kblocks = int(os.environ.get("DMC_FUSE_GN_MIN_KB", "16"))
+    fuse_gn_min_kblocks = int(os.environ.get("DMC_FUSE_GN_MIN_KB", "30"))
+    # "conv1": only where the producer's raw output then disappears (conv1 -> conv2.0 of a ResidualBlock); "all": wherever
+    # the geometry allows (every mode is parity-tested; "conv1" is what the measurements favour)
+    fuse_gn_scope = os.environ.get("DMC_FUSE_GN_SCOPE", "conv1")
 
     def __init__(self, image_size: Tuple[int, int] = (32, 32), in_channels=3, model_channels=128, out_channels=3,
                  num_res_blocks=2, attention_resolutions=(16, 8), dropout=0.1, channel_mult=(1, 2, 2, 2),

@@ -361,8 +361,9 @@ def test_split_bf16_mode_cfg_sampling_and_batch_invariance():
     assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("scope", ["conv1", "all"])
 @pytest.mark.parametrize("case", ["cond_labels", "small_cond"])
-def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(golden, case, monkeypatch):
+def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(golden, case, scope, monkeypatch):
     """the default plan applies GroupNorm(+SiLU) in the epilogue of the producing convolution (most of the 56 passes of the CIFAR UNet: every one
     whose producer is a 3x3 convolution with a long enough K loop); DMC_FUSE_GN=0 / UNet.fuse_groupnorm=False keeps every stand-alone gn_apply pass.  Both are within the bf16 gate of
     the reference golden, and the fused plan is at least as close (it normalises the fp32 accumulator, not its bf16 rounding)."""
@@ -371,6 +372,8 @@ def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(gold
     c = UNET_CASES[case]
     cfg = SMALL_UNET if c.get("small") else synth.CIFAR_UNET
     x, t, y = case_inputs(c)
+    monkeypatch.setattr(UNet, "fuse_gn_scope", scope)
+    monkeypatch.setattr(UNet, "fuse_gn_min_kblocks", 30 if scope == "conv1" else 4)
     net = build_unet(cfg, c["num_classes"], c["wseed"])
     assert net.fuse_groupnorm
     with torch.no_grad():
@@ -384,8 +387,8 @@ def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(gold
     n_gn = lambda names: sum(1 for n_ in names if n_.endswith((".conv1.0", ".conv2.0", ".norm", "output.0")))  # noqa: E731
     assert n_gn(names_a) < n_gn(names_b)
     if not c.get("small"):
-        assert n_gn(names_b) == 56 and n_gn(names_a) <= 20
-        assert net.plan_info(x.shape[0]).fused_gn >= 36
+        assert n_gn(names_b) == 56 and n_gn(names_a) == (37 if scope == "conv1" else 6)
+        assert net.plan_info(x.shape[0]).fused_gn == (19 if scope == "conv1" else 57)
     ref = torch.from_numpy(golden["unet"][case])
     ea, eb = rel_l2(a, ref), rel_l2(b, ref)
     print(f"{case}: eps rel-L2 fused {ea:.3e} unfused {eb:.3e}; fused vs unfused {rel_l2(a, b):.3e}")
