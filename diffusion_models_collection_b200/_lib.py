@@ -150,6 +150,11 @@ class UpsampleDesc(C.Structure):
     _fields_ = [("src", vp), ("out", vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32)]
 
 
+class HeadTapsDesc(C.Structure):
+    _fields_ = [("y", vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32), ("ypitch", C.c_int32),
+                ("bias", vp), ("out", vp)]
+
+
 class StepDesc(C.Structure):
     _fields_ = [("x", vp), ("eps_c", vp), ("eps_u", vp), ("noise", vp), ("x_out", vp), ("B", C.c_int32),
                 ("n_per_sample", C.c_int32), ("coef_dev", vp), ("g", Guidance), ("step_index_dev", vp)]
@@ -208,12 +213,13 @@ SYMBOLS = {
     "dmc_head_supported": (C.c_int, [C.POINTER(HeadDesc)]),
     "dmc_conv_gn_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
+    "dmc_plan_add_head_taps": (C.c_int, [vp, C.POINTER(HeadTapsDesc)]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
 }
 
 OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm", "dit_cond",
-            "patch_embed", "ln_modulate", "head"]
+            "patch_embed", "ln_modulate", "head", "head_taps"]
 
 _lock = threading.Lock()
 _lib = None

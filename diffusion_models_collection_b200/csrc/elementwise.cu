@@ -452,6 +452,61 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   }
 }
 
+// =============================================================================================
+// Output head, second half: out[n, co, i, j] = bias[co] + sum over the 9 taps of y[n, (i + dh, j + dw), tap * Cout + co]
+// (see dmc_head_taps_desc).  One CTA = HT_ROWS image rows of one image: the y rows (+1 halo row above and below) are
+// staged in shared memory with a pixel pitch of ypitch + 1 words (lanes = consecutive pixels -> conflict-free), then every
+// thread owns one output pixel.  y is read from HBM once (the halo rows come from L2).
+// =============================================================================================
+constexpr int HT_ROWS = 8;
+
+__global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict__ y, const float* __restrict__ bias,
+                                                        float* __restrict__ out, int H, int W, int Cout, int ypitch) {
+  extern __shared__ float s_y[];
+  const int n = blockIdx.y, r0 = blockIdx.x * HT_ROWS;
+  const int pitch = ypitch + 1;
+  const int rows = min(HT_ROWS, H - r0);
+  // stage rows r0 - 1 .. r0 + rows (zero outside the image): float4 loads, scalar stores (odd pitch)
+  const int nvec = (rows + 2) * W * (ypitch / 4);
+  for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+    const int v = e % (ypitch / 4), px = (e / (ypitch / 4)) % W, rr = e / ((ypitch / 4) * W);
+    const int gy = r0 - 1 + rr;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H) t = __ldg(reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * H + gy) * W + px) * ypitch) + v);
+    float* d = s_y + (rr * W + px) * pitch + 4 * v;
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < rows * W; e += blockDim.x) {
+    const int j = e % W, i = e / W;  // local row i -> staged row i + 1
+    for (int co = 0; co < Cout; ++co) {
+      float acc = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+        const int jj = j + dw;
+        if (jj >= 0 && jj < W) acc += s_y[((i + 1 + dh) * W + jj) * pitch + tap * Cout + co];
+      }
+      out[((static_cast<size_t>(n) * Cout + co) * H + (r0 + i)) * W + j] = acc;
+    }
+  }
+}
+
+int launch_head_taps(const dmc_head_taps_desc& d, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(HT_ROWS + 2) * d.W * (d.ypitch + 1) * sizeof(float);
+  DMC_REQUIRE(smem <= 200 * 1024, "head_taps: image too wide (W=%d)", d.W);
+  static DeviceOnce attr_set;
+  int attr_dev = 0;
+  if (smem > 48 * 1024 && attr_set.need(&attr_dev)) {
+    DMC_CUDA_OK(cudaFuncSetAttribute(head_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set.done(attr_dev);
+  }
+  dim3 grid((d.H + HT_ROWS - 1) / HT_ROWS, d.B);
+  head_taps_kernel<<<grid, 256, smem, st>>>(d.y, d.bias, d.out, d.H, d.W, d.Cout, d.ypitch);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.nsrc == 1 || d.nsrc == 2, "gn_apply: nsrc=%d", d.nsrc);
   DMC_REQUIRE(d.src[0] && d.stats[0] && d.gamma && d.beta && d.out, "gn_apply: null pointer argument");

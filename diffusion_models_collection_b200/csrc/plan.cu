@@ -26,7 +26,7 @@ int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 
 enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM,
-              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD };
+              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD, OP_HEAD_TAPS };
 
 struct Op {
   int kind;
@@ -44,6 +44,7 @@ struct Op {
     dmc_patch_embed_desc patch;
     dmc_ln_mod_desc ln_mod;
     dmc_head_desc head;
+    dmc_head_taps_desc head_taps;
   };
   ConvPrepared* conv_prep;
   AttnPrepared* attn_prep;
@@ -79,6 +80,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_PATCH_EMBED: return launch_patch_embed(op.patch, st);
     case OP_LN_MOD: return launch_ln_modulate(op.ln_mod, st);
     case OP_HEAD: return launch_head_fused(op.head, st);
+    case OP_HEAD_TAPS: return launch_head_taps(op.head_taps, st);
   }
   set_error("plan: unknown op kind %d", op.kind);
   return -1;
@@ -279,6 +281,7 @@ int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* pt
   if (op.kind == OP_STEM && which == 0) { op.stem.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 0) { op.cond.t = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 1) { op.cond.y = static_cast<const int64_t*>(ptr); return 0; }
+  if (op.kind == OP_HEAD_TAPS && which == 2 && ptr != nullptr) { op.head_taps.out = static_cast<float*>(const_cast<void*>(ptr)); return 0; }
   if (op.kind == OP_HEAD && which == 2 && ptr != nullptr) { op.head.out = static_cast<float*>(const_cast<void*>(ptr)); return 0; }
   if (op.kind == OP_PATCH_EMBED && which == 0) { op.patch.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_DIT_COND && which == 0) { op.dit_cond.t = static_cast<const int64_t*>(ptr); return 0; }
@@ -450,6 +453,18 @@ int dmc_plan_add_head(dmc_plan* p, const dmc_head_desc* d) {
   const double pix = static_cast<double>(d->B) * d->H * d->W;
   op.bytes = pix * (2.0 * d->C + 4.0 * d->Cout);
   op.flops = 2.0 * pix * d->Cout * d->C * 9;
+  return push(p, op);
+}
+
+int dmc_plan_add_head_taps(dmc_plan* p, const dmc_head_taps_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_head_taps: null argument");
+  DMC_REQUIRE(d->y && d->out && d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->ypitch >= 9 * d->Cout && d->ypitch <= 64 &&
+                  d->ypitch % 4 == 0, "dmc_plan_add_head_taps: bad arguments (Cout=%d ypitch=%d)", d->Cout, d->ypitch);
+  Op op;
+  op.kind = OP_HEAD_TAPS;
+  op.head_taps = *d;
+  const double pix = static_cast<double>(d->B) * d->H * d->W;
+  op.bytes = pix * 4.0 * (d->ypitch + d->Cout);
   return push(p, op);
 }
 

@@ -146,7 +146,7 @@ class _PlanBuilder:
     @staticmethod
     def _touched(kind, o):
         """activations an op reads or writes"""
-        if kind in ("stem", "gn_stats", "head"):
+        if kind in ("stem", "gn_stats", "head", "head_taps"):
             return [o.get("out") or o.get("src")]
         if kind == "gn_apply":
             return list(o["srcs"]) + [o["out"]]
@@ -188,7 +188,7 @@ class _PlanBuilder:
                 rd = list(o["srcs"]) + ([o["residual"]] if o["residual"] is not None else [])
             elif kind == "gn_apply":
                 rd = list(o["srcs"])
-            elif kind in ("head", "upsample"):
+            elif kind in ("head", "head_taps", "upsample"):
                 rd = [o["src"]]
             elif kind == "attention":
                 rd = [o["qkv"]]
@@ -242,7 +242,7 @@ class _PlanBuilder:
                     read.add(id(o["residual"]))
             elif kind == "gn_apply":
                 read.update(id(s_) for s_ in o["srcs"])
-            elif kind in ("gn_stats", "head", "upsample"):
+            elif kind in ("gn_stats", "head", "head_taps", "upsample"):
                 read.add(id(o["src"]))
             elif kind == "attention":
                 read.add(id(o["qkv"]))
@@ -289,7 +289,7 @@ class _PlanBuilder:
         return out
 
     def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
-             up_phase=-1, out=None, want_stats=True, sc_slice=None):
+             up_phase=-1, out=None, want_stats=True, sc_slice=None, out_f32=False):
         Ho, Wo = H // stride, W // stride
         if up_phase >= 0:
             Ho, Wo = 2 * H, 2 * W
@@ -304,7 +304,8 @@ class _PlanBuilder:
             srcs, taps, parts = [srcs[0]] * 3, [taps[0]] * 3, ["hi", "lo", "hi"]
         self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), parts=parts, wname=wname, Cout=Cout, H=H, W=W,
                                       stride=stride, bias=bias, cond_col=cond_col, residual=residual, out=out,
-                                      out_nchw=out_nchw, up_phase=up_phase, want_stats=want_stats, sc_slice=sc_slice)))
+                                      out_nchw=out_nchw, up_phase=up_phase, want_stats=want_stats, sc_slice=sc_slice,
+                                      out_f32=out_f32)))
         return out
 
     def fused_head(self, h):
@@ -408,6 +409,14 @@ class _PlanBuilder:
             # GroupNorm + SiLU + conv 3x3 -> fp32 NCHW in ONE kernel (one read of h)
             self.ops.append(("head", dict(src=self.stats_of(h))))
             self.free(h)
+        elif self.net.head_taps and not (self.split or self.keep or self.conv_impl != 0) and 9 * net.out_channels <= 64:
+            # conv3x3 C -> 3 as ONE 1x1 GEMM with 27 (tap, cout) columns (every input pixel read once, not 3 - 9 times) and a
+            # 9-tap fp32 gather that writes the NCHW eps
+            a = self.gn_apply([h], "output.0", 1)
+            ypitch = _round_up(9 * net.out_channels, 32)
+            yact = _Act(self.B * H * W * ypitch * 4, ypitch, H, W)  # fp32 [B, H, W, ypitch]
+            self.conv([a], [1], "output.2.taps", ypitch, H, W, out=yact, want_stats=False, out_f32=True)
+            self.ops.append(("head_taps", dict(src=yact, ypitch=ypitch)))
         else:
             a = self.gn_apply([h], "output.0", 1)
             self.free(h)
@@ -429,6 +438,9 @@ class UNet(nn.Module):
     # output GroupNorm + SiLU + conv as one mma.sync kernel: opt-in -- measured 0.725 ms against 0.20 + 0.53 ms for the
     # two-kernel path at 2048 images (legacy mma.sync issues ~1 per 80 clk per SM sub-partition on sm_100a), no gain
     fuse_head = os.environ.get("DMC_FUSED_HEAD", "0") != "0"
+    # output conv3x3 (C -> 3) as a 1x1 GEMM over 27 (tap, cout) columns + a 9-tap gather (dmc_head_taps_desc); 0: the padded-N
+    # 3x3 implicit GEMM (which re-reads its input 4.5x through the slab path: 0.55 ms against ~0.2 ms at 2048 images)
+    head_taps = os.environ.get("DMC_HEAD_TAPS", "1") != "0"
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
@@ -620,6 +632,11 @@ class UNet(nn.Module):
         head = pack3(sd["output.2.weight"])
         W["output.2"] = torch.cat([head, head.new_zeros(32 - head.shape[0], head.shape[1])], dim=0)
         Bv["output.2"] = sd["output.2.bias"]
+        if 9 * self.out_channels <= 64:
+            # the head as a 1x1 GEMM over (tap, cout) columns + a 9-tap gather (dmc_head_taps_desc): row tap * Cout + co
+            hw = sd["output.2.weight"]
+            ht = hw.permute(2, 3, 0, 1).reshape(9 * self.out_channels, hw.shape[1])
+            W["output.2.taps"] = torch.cat([ht, ht.new_zeros(_round_up(ht.shape[0], 32) - ht.shape[0], ht.shape[1])], dim=0)
 
         # one bf16 blob for all GEMM weights (1 KiB aligned slices: TMA needs 16 B), one fp32 blob for the rest
         offs, total = {}, 0
@@ -676,6 +693,12 @@ class UNet(nn.Module):
             if phases:
                 for dst, wkey, ph in r["phases"]:
                     dst.copy_(phase_weights(sd[wkey], ph))
+                if "output.2.taps" in pk["woffs"]:  # (sampling plans only, like the phase weights)
+                    hw = sd["output.2.weight"]
+                    rows, K = pk["wshape"]["output.2.taps"]
+                    o_ = pk["woffs"]["output.2.taps"] // 2
+                    pk["wblob"][o_: o_ + rows * K].view(rows, K)[: 9 * self.out_channels].copy_(
+                        hw.permute(2, 3, 0, 1).reshape(9 * self.out_channels, hw.shape[1]))
                 return
             if device.type == "cuda":  # all GEMM weights in one launch of the native pack kernel
                 if r["table"] is None:
@@ -1063,6 +1086,8 @@ class _UNetPlan:
                 d.residual_lo = ap_lo(o["residual"]) if o["residual"] is not None else None
                 if o["out_nchw"]:
                     d.out_f32_nchw = self.eps.data_ptr()
+                elif o.get("out_f32"):
+                    d.out_f32_nhwc = ap(o["out"])
                 elif o["out"].raw:
                     d.out_bf16, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 d.impl = conv_impl
@@ -1099,6 +1124,11 @@ class _UNetPlan:
                 self.head_wfrag = torch.empty(9 * (a.C // 16) * 256, dtype=torch.uint8, device=device)
                 d.wfrag = self.head_wfrag.data_ptr()
                 self.head_idx = add(lib.dmc_plan_add_head, d, "output.head")
+            elif kind == "head_taps":
+                d = _lib.HeadTapsDesc()
+                d.y, d.B, d.H, d.W, d.Cout, d.ypitch = ap(o["src"]), nimg, Hh, Ww, net.out_channels, o["ypitch"]
+                d.bias, d.out = sd["output.2.bias"].data_ptr(), self.eps.data_ptr()
+                self.head_idx = add(lib.dmc_plan_add_head_taps, d, "output.2.gather")
             elif kind == "upsample":
                 d = _lib.UpsampleDesc()
                 d.src, d.out, d.B, d.H, d.W, d.C = ap(o["src"]), ap(o["out"]), nimg, o["src"].H, o["src"].W, o["src"].C

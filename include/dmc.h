@@ -515,6 +515,20 @@ typedef struct {
 } dmc_upsample_desc;
 DMC_API int dmc_plan_add_upsample(dmc_plan* p, const dmc_upsample_desc* d);
 
+/* Output head, second half (models/unet.py:240: conv3x3 C -> Cout, Cout <= 3..10, fp32 NCHW eps).  A 3x3 convolution with so
+ * few output channels is bound by re-reading its input 3 - 9 times; instead the head runs as
+ *   y[n, p, tap * Cout + co] = sum_c a[n, p, c] * w[co, c, tap]      one 1x1 tcgen05 GEMM: every input pixel is read ONCE
+ *   out[n, co, i, j] = bias[co] + sum_tap y[n, (i + dh_tap, j + dw_tap), tap * Cout + co]   (this op; zero outside the image)
+ * y is fp32 [B, H, W, ypitch] (ypitch >= 9 * Cout, the GEMM's padded column count), so the nine partial sums are added in
+ * fp32 exactly like the accumulator of the direct convolution. */
+typedef struct {
+  const float* y;    /* fp32 [B, H, W, ypitch] */
+  int32_t B, H, W, Cout, ypitch;
+  const float* bias; /* [Cout] or NULL */
+  float* out;        /* fp32 [B, Cout, H, W] */
+} dmc_head_taps_desc;
+DMC_API int dmc_plan_add_head_taps(dmc_plan* p, const dmc_head_taps_desc* d);
+
 /* Scheduler steps as plan ops, so that "model forward + update" chains (and whole sampling loops) can be
  * replayed with a single call / captured in one CUDA graph. */
 typedef struct {

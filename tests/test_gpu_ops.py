@@ -427,3 +427,37 @@ def test_fused_output_head(C_, H, B, cout):
     p2.add("head", d)
     p2.run()
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("C,H,B,cout", [(128, 32, 3, 3), (128, 32, 1, 3), (64, 16, 2, 3), (128, 8, 5, 1)])
+def test_head_as_1x1_gemm_plus_tap_gather(C, H, B, cout):
+    """the output conv3x3 (C -> cout) as ONE 1x1 GEMM with 9 * cout (tap, cout) columns writing fp32 NHWC, followed by the
+    9-tap gather of dmc_head_taps_desc (models/unet.py:240) vs F.conv2d on the same bf16-rounded operands"""
+    from diffusion_models_collection_b200 import _lib
+
+    x = _q(_rand((B, C, H, H), 31))
+    w = _q(_rand((cout, C, 3, 3), 32, (C * 9) ** -0.5))
+    bias = _rand((cout,), 33, 0.1)
+    ref = F.conv2d(x, w, bias, padding=1)
+    ypitch = (9 * cout + 31) // 32 * 32
+    wt = torch.zeros(ypitch, C, device="cuda")
+    wt[: 9 * cout] = w.permute(2, 3, 0, 1).reshape(9 * cout, C)
+    wq = wt.to(torch.bfloat16).contiguous()
+    src = nhwc_bf16(x)
+    y = torch.full((B, H, H, ypitch), float("nan"), device="cuda")
+    d = _lib.ConvDesc()
+    d.nsrc = 1
+    d.src[0], d.src_c[0], d.src_taps[0] = src.data_ptr(), C, 1
+    d.B, d.Hin, d.Win, d.stride, d.up_phase = B, H, H, 1, -1
+    d.weight, d.Cout, d.Cout_pad, d.Ktot = wq.data_ptr(), ypitch, ypitch, C
+    d.out_f32_nhwc = y.data_ptr()
+    out = torch.full((B, cout, H, H), float("nan"), device="cuda")
+    t = _lib.HeadTapsDesc()
+    t.y, t.B, t.H, t.W, t.Cout, t.ypitch = y.data_ptr(), B, H, H, cout, ypitch
+    t.bias, t.out = bias.data_ptr(), out.data_ptr()
+    p = Plan()
+    p.add("conv", d)
+    p.add("head_taps", t)
+    p.run()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 1e-4  # fp32 output of bf16 operands: only the accumulation order differs
