@@ -469,7 +469,9 @@ def run_train_workload(args, rank, local_rank, world):
         model = (torch.nn.parallel.DistributedDataParallel(net, bucket_cap_mb=bucket_mb, gradient_as_bucket_view=bucket_view)
                  if world > 1 else net)
     ddpm = DDPM(1000, 1e-4, 0.02, "linear", device=dev)
-    fused_opt = os.environ.get("DMC_FUSED_OPT", "0") == "1"  # native clip + AdamW + EMA in two launches (optim.FusedAdamW)
+    # native clip + AdamW + EMA in two launches (optim.FusedAdamW, the default since round 2: it bumps the parameter versions,
+    # so the engine re-packs its bf16 operands after every step); DMC_FUSED_OPT=0: torch's fused AdamW + foreach clip / EMA
+    fused_opt = os.environ.get("DMC_FUSED_OPT", "1") == "1"
     if fused_opt:
         from diffusion_models_collection_b200.optim import FusedAdamW
 

@@ -468,13 +468,28 @@ __global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict_
   const int rows = min(HT_ROWS, H - r0);
   // stage rows r0 - 1 .. r0 + rows (zero outside the image): float4 loads, scalar stores (odd pitch)
   const int nvec = (rows + 2) * W * (ypitch / 4);
-  for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
-    const int v = e % (ypitch / 4), px = (e / (ypitch / 4)) % W, rr = e / ((ypitch / 4) * W);
-    const int gy = r0 - 1 + rr;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H) t = __ldg(reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * H + gy) * W + px) * ypitch) + v);
-    float* d = s_y + (rr * W + px) * pitch + 4 * v;
-    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+  const int vpp = ypitch / 4;  // float4 per pixel
+  for (int e0 = threadIdx.x; e0 < nvec; e0 += blockDim.x * 5) {  // five independent 16-byte loads in flight per thread
+    float4 t[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int e = e0 + u * blockDim.x;
+      t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < nvec) {
+        const int v = e % vpp, px = (e / vpp) % W, rr = e / (vpp * W);
+        const int gy = r0 - 1 + rr;
+        if (gy >= 0 && gy < H) t[u] = __ldg(reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * H + gy) * W + px) * ypitch) + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < nvec) {
+        const int v = e % vpp, px = (e / vpp) % W, rr = e / (vpp * W);
+        float* d = s_y + (rr * W + px) * pitch + 4 * v;
+        d[0] = t[u].x; d[1] = t[u].y; d[2] = t[u].z; d[3] = t[u].w;
+      }
+    }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < rows * W; e += blockDim.x) {
