@@ -404,6 +404,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
            (gn ? VAR_GN : 0);
   kp.Cout = d.Cout;
   kp.bias = d.bias; kp.cond = d.cond; kp.cond_stride = d.cond_stride;
+  kp.prefetch_cond = env_flag("DMC_CONV_PREFETCH_COND", 1);
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
   kp.out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   kp.out_nchw = d.out_f32_nchw;

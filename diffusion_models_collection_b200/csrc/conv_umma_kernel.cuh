@@ -34,6 +34,7 @@ struct ConvKParams {
   const float* bias;
   const float* cond;
   int cond_stride;
+  int prefetch_cond;          // prefetch the tile's conditioning row into L1 before waiting for the accumulator
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
   float* out_nchw;
@@ -452,6 +453,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int sw0 = tw * p.BW + r0 % p.BW, sh0 = th * p.BH + (r0 / p.BW) % p.BH, sn0 = ti * p.BNIMG + r0 / ppi;
       uint8_t* my_stage = store_stage + (warp - 4) * 4096 * p.store_bufs;
 
+      if (UNET && p.cond != nullptr && p.prefetch_cond && valid) {
+        // the conditioning row of this tile's image is a first touch (one row per image per layer): start pulling its lines
+        // into L1 while the tile's MMAs are still running instead of paying the L2 latency inside the chunk loop
+        const float* cp = p.cond + static_cast<size_t>(n) * p.cond_stride + n_tile * BN + col0;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cp + (lane % (COLS / 32)) * 32));
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS +

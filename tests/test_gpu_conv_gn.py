@@ -125,6 +125,9 @@ CASES = [
     (128, 128, 32, 1, 9, 3, True, True, [(128, 0, 16, True)], "1"),
     (256, 128, 32, 1, 9, 40, False, False, [(128, 0, 16, True)], "2"),                     # >= 148 CTAs: the configuration of the bench
     (128, 128, 32, 1, 9, 75, True, True, [(128, 0, 16, True), (256, 0, 32, True)], "2"),   # more image units than CTA groups: 2 iterations
+    # 64x64 (the shipped custom-dataset image size): 4096 pixels per image = 16 CTAs, 128 statistics slots
+    (128, 128, 64, 1, 9, 2, False, False, [(128, 0, 16, True)], "2"),
+    (128, 128, 64, 1, 9, 3, True, True, [(128, 0, 16, True), (256, 128, 32, False)], "1"),
 ]
 
 

@@ -217,6 +217,15 @@ def test_cached_graph_loop_samples_from_the_current_weights(model_kind):
     want = d2.sample_with_cfg(net, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT)
     assert not torch.equal(first, second)
     assert torch.equal(second, want)
+    # ... and the in-place re-pack (GEMM weights, Upsample phase weights, the head's (tap, cout) matrix, bias / conditioning
+    # tables) left nothing stale: a model built from scratch with the new weights samples the same images
+    if model_kind == "unet":
+        fresh = build_unet(SMALL_UNET, 10, 4)
+    else:
+        fresh = DiT(**synth.CIFAR_DIT, num_classes=10)
+    fresh.load_state_dict(net.state_dict())
+    fresh = fresh.cuda().eval()
+    assert torch.equal(d2.sample_with_cfg(fresh, (4, 3, 32, 32), y, cfg_scale=2.0, noise=xT), second)
     if model_kind == "unet":  # values-only change: the plan, its TMA descriptors and the captured graph all survived
         assert d._graph_cache is cache
     # load_state_dict (copy_ into the same storage) is seen as well

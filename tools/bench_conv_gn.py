@@ -27,8 +27,11 @@ def bench(cin, cout, H, taps, B, nver, raw, residual, stride=1, iters=20):
     d.B, d.Hin, d.Win, d.stride, d.up_phase = B, H, H, stride, -1
     d.weight, d.Cout, d.Cout_pad, d.Ktot = w.data_ptr(), cout, cout, K
     d.bias = bias.data_ptr()
+    cond = torch.randn(B, cout, device=dev) * 0.1
+    if os.environ.get("BENCH_COND", "1") == "1" and taps == 9:
+        d.cond, d.cond_stride = cond.data_ptr(), cout
     Ho = H // stride
-    keep = [src, w, bias]
+    keep = [src, w, bias, cond]
     if residual:
         r = torch.randn(B, Ho, Ho, cout, device=dev).to(torch.bfloat16)
         d.residual = r.data_ptr()
