@@ -252,7 +252,9 @@ def workload_config(args, per_rank):
     return {"workload": "UNet cond (10+1 null) CIFAR-10 32x32, DDIM-50, CFG 3.0, dynamic threshold 0.995 "
                         "(BASELINE.json configs[2])", "global_batch": args.batch, "per_gpu_batch": per_rank,
             "sampler": "ddim50", "cfg_scale": 3.0, "parallelism": f"sample-sharded x{args.gpus}",
-            "l2": "inputs larger than L2 (activations of one forward are >10x the 126 MB L2)"}
+            "l2": "inputs larger than L2 (activations of one forward are >10x the 126 MB L2)",
+            "schedule_tables": "built on the device with the reference's own torch expressions: bit-equal to what the reference "
+                               "computes on the same device, last-bit differences against its CPU tables (linspace / cumprod / sqrt)"}
 
 
 # ------------------------------------------------------------------------------------------------------
