@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--model", default="unet", choices=["unet", "dit"],
                     help="unet: BASELINE configs[2] (the bench line); dit: configs[3] (DiT patch-2 DDIM-50 uncond, --batch 1024), "
                          "a side measurement, not the headline")
-    ap.add_argument("--ref-batch", type=int, default=4,
+    ap.add_argument("--ref-batch", type=int, default=8,
                     help="images per step of the CPU reference legs (every step runs all 50 DDIM steps on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -430,7 +430,7 @@ def main():
                                         chunks=-(-nb // max(1, net.max_images_per_launch // (1 if uncond else 2))))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference itself on the host cores: this workload on a bounded sample, and BASELINE configs[0] verbatim
-        _, cb = cpu_reference_images_per_sec(batch=2 * args.ref_batch)
+        _, cb = cpu_reference_images_per_sec(batch=args.ref_batch)
         line["cpu_baseline"] = cb
         if not is_dit and not is_ddpm:
             line["cpu_baseline_config1"] = cpu_reference_config1()
