@@ -150,6 +150,11 @@ class UpsampleDesc(C.Structure):
     _fields_ = [("src", vp), ("out", vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32)]
 
 
+class StemColsDesc(C.Structure):
+    _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("out", vp)]
+
+
 class HeadTapsDesc(C.Structure):
     _fields_ = [("y", vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32), ("ypitch", C.c_int32),
                 ("bias", vp), ("out", vp)]
@@ -214,12 +219,13 @@ SYMBOLS = {
     "dmc_conv_gn_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
     "dmc_plan_add_head_taps": (C.c_int, [vp, C.POINTER(HeadTapsDesc)]),
+    "dmc_plan_add_stem_cols": (C.c_int, [vp, C.POINTER(StemColsDesc)]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
 }
 
 OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm", "dit_cond",
-            "patch_embed", "ln_modulate", "head", "head_taps"]
+            "patch_embed", "ln_modulate", "head", "head_taps", "stem_cols"]
 
 _lock = threading.Lock()
 _lib = None

@@ -453,6 +453,55 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
 }
 
 // =============================================================================================
+// Input convolution, tensor-core form (see dmc_stem_cols_desc): gather the 3x3 neighbourhood of every pixel of the fp32 NCHW
+// input into one 64-channel bf16 NHWC row [taps as bf16 | their rounding remainders | 0]; the 1x1 tcgen05 GEMM does the rest.
+// thread = (pixel, 16-byte chunk of its row): the 8 lanes of a pixel write its 128-byte row as one full line; the fp32
+// reads (up to 2 taps x Cin per lane) come from L1 / L2 -- the whole input is 12 KB per image.
+// =============================================================================================
+__global__ void __launch_bounds__(256) stem_cols_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int x_batch,
+                                                        int B, int Cin, int H, int W) {
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t pix = gid >> 3;
+  const int chunk = static_cast<int>(gid & 7);  // columns [8 chunk, 8 chunk + 8)
+  if (pix >= static_cast<size_t>(B) * H * W) return;
+  const int ww = static_cast<int>(pix % W), hh = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+  const float* xin = x + static_cast<size_t>(n % x_batch) * Cin * H * W;
+  const int K = 9 * Cin;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = chunk * 8 + 2 * j + e;
+      const int k = col < K ? col : col - K;  // the tap this column carries (hi part, then lo part)
+      float val = 0.f;
+      if (col < 2 * K) {
+        const int tap = k / Cin, ci = k % Cin;
+        const int ih = hh + tap / 3 - 1, iw = ww + tap % 3 - 1;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+          const float f = __ldg(xin + (static_cast<size_t>(ci) * H + ih) * W + iw);
+          const float hi = __bfloat162float(__float2bfloat16_rn(f));
+          val = col < K ? hi : f - hi;
+        }
+      }
+      v[e] = val;
+    }
+    o[j] = pack_bf16x2(v[0], v[1]);
+  }
+  reinterpret_cast<uint4*>(out)[gid] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int launch_stem_cols(const dmc_stem_cols_desc& d, cudaStream_t st) {
+  const size_t threads = static_cast<size_t>(d.B) * d.H * d.W * 8;
+  stem_cols_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      d.x, reinterpret_cast<__nv_bfloat16*>(d.out), d.x_batch, d.B, d.Cin, d.H, d.W);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
 // Output head, second half: out[n, co, i, j] = bias[co] + sum over the 9 taps of y[n, (i + dh, j + dw), tap * Cout + co]
 // (see dmc_head_taps_desc).  One CTA = HT_ROWS image rows of one image: the y rows (+1 halo row above and below) are
 // staged in shared memory with a pixel pitch of ypitch + 1 words (lanes = consecutive pixels -> conflict-free), then every

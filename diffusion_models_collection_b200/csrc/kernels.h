@@ -25,6 +25,7 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st);
 int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
 int launch_head_fused(const dmc_head_desc& d, cudaStream_t st);
 int launch_head_taps(const dmc_head_taps_desc& d, cudaStream_t st);
+int launch_stem_cols(const dmc_stem_cols_desc& d, cudaStream_t st);
 bool head_fused_supported(const dmc_head_desc& d);
 
 // dit_ops.cu

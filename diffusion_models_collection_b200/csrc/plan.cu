@@ -26,7 +26,7 @@ int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 
 enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM,
-              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD, OP_HEAD_TAPS };
+              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD, OP_HEAD_TAPS, OP_STEM_COLS };
 
 struct Op {
   int kind;
@@ -45,6 +45,7 @@ struct Op {
     dmc_ln_mod_desc ln_mod;
     dmc_head_desc head;
     dmc_head_taps_desc head_taps;
+    dmc_stem_cols_desc stem_cols;
   };
   ConvPrepared* conv_prep;
   AttnPrepared* attn_prep;
@@ -81,6 +82,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_LN_MOD: return launch_ln_modulate(op.ln_mod, st);
     case OP_HEAD: return launch_head_fused(op.head, st);
     case OP_HEAD_TAPS: return launch_head_taps(op.head_taps, st);
+    case OP_STEM_COLS: return launch_stem_cols(op.stem_cols, st);
   }
   set_error("plan: unknown op kind %d", op.kind);
   return -1;
@@ -279,6 +281,7 @@ int dmc_plan_rebind(dmc_plan* p, int32_t op_index, int32_t which, const void* pt
   DMC_REQUIRE(p && op_index >= 0 && op_index < static_cast<int>(p->ops.size()), "dmc_plan_rebind: bad op index");
   Op& op = p->ops[op_index];
   if (op.kind == OP_STEM && which == 0) { op.stem.x = static_cast<const float*>(ptr); return 0; }
+  if (op.kind == OP_STEM_COLS && which == 0) { op.stem_cols.x = static_cast<const float*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 0) { op.cond.t = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_COND && which == 1) { op.cond.y = static_cast<const int64_t*>(ptr); return 0; }
   if (op.kind == OP_HEAD_TAPS && which == 2 && ptr != nullptr) { op.head_taps.out = static_cast<float*>(const_cast<void*>(ptr)); return 0; }
@@ -453,6 +456,17 @@ int dmc_plan_add_head(dmc_plan* p, const dmc_head_desc* d) {
   const double pix = static_cast<double>(d->B) * d->H * d->W;
   op.bytes = pix * (2.0 * d->C + 4.0 * d->Cout);
   op.flops = 2.0 * pix * d->Cout * d->C * 9;
+  return push(p, op);
+}
+
+int dmc_plan_add_stem_cols(dmc_plan* p, const dmc_stem_cols_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_stem_cols: null argument");
+  DMC_REQUIRE(d->x && d->out && d->B > 0 && d->x_batch > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && 18 * d->Cin <= 64,
+              "dmc_plan_add_stem_cols: bad arguments (Cin=%d)", d->Cin);
+  Op op;
+  op.kind = OP_STEM_COLS;
+  op.stem_cols = *d;
+  op.bytes = static_cast<double>(d->B) * d->H * d->W * (4.0 * d->Cin + 128.0);
   return push(p, op);
 }
 

@@ -146,7 +146,7 @@ class _PlanBuilder:
     @staticmethod
     def _touched(kind, o):
         """activations an op reads or writes"""
-        if kind in ("stem", "gn_stats", "head", "head_taps"):
+        if kind in ("stem", "stem_cols", "gn_stats", "head", "head_taps"):
             return [o.get("out") or o.get("src")]
         if kind == "gn_apply":
             return list(o["srcs"]) + [o["out"]]
@@ -179,7 +179,7 @@ class _PlanBuilder:
             if kind == "conv" and o["out"] is not None:
                 writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 1
                 producer[id(o["out"])] = i
-            elif kind in ("stem", "upsample", "attention", "gn_apply"):
+            elif kind in ("stem", "stem_cols", "upsample", "attention", "gn_apply"):
                 writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 99
         readers = {}  # how many ops read each tensor
         for kind, o in self.ops:
@@ -358,8 +358,15 @@ class _PlanBuilder:
         mc = net.model_channels
         down, middle, up, out_ch = unet_block_structure(net._cfg())
         self.ops.append(("cond", {}))
-        h = self.act(mc, H, W)
-        self.ops.append(("stem", dict(out=h)))
+        if self.net.stem_gemm and not (self.split or self.keep or self.conv_impl != 0) and 18 * net.in_channels <= 64 and mc % 32 == 0:
+            # input conv on the tensor cores: gather (tap, channel) columns of the fp32 input as a bf16 (hi, lo) pair, then ONE
+            # 1x1 GEMM with K = 64 (bias, GroupNorm partial sums from its epilogue: no stand-alone statistics pass)
+            xc = self.act(64, H, W)
+            self.ops.append(("stem_cols", dict(out=xc)))
+            h = self.conv([xc], [1], "input_conv.cols", mc, H, W, bias="input_conv")
+        else:
+            h = self.act(mc, H, W)
+            self.ops.append(("stem", dict(out=h)))
         hs = [h]
         col = 0
 
@@ -441,6 +448,9 @@ class UNet(nn.Module):
     # output conv3x3 (C -> 3) as a 1x1 GEMM over 27 (tap, cout) columns + a 9-tap gather (dmc_head_taps_desc); 0: the padded-N
     # 3x3 implicit GEMM (which re-reads its input 4.5x through the slab path: 0.55 ms against ~0.2 ms at 2048 images)
     head_taps = os.environ.get("DMC_HEAD_TAPS", "1") != "0"
+    # input conv3x3 (3 -> C) as a gather of 27 (tap, channel) columns (bf16 hi + lo of the fp32 input) + a 1x1 tcgen05 GEMM whose
+    # epilogue also writes the GroupNorm partial sums; 0: the fp32 CUDA-core stem kernel + a stand-alone statistics pass
+    stem_gemm = os.environ.get("DMC_STEM_GEMM", "1") != "0"
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
@@ -629,6 +639,12 @@ class UNet(nn.Module):
         entry("middle_block", middle)
         for i, layers in enumerate(up):
             entry(f"up_blocks.{i}", layers)
+        if 18 * self.in_channels <= 64:
+            # the input convolution as a 1x1 GEMM over gathered (tap, channel) columns (dmc_stem_cols_desc): [W | W | 0], the
+            # second copy multiplies the bf16 rounding remainders of the input
+            ws = pack3(sd["input_conv.weight"])
+            W["input_conv.cols"] = torch.cat([ws, ws, ws.new_zeros(ws.shape[0], 64 - 2 * ws.shape[1])], dim=1)
+            Bv["input_conv"] = sd["input_conv.bias"]
         head = pack3(sd["output.2.weight"])
         W["output.2"] = torch.cat([head, head.new_zeros(32 - head.shape[0], head.shape[1])], dim=0)
         Bv["output.2"] = sd["output.2.bias"]
@@ -795,6 +811,13 @@ class UNet(nn.Module):
         entry("middle_block", middle)
         for i, layers in enumerate(up):
             entry(f"up_blocks.{i}", layers)
+        if "input_conv.cols" in pk["woffs"]:
+            k27 = 9 * self.in_channels
+            v = wview("input_conv.cols")
+            w3x3(v[:, :k27], sd["input_conv.weight"])
+            w3x3(v[:, k27: 2 * k27], sd["input_conv.weight"])
+            r["b_dst"].append(pk["bias"]["input_conv"])
+            r["b_src"].append(sd["input_conv.bias"])
         w3x3(wview("output.2")[: self.out_channels], sd["output.2.weight"])
         r["b_dst"].append(pk["bias"]["output.2"])
         r["b_src"].append(sd["output.2.bias"])
@@ -1045,6 +1068,11 @@ class _UNetPlan:
                 d.weight, d.bias = sd["input_conv.weight"].data_ptr(), sd["input_conv.bias"].data_ptr()
                 d.out, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 self.stem_idx = add(lib.dmc_plan_add_stem, d, "input_conv")
+            elif kind == "stem_cols":
+                d = _lib.StemColsDesc()
+                d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
+                d.Cin, d.H, d.W, d.out = net.in_channels, Hh, Ww, ap(o["out"])
+                self.stem_idx = add(lib.dmc_plan_add_stem_cols, d, "input_conv.gather")
             elif kind == "gn_stats":
                 a = o["src"]
                 d = _lib.GnStatsDesc()

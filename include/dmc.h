@@ -310,6 +310,18 @@ typedef struct {
 } dmc_stem_desc;
 DMC_API int dmc_plan_add_stem(dmc_plan* p, const dmc_stem_desc* d);
 
+/* Input convolution, tensor-core form: this op only gathers the 3x3 neighbourhood of every pixel of the fp32 NCHW input into
+ * one 64-channel bf16 NHWC row -- columns [0, 9*Cin): the taps, tap-major / channel-minor, as bf16(v); columns [9*Cin, 18*Cin):
+ * the rounding remainders bf16(v - bf16(v)), so the pair carries 16 mantissa bits of the input; the rest zero -- and the
+ * convolution itself is then ONE 1x1 tcgen05 GEMM (dmc_plan_add_conv, K = 64) against [W | W | 0] with bias, GroupNorm partial
+ * sums and everything else the conv epilogue offers (models/unet.py:188,263).  Needs 18 * Cin <= 64. */
+typedef struct {
+  const float* x;      /* [x_batch, Cin, H, W] fp32; image n reads x[n % x_batch] */
+  int32_t x_batch, B, Cin, H, W;
+  void* out;           /* bf16 [B, H, W, 64] */
+} dmc_stem_cols_desc;
+DMC_API int dmc_plan_add_stem_cols(dmc_plan* p, const dmc_stem_cols_desc* d);
+
 /* Split-bf16 mode ("bf16x3", the fp32-accuracy mode of the UNet): every activation is the SUM of two bf16 tensors, hi =
  * bf16(v) and lo = bf16(v - hi) (16 mantissa bits together), and every convolution is three bf16 tensor-core products
  * hi*W_hi + lo*W_hi + hi*W_lo accumulated in fp32 -- expressed with the ordinary multi-source convolution below as the

@@ -461,3 +461,46 @@ def test_head_as_1x1_gemm_plus_tap_gather(C, H, B, cout):
     p.run()
     assert torch.isfinite(out).all()
     assert rel_l2(out, ref) < 1e-4  # fp32 output of bf16 operands: only the accumulation order differs
+
+
+@pytest.mark.parametrize("B,x_batch,H", [(3, 3, 32), (4, 2, 32), (2, 2, 16), (1, 1, 64)])
+def test_stem_as_gathered_columns_plus_1x1_gemm(B, x_batch, H):
+    """the input conv3x3 (3 -> 128) as dmc_stem_cols (27 (tap, channel) columns of the fp32 input as a bf16 (hi, lo) pair) +
+    ONE 1x1 tcgen05 GEMM against [W | W | 0] (models/unet.py:188,263): the input keeps 16 mantissa bits, so the result matches
+    F.conv2d on the fp32 input with bf16-rounded weights to the bf16 rounding of the output; image n reads x[n % x_batch] (CFG)"""
+    from diffusion_models_collection_b200 import _lib
+
+    cin, cout = 3, 128
+    x = _rand((x_batch, cin, H, H), 41)  # NOT bf16-rounded: the (hi, lo) pair must carry it
+    w = _q(_rand((cout, cin, 3, 3), 42, (cin * 9) ** -0.5))
+    bias = _rand((cout,), 43, 0.1)
+    ref = F.conv2d(x[[n % x_batch for n in range(B)]], w, bias, padding=1)
+    cols = torch.full((B, H, H, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    s = _lib.StemColsDesc()
+    s.x, s.x_batch, s.B, s.Cin, s.H, s.W, s.out = x.data_ptr(), x_batch, B, cin, H, H, cols.data_ptr()
+    wp = pack3(w)
+    wmat = torch.cat([wp, wp, wp.new_zeros(cout, 64 - 54)], dim=1).to(torch.bfloat16).contiguous()
+    out = torch.full((B, H, H, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    slots = max(1, H * H // 32)
+    st = torch.full((B, slots, cout // 8, 2), float("nan"), device="cuda")
+    d = _lib.ConvDesc()
+    d.nsrc = 1
+    d.src[0], d.src_c[0], d.src_taps[0] = cols.data_ptr(), 64, 1
+    d.B, d.Hin, d.Win, d.stride, d.up_phase = B, H, H, 1, -1
+    d.weight, d.Cout, d.Cout_pad, d.Ktot = wmat.data_ptr(), cout, cout, 64
+    d.bias, d.out_bf16 = bias.data_ptr(), out.data_ptr()
+    d.stats, d.stats_slots = st.data_ptr(), slots
+    p = Plan()
+    p.add("stem_cols", s)
+    p.add("conv", d)
+    p.run()
+    assert torch.isfinite(cols.float()).all() and float(cols[..., 54:].float().abs().max()) == 0.0
+    # hi + lo reproduces the fp32 input to 2^-16 relative
+    centre = (cols[..., 4 * cin: 5 * cin].float() + cols[..., 27 + 4 * cin: 27 + 5 * cin].float()).permute(0, 3, 1, 2)
+    xin = x[[n % x_batch for n in range(B)]]
+    assert float((centre - xin).abs().max()) <= 2.0 ** -15 * float(xin.abs().max())
+    got = nchw_f32(out)
+    assert rel_l2(got, ref) < 3e-3
+    tot = st.sum(dim=1)
+    want_ss = (ref * ref).reshape(B, cout // 8, 8, -1).sum(dim=(2, 3))
+    assert rel_l2(tot[..., 1], want_ss) < 1e-3
