@@ -449,8 +449,10 @@ class UNet(nn.Module):
     # 3x3 implicit GEMM (which re-reads its input 4.5x through the slab path: 0.55 ms against ~0.2 ms at 2048 images)
     head_taps = os.environ.get("DMC_HEAD_TAPS", "1") != "0"
     # input conv3x3 (3 -> C) as a gather of 27 (tap, channel) columns (bf16 hi + lo of the fp32 input) + a 1x1 tcgen05 GEMM whose
-    # epilogue also writes the GroupNorm partial sums; 0: the fp32 CUDA-core stem kernel + a stand-alone statistics pass
-    stem_gemm = os.environ.get("DMC_STEM_GEMM", "1") != "0"
+    # epilogue also writes the GroupNorm partial sums.  OPT-IN: measured (run 12, 2048 images) 0.45 ms gather + 0.25 ms GEMM
+    # against 0.49 + 0.10 ms for the fp32 CUDA-core stem kernel + the stand-alone statistics pass, and the bf16 weights of the
+    # first layer cost parity (whole-model eps error at batch 16: 6.8e-3 against 6.2e-3) -- the exact fp32 stem stays the default
+    stem_gemm = os.environ.get("DMC_STEM_GEMM", "0") != "0"
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"

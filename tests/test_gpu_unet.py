@@ -408,6 +408,24 @@ def test_groupnorm_fused_into_conv_epilogues_matches_the_stand_alone_passes(gold
     assert ea < TOL_EPS_BF16 and eb < TOL_EPS_BF16 and rel_l2(a, b) < 1.5e-2
 
 
+def test_stem_gemm_option_matches_the_fp32_stem(monkeypatch, golden):
+    """UNet.stem_gemm (opt-in): input conv as gathered bf16 (hi, lo) columns + a 1x1 tcgen05 GEMM, no stand-alone statistics pass"""
+    from diffusion_models_collection_b200.models import UNet
+
+    c = UNET_CASES["cond_labels"]
+    x, t, y = case_inputs(c)
+    net = build_unet(synth.CIFAR_UNET, 10, c["wseed"])
+    with torch.no_grad():
+        a = net(x.cuda(), t.cuda(), y.cuda())
+    monkeypatch.setattr(UNet, "stem_gemm", True)
+    net2 = build_unet(synth.CIFAR_UNET, 10, c["wseed"])
+    with torch.no_grad():
+        b = net2(x.cuda(), t.cuda(), y.cuda())
+    names = net2.plan_info(4).op_names
+    assert "input_conv.gather" in names and "gn_stats" not in names and "gn_stats" in net.plan_info(4).op_names
+    assert rel_l2(a, b) < 5e-3 and rel_l2(b, torch.from_numpy(golden["unet"]["cond_labels"])) < TOL_EPS_BF16
+
+
 def test_fused_head_path_matches_two_kernel_path(monkeypatch):
     """the opt-in fused output head (GroupNorm + SiLU + conv3x3 in one kernel) vs the default gn_apply + conv path"""
     from diffusion_models_collection_b200.models import UNet

@@ -108,7 +108,7 @@ def test_weight_repack_items_describe_every_gemm_operand(fake_lib):
         assert it.mode == 0 and it.taps in (1, 9) and it.cin == it.cin_total
         rows.setdefault(it.dst, []).append(it)
     names = [n for n, p in net.named_parameters() if p.dim() == 4 and not n.startswith("input_conv")]
-    # + the input convolution twice: [W | W | 0], the matrix of the gathered-columns GEMM (hi and lo parts of the fp32 input)
+    # + the input convolution twice: [W | W | 0], the matrix of the opt-in gathered-columns stem GEMM (hi / lo parts of the input)
     assert len(items) == len(names) + 2
     x, t, y = torch.randn(2, 3, 32, 32), torch.randint(0, 1000, (2,)), torch.randint(0, 11, (2,))
     net._run_train(x, t, y)
