@@ -102,12 +102,62 @@ _REF = {}
 
 def _reference():
     """the reference's own classes (oracle/ref_loader.py: /root/reference in the build container, the archive
-    oracle/_ref/reference_src.zip on the GPU box)"""
+    oracle/_ref/reference_src.zip on the GPU box).  Only when NEITHER exists (a checkout of this repo that never ran
+    `python oracle/make_ref.py`): the oracle port behind the same three call signatures, labelled kind = "port"."""
     if not _REF:
         from oracle import ref_loader
 
-        _REF.update(ref_loader.import_reference())
+        if ref_loader.available():
+            _REF.update(ref_loader.import_reference())
+            _REF["cpu_kind"] = "reference"
+        else:
+            _REF.update(_port_adapters())
     return _REF
+
+
+def _port_adapters():
+    """UNet / DDIM / DDPM look-alikes over the CPU oracle restatement (oracle/model_oracle.py, oracle/sched_oracle.py): the
+    few calls the CPU legs make -- construct, load_state_dict, eval / train, sample, sample_with_cfg, p_losses"""
+    from diffusion_models_collection_b200 import synth
+    from oracle import model_oracle, sched_oracle as so
+
+    class PortUNet(torch.nn.Module):
+        def __init__(self, num_classes=None, **cfg):
+            super().__init__()
+            self.cfg, self.num_classes = cfg, num_classes
+            sd = synth.make_unet_state_dict(cfg, num_classes, seed=42)
+            self.names = list(sd)
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(v) for v in sd.values()])
+
+        def load_state_dict(self, sd, strict=True):
+            with torch.no_grad():
+                for n, p in zip(self.names, self.ps):
+                    p.copy_(sd[n])
+
+        def forward(self, x, t, y=None):
+            sd = dict(zip(self.names, self.ps))
+            fn = model_oracle.unet_forward if not torch.is_grad_enabled() else model_oracle.unet_forward.__wrapped__
+            return fn(sd, self.cfg, x, t, y, self.num_classes)
+
+    class PortDDIM:
+        def __init__(self, T, S, b0, b1, sched, eta=0.0, device="cpu"):
+            self.tb, self.ts = so.make_tables(T, b0, b1, sched), so.ddim_timesteps(T, S)
+
+        def sample(self, model, shape):
+            return so.ddim_sample(model, self.tb, self.ts, torch.randn(shape))
+
+        def sample_with_cfg(self, model, shape, y, cfg_scale=3.0):
+            return so.ddim_sample_cfg(model, self.tb, self.ts, torch.randn(shape), y, cfg_scale=cfg_scale)
+
+    class PortDDPM:
+        def __init__(self, T, b0, b1, sched, device="cpu"):
+            self.tb = so.make_tables(T, b0, b1, sched)
+
+        def p_losses(self, model, x0, t, y=None, loss_type="l2"):
+            noise = torch.randn_like(x0)
+            return torch.nn.functional.mse_loss(noise, model(so.q_sample(self.tb, x0, t, noise), t, y))
+
+    return dict(UNet=PortUNet, DDIM=PortDDIM, DDPM=PortDDPM, kind="oracle port: oracle/_ref is missing", cpu_kind="port")
 
 
 def _set_seed(seed):
@@ -137,7 +187,7 @@ def cpu_reference_config1():
         img = d.sample(net, (16, 3, 32, 32))
     dt = time.perf_counter() - t0
     assert tuple(img.shape) == (16, 3, 32, 32) and bool(torch.isfinite(img).all())
-    return {"value": 16 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference", "seconds": dt,
+    return {"value": 16 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref["cpu_kind"], "seconds": dt,
             "sample": "BASELINE.json configs[0] verbatim: the reference's own DDIM(50 steps).sample(UNet uncond, default init "
                       f"under seed 42, (16, 3, 32, 32)), fp32 on the host, all 50 steps, no extrapolation ({ref['kind']})"}
 
@@ -166,7 +216,7 @@ def cpu_reference_images_per_sec(batch=4):
         img = _CFG_NET["ddim"].sample_with_cfg(_CFG_NET["net"], (batch, 3, 32, 32), y, cfg_scale=3.0)
     dt = time.perf_counter() - t0
     assert tuple(img.shape) == (batch, 3, 32, 32) and bool(torch.isfinite(img).all())
-    return batch / dt, {"value": batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+    return batch / dt, {"value": batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref["cpu_kind"],
                         "sample": f"{batch} images of the 4096-image step through the reference's own DDIM.sample_with_cfg (all 50 "
                                   f"steps, 2 UNet forwards each, CFG 3.0, dynamic threshold 0.995), fp32 on the host ({ref['kind']})"}
 
@@ -198,7 +248,7 @@ def cpu_reference_train_images_per_sec(batch=8, steps=1):
         opt.zero_grad()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return batch / best, {"value": batch / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+    return batch / best, {"value": batch / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref["cpu_kind"],
                           "sample": f"{steps} training step(s) of {batch} images through the reference's own DDPM.p_losses + "
                                     f"backward + clip_grad_norm_ + AdamW, fp32 on the host ({ref['kind']})"}
 
