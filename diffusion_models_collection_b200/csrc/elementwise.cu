@@ -509,23 +509,39 @@ int launch_stem_cols(const dmc_stem_cols_desc& d, cudaStream_t st) {
 // =============================================================================================
 constexpr int HT_ROWS = 8;
 
+// POW2: W and ypitch / 4 are powers of two (the CIFAR head: W = 32, ypitch = 32) -- the index arithmetic is shifts and masks;
+// the generic form spends more time in integer division than in memory traffic
+template <bool POW2>
 __global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict__ y, const float* __restrict__ bias,
-                                                        float* __restrict__ out, int H, int W, int Cout, int ypitch) {
+                                                        float* __restrict__ out, int H, int W, int Cout, int ypitch, int lw,
+                                                        int lv) {
   extern __shared__ float s_y[];
   const int n = blockIdx.y, r0 = blockIdx.x * HT_ROWS;
   const int pitch = ypitch + 1;
   const int rows = min(HT_ROWS, H - r0);
-  // stage rows r0 - 1 .. r0 + rows (zero outside the image): float4 loads, scalar stores (odd pitch)
-  const int nvec = (rows + 2) * W * (ypitch / 4);
   const int vpp = ypitch / 4;  // float4 per pixel
-  for (int e0 = threadIdx.x; e0 < nvec; e0 += blockDim.x * 5) {  // five independent 16-byte loads in flight per thread
+  const int nvec = (rows + 2) * W * vpp;
+  auto split = [&](int e, int& v, int& px, int& rr) {
+    if (POW2) {
+      v = e & (vpp - 1);
+      px = (e >> lv) & (W - 1);
+      rr = e >> (lv + lw);
+    } else {
+      v = e % vpp;
+      px = (e / vpp) % W;
+      rr = e / (vpp * W);
+    }
+  };
+  // stage rows r0 - 1 .. r0 + rows (zero outside the image): float4 loads (five in flight per thread), scalar stores (odd pitch)
+  for (int e0 = threadIdx.x; e0 < nvec; e0 += blockDim.x * 5) {
     float4 t[5];
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       const int e = e0 + u * blockDim.x;
       t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e < nvec) {
-        const int v = e % vpp, px = (e / vpp) % W, rr = e / (vpp * W);
+        int v, px, rr;
+        split(e, v, px, rr);
         const int gy = r0 - 1 + rr;
         if (gy >= 0 && gy < H) t[u] = __ldg(reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * H + gy) * W + px) * ypitch) + v);
       }
@@ -534,7 +550,8 @@ __global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict_
     for (int u = 0; u < 5; ++u) {
       const int e = e0 + u * blockDim.x;
       if (e < nvec) {
-        const int v = e % vpp, px = (e / vpp) % W, rr = e / (vpp * W);
+        int v, px, rr;
+        split(e, v, px, rr);
         float* d = s_y + (rr * W + px) * pitch + 4 * v;
         d[0] = t[u].x; d[1] = t[u].y; d[2] = t[u].z; d[3] = t[u].w;
       }
@@ -542,7 +559,7 @@ __global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict_
   }
   __syncthreads();
   for (int e = threadIdx.x; e < rows * W; e += blockDim.x) {
-    const int j = e % W, i = e / W;  // local row i -> staged row i + 1
+    const int j = POW2 ? (e & (W - 1)) : e % W, i = POW2 ? (e >> lw) : e / W;  // local row i -> staged row i + 1
     for (int co = 0; co < Cout; ++co) {
       float acc = bias ? __ldg(bias + co) : 0.f;
 #pragma unroll
@@ -559,14 +576,21 @@ __global__ void __launch_bounds__(256) head_taps_kernel(const float* __restrict_
 int launch_head_taps(const dmc_head_taps_desc& d, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(HT_ROWS + 2) * d.W * (d.ypitch + 1) * sizeof(float);
   DMC_REQUIRE(smem <= 200 * 1024, "head_taps: image too wide (W=%d)", d.W);
+  const int vpp = d.ypitch / 4;
+  const bool pow2 = (d.W & (d.W - 1)) == 0 && (vpp & (vpp - 1)) == 0;
+  int lw = 0, lv = 0;
+  while ((1 << lw) < d.W) ++lw;
+  while ((1 << lv) < vpp) ++lv;
   static DeviceOnce attr_set;
   int attr_dev = 0;
   if (smem > 48 * 1024 && attr_set.need(&attr_dev)) {
-    DMC_CUDA_OK(cudaFuncSetAttribute(head_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DMC_CUDA_OK(cudaFuncSetAttribute(head_taps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DMC_CUDA_OK(cudaFuncSetAttribute(head_taps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set.done(attr_dev);
   }
   dim3 grid((d.H + HT_ROWS - 1) / HT_ROWS, d.B);
-  head_taps_kernel<<<grid, 256, smem, st>>>(d.y, d.bias, d.out, d.H, d.W, d.Cout, d.ypitch);
+  if (pow2) head_taps_kernel<true><<<grid, 256, smem, st>>>(d.y, d.bias, d.out, d.H, d.W, d.Cout, d.ypitch, lw, lv);
+  else head_taps_kernel<false><<<grid, 256, smem, st>>>(d.y, d.bias, d.out, d.H, d.W, d.Cout, d.ypitch, lw, lv);
   DMC_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -122,6 +122,11 @@ class DiffusionBase:
         total, lo, hi = sh
         return torch.randn((total,) + tuple(img.shape[1:]), device=img.device, dtype=img.dtype)[lo:hi]
 
+    def _steps_for_empty(self):
+        """the steps a sampling loop would run (length of the trajectory returned with return_all_timesteps)"""
+        ts = getattr(self, "inference_timesteps", None)
+        return range(len(ts)) if ts is not None else range(self.num_timesteps)
+
     # ---- whole-loop CUDA graph ------------------------------------------------------------------
     def _graph_ok(self, model, return_all_timesteps, step_noise):
         return (self.use_cuda_graph and not return_all_timesteps and step_noise is None

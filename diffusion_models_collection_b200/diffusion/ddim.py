@@ -102,6 +102,8 @@ class DDIM(DiffusionBase):
         device = self.device
         img = torch.randn(shape, device=device) if noise is None else noise.to(device).float().clone()
         self._require_cuda(img, "DDIM.sample")
+        if img.shape[0] == 0:  # empty batch: the reference's loop runs S no-op steps and returns the empty tensor
+            return img.new_empty((len(self._steps_for_empty()),) + tuple(img.shape)).cpu() if return_all_timesteps else img
         B = shape[0]
         n = img.numel() // B
         coefs = self._coef_table().to(img.device)
@@ -142,6 +144,8 @@ class DDIM(DiffusionBase):
         device = self.device
         img = torch.randn(shape, device=device) if noise is None else noise.to(device).float().clone()
         self._require_cuda(img, "DDIM.sample_with_cfg")
+        if img.shape[0] == 0:  # empty batch: the reference's loop runs S no-op steps and returns the empty tensor
+            return img.new_empty((len(self._steps_for_empty()),) + tuple(img.shape)).cpu() if return_all_timesteps else img
         B = shape[0]
         n = img.numel() // B
         coefs = self._coef_table().to(img.device)

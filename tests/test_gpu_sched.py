@@ -277,3 +277,20 @@ def test_sharded_sampling_with_per_step_noise_reproduces_the_single_process_run(
         d._noise_shard = (B, lo, hi)
         parts.append(d.sample(model, (hi - lo,) + shape[1:], noise=x_T[lo:hi]))
     assert torch.equal(torch.cat(parts, dim=0), whole)
+
+
+def test_empty_batch_samples_like_the_reference():
+    """shape (0, C, H, W): the reference's loops run S no-op steps and return an empty tensor (a trajectory of S empty ones)"""
+    from diffusion_models_collection_b200.diffusion import DDIM, DDPM
+    from oracle.sched_oracle import toy_model
+
+    d = DDIM(1000, 5, device=torch.device("cuda"))
+    d.progress = False
+    assert tuple(d.sample(toy_model, (0, 3, 32, 32)).shape) == (0, 3, 32, 32)
+    assert tuple(d.sample(toy_model, (0, 3, 32, 32), return_all_timesteps=True).shape) == (5, 0, 3, 32, 32)
+    y = torch.zeros(0, dtype=torch.long, device="cuda")
+    assert tuple(d.sample_with_cfg(toy_model, (0, 3, 32, 32), y).shape) == (0, 3, 32, 32)
+    p = DDPM(7, device=torch.device("cuda"))
+    p.progress = False
+    assert tuple(p.sample(toy_model, (0, 3, 32, 32)).shape) == (0, 3, 32, 32)
+    assert tuple(p.sample_with_cfg(toy_model, (0, 3, 32, 32), y, return_all_timesteps=True).shape) == (7, 0, 3, 32, 32)
