@@ -69,7 +69,7 @@ class ConvDesc(C.Structure):
                 ("out_lo", vp), ("residual_lo", vp), ("unpatch_p", C.c_int32),
                 ("gn_nver", C.c_int32), ("gn_out", vp * 2), ("gn_pitch", C.c_int32 * 2), ("gn_coff", C.c_int32 * 2),
                 ("gn_gamma", vp * 2), ("gn_beta", vp * 2), ("gn_gsize", C.c_int32 * 2), ("gn_silu", C.c_int32 * 2),
-                ("gn_eps", C.c_float), ("gn_counters", vp)]
+                ("gn_eps", C.c_float), ("gn_counters", vp), ("a_affine", vp)]
 
 
 class DitCondDesc(C.Structure):
@@ -150,6 +150,11 @@ class UpsampleDesc(C.Structure):
     _fields_ = [("src", vp), ("out", vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32)]
 
 
+class GnCoeffDesc(C.Structure):
+    _fields_ = [("stats", vp), ("stats_slots", C.c_int32), ("B", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32),
+                ("groups", C.c_int32), ("gamma", vp), ("beta", vp), ("eps", C.c_float), ("out", vp)]
+
+
 class StemColsDesc(C.Structure):
     _fields_ = [("x", vp), ("x_batch", C.c_int32), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("out", vp)]
@@ -220,12 +225,14 @@ SYMBOLS = {
     "dmc_plan_add_upsample": (C.c_int, [vp, C.POINTER(UpsampleDesc)]),
     "dmc_plan_add_head_taps": (C.c_int, [vp, C.POINTER(HeadTapsDesc)]),
     "dmc_plan_add_stem_cols": (C.c_int, [vp, C.POINTER(StemColsDesc)]),
+    "dmc_plan_add_gn_coeff": (C.c_int, [vp, C.POINTER(GnCoeffDesc)]),
+    "dmc_conv_affine_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmc_plan_add_ddim_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
     "dmc_plan_add_ddpm_step": (C.c_int, [vp, C.POINTER(StepDesc)]),
 }
 
 OP_KINDS = ["memset", "cond", "stem", "gn_stats", "gn_apply", "conv", "attention", "upsample", "ddim", "ddpm", "dit_cond",
-            "patch_embed", "ln_modulate", "head", "head_taps", "stem_cols"]
+            "patch_embed", "ln_modulate", "head", "head_taps", "stem_cols", "gn_coeff"]
 
 _lock = threading.Lock()
 _lib = None

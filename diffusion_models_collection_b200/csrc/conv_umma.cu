@@ -97,6 +97,22 @@ static int conv_m_tiles(int B, int Hout, int Wout, int* tiles_w_out) {
   return ((B + BNIMG - 1) / BNIMG) * (Wout / BW) * (Hout / BH);
 }
 
+// resident weights (the whole K extent of one weight tile stays in shared memory): short-K GEMMs only
+static bool bres_ok(const TileCfg& tc, int num_kb, int num_n_tiles) {
+  const int b_tile = (tc.bn / tc.cg) * KB * 2;
+  return num_kb <= 8 && num_kb * b_tile <= 112 * 1024 && num_n_tiles <= 12 && num_n_tiles <= (num_sms() / tc.cg);
+}
+
+bool conv_affine_supported(int B, int H, int W, int Cin, int Cout) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cin % KB != 0 || Cout % 32 != 0) return false;
+  const int m_tiles = conv_m_tiles(B, H, W, nullptr);
+  if (m_tiles == 0) return false;
+  const TileCfg tc = pick_cfg(Cout, m_tiles);
+  const char* e = getenv("DMC_CONV_BRES");
+  if (e && e[0] == '0') return false;
+  return bres_ok(tc, Cin / KB, Cout / tc.bn);
+}
+
 bool conv_gn_supported(int B, int Hout, int Wout, int Cout, int max_gsz) {
   if (B <= 0 || Hout <= 0 || Wout <= 0 || Cout % 32 != 0 || !(max_gsz == 16 || max_gsz == 32 || max_gsz == 64)) return false;
   int tiles_w = 0;
@@ -276,8 +292,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   //     are L2->SM bound; with the whole K extent of one weight tile resident only activations stream.
   kp.bres = 0;
   kp.b_region_bytes = 0;
-  if (env_flag("DMC_CONV_BRES", 1) && epi != 2 && epi != 4 && kp.num_kb <= 8 && kp.num_kb * b_tile <= 112 * 1024 &&
-      kp.num_n_tiles <= 12 && kp.num_n_tiles <= (num_sms() / tc.cg)) {
+  if (env_flag("DMC_CONV_BRES", 1) && epi != 2 && epi != 4 && bres_ok(tc, kp.num_kb, kp.num_n_tiles)) {
     kp.bres = 1;
     kp.b_region_bytes = kp.num_kb * b_tile;
   }
@@ -405,6 +420,12 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.Cout = d.Cout;
   kp.bias = d.bias; kp.cond = d.cond; kp.cond_stride = d.cond_stride;
   kp.prefetch_cond = env_flag("DMC_CONV_PREFETCH_COND", 1);
+  kp.a_affine = reinterpret_cast<const float2*>(d.a_affine);
+  kp.aff_C = d.src_c[0];
+  if (d.a_affine != nullptr && !(kp.bres && !kp.slab && epi == 0 && d.nsrc == 1 && d.src_taps[0] == 1 && d.stride == 1 && !gn)) {
+    delete P;
+    DMC_REQUIRE(false, "conv: a_affine needs a plain 1x1 convolution (one source, stride 1) that runs with resident weights");
+  }
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
   kp.out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   kp.out_nchw = d.out_f32_nchw;

@@ -35,6 +35,10 @@ struct ConvKParams {
   const float* cond;
   int cond_stride;
   int prefetch_cond;          // prefetch the tile's conditioning row into L1 before waiting for the accumulator
+  // A-operand affine transform (GroupNorm without SiLU applied to the input of a 1x1 convolution, models/unet.py:80-81): the
+  // otherwise idle warps 2 and 3 rewrite every landed A tile in shared memory as x * scale[n, c] + shift[n, c] before the MMAs
+  const float2* a_affine;     // [B, C_src] (scale, shift) of source 0, or nullptr
+  int aff_C;                  // channels of source 0
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
   float* out_nchw;
@@ -208,6 +212,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* bfull_bar = tempty_bar + 2;   // resident weights loaded
   uint64_t* rbar = bfull_bar + 1;         // residual boxes: [epilogue warp][staging buffer]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * (EPI_THREADS / 32));
+  uint64_t* afull_bar = rbar + 2 * (EPI_THREADS / 32) + 1;  // A-affine mode: this CTA's A tile has landed (per stage)
+  uint64_t* xf_bar = afull_bar + MAX_NST;                   // ... and has been transformed in BOTH CTAs of a pair (on the leader)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -250,6 +256,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tempty_bar[i], CG * (EPI_THREADS / 32));  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bfull_bar, 1);
+    if (p.a_affine != nullptr) {
+      for (int i = 0; i < NST; ++i) {
+        mbar_init(&afull_bar[i], 1);
+        mbar_init(&xf_bar[i], CG * 2);  // warps 2 and 3 of every CTA of the group
+      }
+    }
     for (int i = 0; i < 2 * (EPI_THREADS / 32); ++i) mbar_init(&rbar[i], 1);
     mbar_fence_init();
   }
@@ -323,10 +335,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           } else {
             const int kb = reg_kb0 + (step - slab_steps);
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (Cfg::A_BYTES + (bres ? 0 : B_TILE)));
             const int chunks = p.seg_chunks[seg];
             const int tap = kb_in_seg / chunks, chunk = kb_in_seg % chunks;
             const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+            if (bres && p.a_affine != nullptr) {
+              // A-affine mode (resident weights: the ring holds A tiles only): every CTA counts ITS OWN A tile on its own
+              // barrier -- its transform warps wait there, and hand the tile to the MMA warp through xf_bar
+              mbar_expect_tx(&afull_bar[stage], Cfg::A_BYTES);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &afull_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
+                            h0[mt] + p.dh[seg][tap], n0[mt]);
+            } else {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (Cfg::A_BYTES + (bres ? 0 : B_TILE)));
             if (CG == 2) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt)
@@ -339,6 +360,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tma_load_4d(sa + mt * A_STAGE_BYTES, tm, &full_bar[stage], chunk * KB, w0[mt] + p.dw[seg][tap],
                             h0[mt] + p.dh[seg][tap], n0[mt]);
               if (!bres) tma_load_2d(sb, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
+            }
             }
             if (++kb_in_seg == p.seg_taps[seg] * chunks) {
               ++seg;
@@ -373,7 +395,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         uint32_t accum = 0;
         for (int step = 0; step < num_steps; ++step) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait((bres && p.a_affine != nullptr) ? &xf_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
           const uint32_t sb = sa + p.a_bytes;
@@ -421,7 +443,69 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         else umma_commit(&tfull_bar[acc]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ===================== A-operand affine transform (warps 2 and 3, 1x1 convolutions with resident weights) ==========
+    // thread = (16-byte chunk cl of the 128-byte row, row group rg): it owns 8 fixed channels of the K block -- its
+    // (scale, shift) pairs are loaded once per image -- and rewrites rows rg, rg + 8, ... in place; the physical chunk is
+    // cl ^ (row & 7) = cl ^ rg (128-byte swizzle).  y = fma(x, scale, shift) rounded to bf16: bit-identical to gn_apply_kernel.
+    if (bres && p.a_affine != nullptr) {
+      const int tw = (warp - 2) * 32 + lane;
+      const int cl = tw & 7, rg = tw >> 3;
+      const int ppi = p.BW * p.BH;
+      uint32_t phase = 0;
+      int stage = 0;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        DMC_DECODE_TILE(tile, n_tile, ct)
+        (void)n_tile;
+        for (int step = 0; step < num_steps; ++step) {
+          mbar_wait(&afull_bar[stage], phase);
+          const int ch0 = step * KB + cl * 8;  // (one source, one tap: K block = 64-channel chunk `step`)
+#pragma unroll 1
+          for (int mt = 0; mt < MT; ++mt) {
+            const int m_tile = ct * MTG + rank * MT + mt;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.BNIMG;
+            uint8_t* base = ring + stage * p.stage_bytes + mt * A_STAGE_BYTES + ((cl ^ rg) << 4);
+            int cur = -1;
+            float sc[8], sh[8];
+#pragma unroll 4
+            for (int i = 0; i < TILE_M / 8; ++i) {
+              const int r = rg + 8 * i;
+              const int img = min(n0 + r / ppi, p.B - 1);  // (rows past the batch are zero-filled and never stored)
+              if (img != cur) {
+                cur = img;
+                const float4* c4 = reinterpret_cast<const float4*>(p.a_affine + static_cast<size_t>(img) * p.aff_C + ch0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 t = __ldg(c4 + j);
+                  sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
+                }
+              }
+              uint4* ptr = reinterpret_cast<uint4*>(base + r * 128);
+              const uint4 v = *ptr;
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(w[j]);
+                o[j] = pack_bf16x2(fmaf(f.x, sc[2 * j], sh[2 * j]), fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]));
+              }
+              *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's shared-memory reads
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&xf_bar[stage]), 0));
+            else mbar_arrive(&xf_bar[stage]);
+          }
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
     // ===================== epilogue (8 warps) =====================
     // warp -> TMEM lane quarter q (= warp % 4, the hardware rule) and group grp: with MT == 2 the group is the
     // 128-pixel sub-tile, with MT == 1 it is the half of the BN output channels this warp converts.

@@ -453,6 +453,55 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
 }
 
 // =============================================================================================
+// GroupNorm coefficients: out[n, c] = (scale, shift) with scale = rstd_g * gamma_c, shift = beta_c - mean_g * scale.  One CTA per
+// image; phase 1 is gn_apply_kernel's (warp g reduces the partial sums of group g: lane-strided loads, fixed shuffle tree), so
+// the statistics -- and fma(x, scale, shift) -- are bit-identical to the stand-alone pass.  Consumed by the A-operand affine
+// transform of the 1x1 convolution that follows (dmc_conv_desc.a_affine).
+// =============================================================================================
+__global__ void __launch_bounds__(256) gn_coeff_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float2* __restrict__ out, int slots, int HW,
+                                                       int C, int groups, float eps) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int n = blockIdx.x, C8 = C >> 3, gs8 = C8 / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < groups; g += 8) {
+    const int blo = g * gs8;
+    float s = 0.f, ss = 0.f;
+    const float2* base = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(n) * slots * C8;
+    for (int e = lane; e < gs8 * slots; e += 32) {
+      const float2 v = __ldg(base + static_cast<size_t>(e / gs8) * C8 + blo + e % gs8);
+      s += v.x;
+      ss += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    }
+    if (lane == 0) {
+      const float inv_cnt = 1.0f / (static_cast<float>(gs8 * 8) * static_cast<float>(HW));
+      const float mean = s * inv_cnt;
+      const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + eps);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = (c >> 3) / gs8;
+    const float s1 = s_rstd[g] * __ldg(gamma + c);
+    out[static_cast<size_t>(n) * C + c] = make_float2(s1, __ldg(beta + c) - s_mean[g] * s1);
+  }
+}
+
+int launch_gn_coeff(const dmc_gn_coeff_desc& d, cudaStream_t st) {
+  gn_coeff_kernel<<<d.B, 256, 0, st>>>(d.stats, d.gamma, d.beta, reinterpret_cast<float2*>(d.out), d.stats_slots, d.HW, d.C,
+                                        d.groups, d.eps);
+  DMC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
 // Input convolution, tensor-core form (see dmc_stem_cols_desc): gather the 3x3 neighbourhood of every pixel of the fp32 NCHW
 // input into one 64-channel bf16 NHWC row [taps as bf16 | their rounding remainders | 0]; the 1x1 tcgen05 GEMM does the rest.
 // thread = (pixel, 16-byte chunk of its row): the 8 lanes of a pixel write its 128-byte row as one full line; the fp32

@@ -26,6 +26,7 @@ int launch_upsample(const dmc_upsample_desc& d, cudaStream_t st);
 int launch_head_fused(const dmc_head_desc& d, cudaStream_t st);
 int launch_head_taps(const dmc_head_taps_desc& d, cudaStream_t st);
 int launch_stem_cols(const dmc_stem_cols_desc& d, cudaStream_t st);
+int launch_gn_coeff(const dmc_gn_coeff_desc& d, cudaStream_t st);
 bool head_fused_supported(const dmc_head_desc& d);
 
 // dit_ops.cu
@@ -49,6 +50,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out);
 void conv_release(ConvPrepared* p);
 int launch_conv(const dmc_conv_desc& d, const ConvPrepared* p, cudaStream_t st);
 bool conv_gn_supported(int B, int Hout, int Wout, int Cout, int max_gsz);
+bool conv_affine_supported(int B, int H, int W, int Cin, int Cout);
 // train_ops.cu : non-GEMM backward kernels
 uint32_t dropout_threshold(float p);
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st);

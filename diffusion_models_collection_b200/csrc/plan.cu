@@ -26,7 +26,7 @@ int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 
 enum OpKind { OP_MEMSET = 0, OP_COND, OP_STEM, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_UPSAMPLE, OP_DDIM, OP_DDPM,
-              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD, OP_HEAD_TAPS, OP_STEM_COLS };
+              OP_DIT_COND, OP_PATCH_EMBED, OP_LN_MOD, OP_HEAD, OP_HEAD_TAPS, OP_STEM_COLS, OP_GN_COEFF };
 
 struct Op {
   int kind;
@@ -46,6 +46,7 @@ struct Op {
     dmc_head_desc head;
     dmc_head_taps_desc head_taps;
     dmc_stem_cols_desc stem_cols;
+    dmc_gn_coeff_desc gn_coeff;
   };
   ConvPrepared* conv_prep;
   AttnPrepared* attn_prep;
@@ -83,6 +84,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_HEAD: return launch_head_fused(op.head, st);
     case OP_HEAD_TAPS: return launch_head_taps(op.head_taps, st);
     case OP_STEM_COLS: return launch_stem_cols(op.stem_cols, st);
+    case OP_GN_COEFF: return launch_gn_coeff(op.gn_coeff, st);
   }
   set_error("plan: unknown op kind %d", op.kind);
   return -1;
@@ -456,6 +458,22 @@ int dmc_plan_add_head(dmc_plan* p, const dmc_head_desc* d) {
   const double pix = static_cast<double>(d->B) * d->H * d->W;
   op.bytes = pix * (2.0 * d->C + 4.0 * d->Cout);
   op.flops = 2.0 * pix * d->Cout * d->C * 9;
+  return push(p, op);
+}
+
+int dmc_conv_affine_supported(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+  return conv_affine_supported(B, H, W, Cin, Cout) ? 1 : 0;
+}
+
+int dmc_plan_add_gn_coeff(dmc_plan* p, const dmc_gn_coeff_desc* d) {
+  DMC_REQUIRE(p && d, "dmc_plan_add_gn_coeff: null argument");
+  DMC_REQUIRE(d->stats && d->gamma && d->beta && d->out && d->B > 0 && d->HW > 0 && d->stats_slots > 0 && d->groups > 0 &&
+                  d->groups <= 32 && d->C % 8 == 0 && (d->C / 8) % d->groups == 0 && d->C <= 1024,
+              "dmc_plan_add_gn_coeff: bad arguments (C=%d groups=%d)", d->C, d->groups);
+  Op op;
+  op.kind = OP_GN_COEFF;
+  op.gn_coeff = *d;
+  op.bytes = static_cast<double>(d->B) * (8.0 * d->stats_slots * (d->C / 8) + 8.0 * d->C);
   return push(p, op);
 }
 

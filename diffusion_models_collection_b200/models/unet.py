@@ -157,7 +157,11 @@ class _PlanBuilder:
             if o["out"] is not None:
                 t.append(o["out"])
             t += [v["dst"] for v in o.get("gn", ())]
+            if o.get("aff") is not None:
+                t.append(o["aff"])
             return t
+        if kind == "gn_coeff":
+            return [o["src"], o["out"]]
         if kind == "attention":
             return [o["qkv"], o["out"]]
         if kind == "upsample":
@@ -179,7 +183,7 @@ class _PlanBuilder:
             if kind == "conv" and o["out"] is not None:
                 writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 1
                 producer[id(o["out"])] = i
-            elif kind in ("stem", "stem_cols", "upsample", "attention", "gn_apply"):
+            elif kind in ("stem", "stem_cols", "upsample", "attention", "gn_apply", "gn_coeff"):
                 writers[id(o["out"])] = writers.get(id(o["out"]), 0) + 99
         readers = {}  # how many ops read each tensor
         for kind, o in self.ops:
@@ -188,7 +192,7 @@ class _PlanBuilder:
                 rd = list(o["srcs"]) + ([o["residual"]] if o["residual"] is not None else [])
             elif kind == "gn_apply":
                 rd = list(o["srcs"])
-            elif kind in ("head", "head_taps", "upsample"):
+            elif kind in ("head", "head_taps", "upsample", "gn_coeff"):
                 rd = [o["src"]]
             elif kind == "attention":
                 rd = [o["qkv"]]
@@ -242,7 +246,7 @@ class _PlanBuilder:
                     read.add(id(o["residual"]))
             elif kind == "gn_apply":
                 read.update(id(s_) for s_ in o["srcs"])
-            elif kind in ("gn_stats", "head", "head_taps", "upsample"):
+            elif kind in ("gn_stats", "gn_coeff", "head", "head_taps", "upsample"):
                 read.add(id(o["src"]))
             elif kind == "attention":
                 read.add(id(o["qkv"]))
@@ -289,7 +293,7 @@ class _PlanBuilder:
         return out
 
     def conv(self, srcs, taps, wname, Cout, H, W, stride=1, bias=None, cond_col=None, residual=None, out_nchw=False,
-             up_phase=-1, out=None, want_stats=True, sc_slice=None, out_f32=False):
+             up_phase=-1, out=None, want_stats=True, sc_slice=None, out_f32=False, aff=None):
         Ho, Wo = H // stride, W // stride
         if up_phase >= 0:
             Ho, Wo = 2 * H, 2 * W
@@ -305,7 +309,7 @@ class _PlanBuilder:
         self.ops.append(("conv", dict(srcs=list(srcs), taps=list(taps), parts=parts, wname=wname, Cout=Cout, H=H, W=W,
                                       stride=stride, bias=bias, cond_col=cond_col, residual=residual, out=out,
                                       out_nchw=out_nchw, up_phase=up_phase, want_stats=want_stats, sc_slice=sc_slice,
-                                      out_f32=out_f32)))
+                                      out_f32=out_f32, aff=aff)))
         return out
 
     def fused_head(self, h):
@@ -342,9 +346,17 @@ class _PlanBuilder:
         return out
 
     def attnblock(self, x, prefix):
-        an = self.gn_apply([x], prefix + ".norm", 0)
-        qkv = self.conv([an], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv", want_stats=False)
-        self.free(an)
+        if (self.net.fuse_norm_qkv and not (self.split or self.keep or self.conv_impl != 0) and (x.C // 8) in (16, 32, 64) and
+                _lib.load().dmc_conv_affine_supported(self.B, x.H, x.W, x.C, 3 * x.C)):
+            # GroupNorm (no activation) of the block input applied to the A operand of the qkv GEMM inside the GEMM kernel
+            # (models/unet.py:80-81,86-87): a tiny per-image coefficient kernel replaces the whole normalisation pass
+            co = _Act(self.B * x.C * 8, x.C, 1, 1)  # fp32 [B, C, 2] (scale, shift)
+            self.ops.append(("gn_coeff", dict(src=self.stats_of(x), prefix=prefix + ".norm", out=co)))
+            qkv = self.conv([x], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv", want_stats=False, aff=co)
+        else:
+            an = self.gn_apply([x], prefix + ".norm", 0)
+            qkv = self.conv([an], [1], prefix + ".qkv", 3 * x.C, x.H, x.W, bias=prefix + ".qkv", want_stats=False)
+            self.free(an)
         ao = self.act(x.C, x.H, x.W)
         self.ops.append(("attention", dict(qkv=qkv, out=ao, L=x.H * x.W, C=x.C)))
         self.free(qkv)
@@ -453,6 +465,9 @@ class UNet(nn.Module):
     # against 0.49 + 0.10 ms for the fp32 CUDA-core stem kernel + the stand-alone statistics pass, and the bf16 weights of the
     # first layer cost parity (whole-model eps error at batch 16: 6.8e-3 against 6.2e-3) -- the exact fp32 stem stays the default
     stem_gemm = os.environ.get("DMC_STEM_GEMM", "0") != "0"
+    # AttentionBlock: GroupNorm (no activation) of the block input applied to the A operand of the qkv 1x1 GEMM by two otherwise
+    # idle warps of that kernel (bit-identical to the stand-alone pass, which disappears); 0: gn_apply + plain GEMM
+    fuse_norm_qkv = os.environ.get("DMC_FUSE_NORM_QKV", "1") != "0"
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
@@ -1070,6 +1085,13 @@ class _UNetPlan:
                 d.weight, d.bias = sd["input_conv.weight"].data_ptr(), sd["input_conv.bias"].data_ptr()
                 d.out, d.out_lo = ap(o["out"]), ap_lo(o["out"])
                 self.stem_idx = add(lib.dmc_plan_add_stem, d, "input_conv")
+            elif kind == "gn_coeff":
+                a = o["src"]
+                d = _lib.GnCoeffDesc()
+                d.stats, d.stats_slots, d.B, d.HW, d.C, d.groups = wsp + a.stats[0], a.slots, nimg, a.H * a.W, a.C, 8
+                d.gamma, d.beta = sd[o["prefix"] + ".weight"].data_ptr(), sd[o["prefix"] + ".bias"].data_ptr()
+                d.eps, d.out = 1e-5, ap(o["out"])
+                add(lib.dmc_plan_add_gn_coeff, d, o["prefix"] + ".coeff")
             elif kind == "stem_cols":
                 d = _lib.StemColsDesc()
                 d.x, d.x_batch, d.B = self.eps.data_ptr(), x_batch, nimg  # x is re-bound on every run
@@ -1120,6 +1142,8 @@ class _UNetPlan:
                     d.out_f32_nhwc = ap(o["out"])
                 elif o["out"].raw:
                     d.out_bf16, d.out_lo = ap(o["out"]), ap_lo(o["out"])
+                if o.get("aff") is not None:
+                    d.a_affine = ap(o["aff"])
                 d.impl = conv_impl
                 if conv_impl == 0 and o["out"] is not None and o["out"].stats is not None and o["want_stats"]:
                     d.stats, d.stats_slots = wsp + o["out"].stats[0], o["out"].slots

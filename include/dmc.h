@@ -426,8 +426,26 @@ typedef struct {
   int32_t gn_silu[2];
   float gn_eps;
   int32_t* gn_counters;       /* int32 [2 * B * (Cout / 32)] zeroed once by the caller (only touched when an image spans CTAs) */
+  /* --- GroupNorm WITHOUT activation applied to the INPUT of a 1x1 convolution (the `norm` -> `qkv` pair of AttentionBlock,
+   * models/unet.py:80-81,86-87): src[0] is the raw tensor and a_affine[n, c] = (scale, shift) from dmc_plan_add_gn_coeff; two
+   * otherwise idle warps rewrite every A tile in shared memory as bf16(x * scale + shift) before the MMAs read it -- bit-identical
+   * to the stand-alone GroupNorm pass, which disappears.  One source, one tap, resident weights (dmc_conv_affine_supported). --- */
+  const float* a_affine;      /* fp32 [B, src_c[0], 2] or NULL */
 } dmc_conv_desc;
 DMC_API int dmc_plan_add_conv(dmc_plan* p, const dmc_conv_desc* d);
+/* 1 when a 1x1 convolution of this geometry runs with resident weights, i.e. can take a_affine */
+DMC_API int dmc_conv_affine_supported(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+/* per-image per-channel (scale, shift) of GroupNorm(groups, C) from the partial sums of a tensor: out[n, c] = (rstd_g * gamma_c,
+ * beta_c - mean_g * rstd_g * gamma_c), same summation order as dmc_plan_add_gn_apply */
+typedef struct {
+  const float* stats;  /* [B, stats_slots, C/8, 2] */
+  int32_t stats_slots, B, HW, C, groups;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out;          /* fp32 [B, C, 2] */
+} dmc_gn_coeff_desc;
+DMC_API int dmc_plan_add_gn_coeff(dmc_plan* p, const dmc_gn_coeff_desc* d);
 /* 1 when some tile configuration of the tcgen05 kernel can fuse the GroupNorm of a [B, Hout, Wout, Cout] output whose largest
  * statistics group has max_gsize channels (pure geometry: no pointers, no device), else 0 (use dmc_plan_add_gn_apply) */
 DMC_API int dmc_conv_gn_supported(int32_t B, int32_t Hout, int32_t Wout, int32_t Cout, int32_t max_gsize);

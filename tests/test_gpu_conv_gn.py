@@ -205,3 +205,58 @@ def test_gn_support_query_and_bad_requests():
     v[0]["coff"] = 8  # slice offset not a multiple of the group size
     with pytest.raises(_lib.DmcError):
         run_conv_gn(x, w, 9, versions=v)
+
+
+@pytest.mark.parametrize("pairs", ["1", "2"])
+@pytest.mark.parametrize("C,H,B", [(256, 16, 3), (256, 16, 40), (256, 8, 5), (256, 4, 9), (128, 16, 2), (256, 32, 2)])
+def test_groupnorm_applied_to_the_qkv_operand_is_bit_identical_to_the_stand_alone_pass(C, H, B, pairs, monkeypatch):
+    """AttentionBlock norm -> qkv (models/unet.py:80-81,86-87): dmc_plan_add_gn_coeff + dmc_conv_desc.a_affine (two idle warps of
+    the GEMM kernel rewrite the landed A tiles as bf16(x * scale + shift)) against gn_apply + the plain GEMM: the same bits"""
+    monkeypatch.setenv("DMC_CONV_CG", pairs)
+    lib = _lib.load()
+    if not lib.dmc_conv_affine_supported(B, H, H, C, 3 * C):
+        pytest.skip("this geometry does not run with resident weights")
+    x = nhwc_bf16(_rand((B, C, H, H), 1))
+    gamma, beta = 1.0 + _rand((C,), 2, 0.2), _rand((C,), 3, 0.1)
+    w = (_rand((3 * C, C), 4, C ** -0.5)).to(torch.bfloat16).contiguous()
+    bias = _rand((3 * C,), 5, 0.1)
+    slots = (H * H + 127) // 128
+    st = torch.full((B, slots, C // 8, 2), float("nan"), device="cuda")
+    an = torch.full((B, H, H, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    coeff = torch.full((B, C, 2), float("nan"), device="cuda")
+    outs = [torch.full((B, H, H, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    gs = _lib.GnStatsDesc()
+    gs.src, gs.B, gs.HW, gs.C, gs.stats = x.data_ptr(), B, H * H, C, st.data_ptr()
+    ga = _lib.GnApplyDesc()
+    ga.nsrc = 1
+    ga.src[0], ga.src_c[0], ga.stats[0], ga.stats_slots[0] = x.data_ptr(), C, st.data_ptr(), slots
+    ga.B, ga.HW, ga.groups, ga.gamma, ga.beta, ga.eps, ga.silu, ga.out = B, H * H, 8, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0, an.data_ptr()
+    gc = _lib.GnCoeffDesc()
+    gc.stats, gc.stats_slots, gc.B, gc.HW, gc.C, gc.groups = st.data_ptr(), slots, B, H * H, C, 8
+    gc.gamma, gc.beta, gc.eps, gc.out = gamma.data_ptr(), beta.data_ptr(), 1e-5, coeff.data_ptr()
+
+    def conv(src, out, aff):
+        d = _lib.ConvDesc()
+        d.nsrc = 1
+        d.src[0], d.src_c[0], d.src_taps[0] = src.data_ptr(), C, 1
+        d.B, d.Hin, d.Win, d.stride, d.up_phase = B, H, H, 1, -1
+        d.weight, d.Cout, d.Cout_pad, d.Ktot = w.data_ptr(), 3 * C, 3 * C, C
+        d.bias, d.out_bf16 = bias.data_ptr(), out.data_ptr()
+        if aff is not None:
+            d.a_affine = aff.data_ptr()
+        return d
+
+    p = Plan()
+    p.add("gn_stats", gs)
+    p.add("gn_apply", ga)
+    p.add("conv", conv(an, outs[0], None))
+    p.add("gn_coeff", gc)
+    p.add("conv", conv(x, outs[1], coeff))
+    p.run()
+    p.run()  # the ring / barrier phases survive a second launch
+    assert torch.isfinite(outs[0].float()).all() and torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[0], outs[1])
+    # and against plain PyTorch
+    xf = nchw_f32(x)
+    ref = F.conv2d(F.group_norm(xf, 8, gamma, beta, eps=1e-5).to(torch.bfloat16).float(), w.float()[:, :, None, None], bias)
+    assert rel_l2(nchw_f32(outs[1]), ref) < 5e-3
