@@ -466,8 +466,10 @@ class UNet(nn.Module):
     # first layer cost parity (whole-model eps error at batch 16: 6.8e-3 against 6.2e-3) -- the exact fp32 stem stays the default
     stem_gemm = os.environ.get("DMC_STEM_GEMM", "0") != "0"
     # AttentionBlock: GroupNorm (no activation) of the block input applied to the A operand of the qkv 1x1 GEMM by two otherwise
-    # idle warps of that kernel (bit-identical to the stand-alone pass, which disappears); 0: gn_apply + plain GEMM
-    fuse_norm_qkv = os.environ.get("DMC_FUSE_NORM_QKV", "1") != "0"
+    # idle warps of that kernel (bit-identical to the stand-alone pass, which disappears).  OPT-IN: measured (run 13, 2048 images)
+    # the two transform warps are ~4x too slow for the operand stream -- qkv 0.26 -> 1.10 ms per 16x16 layer against the 0.09 ms
+    # pass it removes; a transform needs a warpgroup or more, which the kernel's register budget (384 threads x 168) does not have
+    fuse_norm_qkv = os.environ.get("DMC_FUSE_NORM_QKV", "0") != "0"
     # GroupNorm(+SiLU) applied by the epilogue of the convolution that produces the tensor (see _PlanBuilder._fuse_groupnorm);
     # DMC_FUSE_GN=0 keeps the stand-alone gn_apply passes everywhere (A/B measurements, tests)
     fuse_groupnorm = os.environ.get("DMC_FUSE_GN", "1") != "0"
