@@ -606,7 +606,7 @@ def run_train_workload(args, rank, local_rank, world):
             "config": {"workload": "UNet cond (10+1 null) CIFAR-10 32x32 training step: CFG label dropout 0.2, t~U[0,1000), q_sample, "
                                    "eps-MSE, backward, clip_grad_norm 1.0, fused AdamW, EMA on rank 0 (BASELINE.json configs[4]); "
                                    "side measurement, not the headline metric",
-                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": (f"native per-entry all-reduce x{world} (NCCL, overlapped, no DDP wrapper)" if (world > 1 and os.environ.get("DMC_NATIVE_ALLREDUCE", "0") == "1") else f"DDP x{world} (NCCL all-reduce overlapped)"),
+                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": (f"native per-entry all-reduce x{world} (NCCL, overlapped, no DDP wrapper)" if (world > 1 and os.environ.get("DMC_NATIVE_ALLREDUCE", "0") == "1") else (f"DDP(model) x{world}: the wrapper is handed all parameters but one to ignore, the engine's per-entry NCCL all-reduce averages them (overlapped)" if (world > 1 and getattr(net, "_ddp_sentinel", None)) else f"DDP x{world} (NCCL all-reduce overlapped)")),
                        "l2": "activations + gradients of one step are > 10x the 126 MB L2", "dropout": 0.1},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (3 * 32 * 32 * 4 + 8)), "d2h_bytes_per_step": 4},

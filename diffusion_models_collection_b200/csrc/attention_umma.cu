@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 #include <new>
 
 namespace dmc {
@@ -39,12 +41,14 @@ struct AttnParams {
   int total_rows;      // B * L
   float scale_log2e;
   __nv_bfloat16* out;
+  int debug;           // DMC_ATTN_DEBUG timing switches of the ping-pong kernel (results are WRONG when set; profiling only)
 };
 
 struct AttnPrepared {
   CUtensorMap tmQ, tmKV;
   AttnParams p;
   int grid;
+  int pp;   // L == 256: the ping-pong kernel (DMC_ATTN_PP=0 keeps the one-warpgroup-per-tile kernel, for A/B runs)
 };
 
 // MN-major SWIZZLE_128B descriptor (operand rows = K index, 128-byte rows of 64 MN elements): 8-row groups 1024 B apart
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;                      // 2 x 16 KB
   uint8_t* sK = sQ + 2 * AT_Q_BYTES;       // 32 KB
   uint8_t* sV = sK + AT_KV_BYTES;          // 32 KB
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * AT_Q_BYTES;
   uint8_t* sV = sK + AT_KV_BYTES;
@@ -591,6 +595,314 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// L = 256 (the UNet's 16 x 16 blocks, every DiT-32 layer): the "ping-pong" form.  Measured on the kernel above (run 13,
+// 2048 images): 9 400 clocks per (image, head) item against 4 096 clocks of exponentials at 16 lanes / clk / SM -- one
+// warpgroup per q-tile leaves ONE warp per scheduler on each tile's serial chain (S -> max -> exp -> P -> PV -> O -> next S)
+// and the O read-out sits on that chain because O aliases S in tensor memory.  Here
+//   * all EIGHT softmax warps work on ONE q-tile at a time (thread = one query row x 128 of its 256 keys; the two threads of
+//     a row exchange their maxima through shared memory around one 256-thread named barrier), so a tile's softmax takes half
+//     as long and the two tiles of an item alternate: while the warps run tile B's exponentials the tensor core does tile A's
+//     P V, then A's next S = Q K^T;
+//   * FOUR further warps own the output: they read O, scale by 1 / rowsum, store, and hand the accumulator back
+//     (s_empty) -- none of that is on the softmax warps' path any more;
+//   * the partial row sums travel in TENSOR MEMORY (one dead S column per half, tcgen05.st), not shared memory: the 224 KB of
+//     Q / K / V / P leave no room for them.
+// 448 threads: warps 0-7 softmax, 8-11 output, 12 TMA producer, 13 MMA issuer (+ TMEM allocation).
+// ------------------------------------------------------------------------------------------------
+constexpr int PP_THREADS = 448;
+constexpr int PP_DATA_BYTES = 2 * AT_Q_BYTES + 2 * AT_KV_BYTES + 2 * AT_P_BYTES;   // 224 KB
+constexpr int PP_MX_BYTES = 2 * 2 * AT_M * 4;                                     // [slot][half][row] row maxima
+constexpr int PP_NEED = PP_DATA_BYTES + PP_MX_BYTES + 256;                        // + barriers
+constexpr size_t PP_SMEM = 232448;                                                // the whole opt-in window (227 KB)
+
+__device__ __forceinline__ void tmem_st_1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  if (threadIdx.x == 0 && (smem - smem_raw) + PP_NEED > static_cast<long long>(PP_SMEM)) {
+    printf("dmc: attention_pp_kernel: dynamic shared memory base is not 1024-byte aligned enough (%d bytes lost)\n",
+           static_cast<int>(smem - smem_raw));
+    __trap();
+  }
+  uint8_t* sQ = smem;                      // 2 x 16 KB (tile A = rows 0..127, tile B = rows 128..255 of the image)
+  uint8_t* sK = sQ + 2 * AT_Q_BYTES;       // 32 KB
+  uint8_t* sV = sK + AT_KV_BYTES;          // 32 KB
+  uint8_t* sP = sV + AT_KV_BYTES;          // 2 x 64 KB
+  float* s_mx = reinterpret_cast<float*>(sP + 2 * AT_P_BYTES);   // [2 slots][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_mx) + PP_MX_BYTES);
+  uint64_t* k_full = bars + 0;
+  uint64_t* k_empty = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_empty = bars + 3;
+  uint64_t* q_full = bars + 4;    // [2]
+  uint64_t* q_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;    // [2]
+  uint64_t* s_empty = bars + 10;  // [2]  128 arrivals: the output warps have read O and the row sums
+  uint64_t* p_full = bars + 12;   // [2]  256 arrivals: P is in shared memory, the row sums are in tensor memory
+  uint64_t* o_full = bars + 14;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 256);
+      mbar_init(&o_full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int L = AT_MAXKEYS;   // 256 keys = 2 q-tiles per (image, head)
+
+  if (warp == 12) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        const int h = item % p.heads;
+        const int row0 = (item / p.heads) * L;
+        mbar_wait(k_empty, ph ^ 1u);
+        mbar_expect_tx(k_full, AT_KV_BYTES);
+        tma_load_2d(sK, &tmKV, k_full, p.C + h * AT_HD, row0);
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&q_empty[s], ph ^ 1u);
+          mbar_expect_tx(&q_full[s], AT_Q_BYTES);
+          tma_load_2d(sQ + s * AT_Q_BYTES, &tmQ, &q_full[s], h * AT_HD, row0 + s * AT_M);
+        }
+        mbar_wait(v_empty, ph ^ 1u);
+        mbar_expect_tx(v_full, AT_KV_BYTES);
+        tma_load_2d(sV, &tmKV, v_full, 2 * p.C + h * AT_HD, row0);
+      }
+    }
+  } else if (warp == 13) {
+    // ===================== MMA issuer =====================
+    // order:  S_A(0) S_B(0);  per item i:  PV_A(i)  S_A(i+1)  PV_B(i)  S_B(i+1)
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_M, L);
+      const uint32_t idesc_o = umma_idesc_bf16(AT_M, AT_HD, /*b_mn_major=*/1);
+      const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK));
+      auto issue_s = [&](int s) {
+        const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + s * AT_Q_BYTES));
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k)
+          umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&q_empty[s]);
+        umma_commit(&s_full[s]);
+      };
+      uint32_t it = 0;
+      int item = blockIdx.x;
+      if (item < p.items) {
+        mbar_wait(k_full, 0u);
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&q_full[s], 0u);
+          tc_fence_after();
+          issue_s(s);
+        }
+        umma_commit(k_empty);
+      }
+      for (; item < p.items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        const bool next = item + static_cast<int>(gridDim.x) < p.items;
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&p_full[s], ph);
+          if (s == 0) mbar_wait(v_full, ph);
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(sP + s * AT_P_BYTES);
+          const uint32_t vbase = smem_u32(sV);
+#pragma unroll 4
+          for (int j = 0; j < L / 16; ++j) {
+            const uint64_t pdesc = umma_desc_k_sw128(pbase + (j >> 2) * (AT_M * 128)) + 2 * (j & 3);
+            const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
+            umma_bf16(tmem_base + s * 256, pdesc, vdesc, idesc_o, j != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[s]);
+          if (s == 1) umma_commit(v_empty);
+          if (next) {
+            if (s == 0) mbar_wait(k_full, ph ^ 1u);
+            mbar_wait(&q_full[s], ph ^ 1u);
+            mbar_wait(&s_empty[s], ph);   // the output warps have read O(i) and the row sums of this slot
+            tc_fence_after();
+            issue_s(s);
+            if (s == 1) umma_commit(k_empty);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== softmax: 8 warps on one q-tile; thread = (query row, half of the keys) =====================
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int dbg = p.debug;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint32_t la = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256 + half * 128;
+        uint8_t* sPs = sP + slot * AT_P_BYTES + (half * 2) * (AT_M * 128) + row * 128;
+        float* mx = s_mx + slot * 2 * AT_M;
+        mbar_wait(&s_full[slot], ph);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        float m = -INFINITY;
+        // pass 1: maximum of this thread's 128 scores (one TMEM load kept in flight)
+        if (!(dbg & 1)) {
+        tmem_ld_32x32(la, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 32, rb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 64, ra);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 96, rb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la, ra);  // chunk 0 again, for pass 2
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        } else {
+          m = 30.f;
+          tmem_ld_32x32(la, ra);
+        }
+        if (!(dbg & 16)) {
+        mx[half * AT_M + row] = m;
+        named_bar_sync(1, 256);
+        m = fmaxf(m, mx[(half ^ 1) * AT_M + row]);
+        }
+        const float ms = m * p.scale_log2e;
+        float sum = 0.f;
+        // pass 2: p = 2^(s * scale - max * scale), partial row sum, bf16 P into the K-major SWIZZLE_128B operand layout
+        auto emit = [&](const uint32_t (&r)[32], int c0) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float e0 = fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms);
+            float e1 = fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms);
+            if (!(dbg & 4)) {
+              e0 = ex2_approx(e0);
+              e1 = ex2_approx(e1);
+            }
+            if (!(dbg & 64)) sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          uint8_t* sub = sPs + (c0 >> 6) * (AT_M * 128);
+          const int chunk0 = (c0 & 63) >> 3;
+          if (dbg & 2) {
+            if (pk[0] == 0x12345678u && pk[7] == pk[15]) *reinterpret_cast<uint4*>(sub) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          } else
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (chunk0 + q4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        };
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 32, rb);
+        emit(ra, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 64, ra);
+        emit(rb, 32);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 96, rb);
+        emit(ra, 64);
+        tmem_ld_wait();
+        emit(rb, 96);
+        // the partial row sum goes to a dead S column of this thread's own half (64 / 192: outside O's columns 0..63)
+        if (!(dbg & 8)) {
+          tmem_st_1(la + 64, __float_as_uint(sum));
+          tmem_st_wait();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[slot]);
+      }
+    }
+  } else {
+    // ===================== output warps: O * (1 / rowsum) -> bf16 -> global; hand the accumulator back =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int h = item % p.heads;
+      const int row0 = (item / p.heads) * L;
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint32_t la = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256;
+        mbar_wait(&o_full[slot], ph);
+        tc_fence_after();
+        uint32_t ro[2][32];
+        tmem_ld_32x32(la, ro[0]);
+        tmem_ld_32x32(la + 32, ro[1]);
+        const uint32_t s0 = tmem_ld_1(la + 64);
+        const uint32_t s1 = tmem_ld_1(la + 192);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[slot]);
+        const float inv = 1.0f / (__uint_as_float(s0) + __uint_as_float(s1));
+        const int grow = row0 + slot * AT_M + row;
+        __nv_bfloat16* op = p.out + static_cast<size_t>(grow) * p.C + h * AT_HD;
+        if (p.debug & 32) continue;
+#pragma unroll
+        for (int c0 = 0; c0 < AT_HD; c0 += 32) {
+          const uint32_t (&r)[32] = ro[c0 >> 5];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * q4]) * inv, __uint_as_float(r[8 * q4 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv, __uint_as_float(r[8 * q4 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv, __uint_as_float(r[8 * q4 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv, __uint_as_float(r[8 * q4 + 7]) * inv);
+            reinterpret_cast<uint4*>(op + c0)[q4] = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   DMC_REQUIRE(fn != nullptr, "attention: cuTensorMapEncodeTiled unavailable -- call dmc_init()");
@@ -631,6 +943,11 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
     delete P;
     return -1;
   }
+  const char* e = getenv("DMC_ATTN_PP");
+  P->pp = (d.L == AT_MAXKEYS && !(e && e[0] == '0')) ? 1 : 0;
+  if (P->pp) p.items = p.tiles / 2;   // one item = one (image, head): both q-tiles, shared K / V
+  const char* dbg = getenv("DMC_ATTN_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
   P->grid = std::min(p.items, num_sms());
   *out = P;
   return 0;
@@ -648,7 +965,14 @@ int launch_attention_umma(const AttnPrepared* P, cudaStream_t st) {
                                      static_cast<int>(AT_SMEM)));
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(AT_SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(PP_SMEM)));
     attr_set.done(attr_set_dev);
+  }
+  if (P->pp) {
+    attention_pp_kernel<<<P->grid, PP_THREADS, PP_SMEM, st>>>(P->tmQ, P->tmKV, P->p);
+    DMC_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   if (P->p.L > AT_MAXKEYS) {
     attention_long_kernel<<<P->grid, AT_THREADS, AT_SMEM, st>>>(P->tmQ, P->tmKV, P->p);

@@ -100,6 +100,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// First 1024-byte aligned address inside the dynamic shared-memory window, as POINTER ARITHMETIC on the shared array: a round trip
+// through uintptr_t makes the compiler lose the address space, and every access through a pointer derived from it becomes a
+// GENERIC load / store (LD.E / ST.E with 64-bit address arithmetic and window resolution) instead of LDS / STS -- found in the
+// SASS of the attention softmax and of the convolution epilogue's staging buffers (round 2, run 14).
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

@@ -58,6 +58,7 @@ struct ConvKParams {
   int qbw, qbh;               // quarter box: qbw pixels x qbh rows x 32/(qbw*qbh) images
   int store_bufs;             // staging buffers per epilogue warp (1 or 2)
   int res_tma;                // the residual (bf16 or fp32 stream) is fetched as TMA boxes into the staging buffer
+  int epi_fast;               // bf16 TMA-store epilogue with bias only (+ GELU, + TMA residual): the straight-line box loop
   // shared-memory plan (host computed): [resident weights][ring: nst stages][store staging][barriers]
   int nst, stage_bytes, a_bytes, b_region_bytes;
   int bres;                   // weights of the whole K extent stay resident (short-K GEMMs: 1x1 convs, transformer linears)
@@ -202,7 +203,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   // [resident weights (bres)] [ring: nst x stage_bytes] [TMA-store staging] [barriers]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* ring = smem + p.b_region_bytes;
   uint8_t* store_stage = ring + NST * p.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + (TS ? Cfg::STORE_BYTES * p.store_bufs : 0));
@@ -874,6 +875,105 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       } else
       if (!idle) {
+        bool fast_done = false;
+        if constexpr (TS && (EPI == 0 || EPI == 1) && (COLS % 64) == 0) {
+          // ---- straight-line box loop (short-K GEMMs: qkv / proj 1x1 convolutions, transformer qkv / fc1) ----
+          // The generic chunk loop below executes ~210 instructions per 32 columns (run 14: 21 ISETP, 17 BRA, 13 BSSY / BSYNC,
+          // 16 CS2R ... around 32 FADD + 16 F2FP + 8 LDG + 4 STS of real work) and the 8 epilogue warps -- two per scheduler, in
+          // order -- are latency-bound on it (36 % of their samples on fixed-latency dependencies, 9 % resolving branches, 8 %
+          // waiting for instruction fetch): 5 600 clocks per 128 x 256 tile against 2 048 clocks of MMAs in the qkv GEMM.
+          // When the epilogue is bias only (+ GELU, + a residual fetched by TMA) this loop handles one 64-channel box per
+          // iteration with both tcgen05.ld in flight and no per-chunk decisions; rows past the batch are computed on zeros
+          // and clipped by the TMA store.
+          if (p.epi_fast && n_tile * BN + col0 + COLS <= p.Cout) {
+            fast_done = true;
+            const bool res_tma = EPI == 0 && p.res_tma != 0;
+            const uint32_t xr = static_cast<uint32_t>(lane & 7) << 4;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS; c0 += 64) {
+              const int cg = n_tile * BN + col0 + c0;
+              const uint32_t bi = (p.store_bufs == 2) ? (boxi & 1u) : 0u;
+              uint8_t* stg = my_stage + bi * 4096u;
+              uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
+              if (lane == 0) {
+                if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (res_tma) {
+                  mbar_expect_tx(rb, 4096);
+                  tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+                }
+              }
+              __syncwarp();
+              uint32_t r0[32], r1[32];
+              tmem_ld_32x32(taddr + c0, r0);
+              tmem_ld_32x32(taddr + c0 + 32, r1);
+              float v[64];
+              tmem_ld_wait();
+              if (p.bias != nullptr) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(b4 + j);
+                  v[4 * j] = __uint_as_float(r0[4 * j]) + b.x;
+                  v[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + b.y;
+                  v[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + b.z;
+                  v[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + b.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(b4 + 8 + j);
+                  v[32 + 4 * j] = __uint_as_float(r1[4 * j]) + b.x;
+                  v[32 + 4 * j + 1] = __uint_as_float(r1[4 * j + 1]) + b.y;
+                  v[32 + 4 * j + 2] = __uint_as_float(r1[4 * j + 2]) + b.z;
+                  v[32 + 4 * j + 3] = __uint_as_float(r1[4 * j + 3]) + b.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  v[j] = __uint_as_float(r0[j]);
+                  v[32 + j] = __uint_as_float(r1[j]);
+                }
+              }
+              if (EPI == 1 && p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = gelu_fast(v[j]);
+              }
+              uint8_t* rowp = stg + lane * 128;
+              if (res_tma) {
+                mbar_wait(rb, (rphase >> bi) & 1u);
+                rphase ^= 1u << bi;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(j) << 4) ^ xr));
+                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack_bf16x2(w[k]);
+                    v[8 * j + 2 * k] += f.x;
+                    v[8 * j + 2 * k + 1] += f.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>(j) << 4) ^ xr)) = u;
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, stg, cg, sw0, sh0, sn0);  // clipped at the tensor bounds (n >= B)
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++boxi;
+            }
+          }
+        }
+        if (!fast_done)
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS; c0 += 32) {
           const int cg = n_tile * BN + col0 + c0;  // first global output channel of this chunk

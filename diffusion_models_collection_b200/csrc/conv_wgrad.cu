@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* done_bar = empty_bar + 8;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        const __grid_constant__ WgradSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* done_bar = empty_bar + 8;

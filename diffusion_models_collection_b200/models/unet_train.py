@@ -503,11 +503,15 @@ class UNetTrainEngine:
                     cg[i] = cflat[off: off + n].view(cg[i].shape)
                     off += n
             grads += cg
+            # under a DistributedDataParallel wrapper (UNet._ddp_params_and_buffers_to_ignore) one sentinel parameter stays with
+            # DDP: its averaged gradient is returned through autograd below instead of being assigned here
+            sentinel = getattr(self.net, "_ddp_sentinel", None)
+            sent_p = self.net.get_parameter(sentinel) if sentinel else None
             fresh_p, acc_p, acc_g = [], [], []
             for work, ps, gs, mk in self._pending:
                 work.wait()  # the current stream waits for the collective; the host does not
                 for p_, g_, m_ in zip(ps, gs, mk):
-                    if not m_ or g_ is None:
+                    if not m_ or g_ is None or p_ is sent_p:
                         continue
                     if p_.grad is None:
                         p_.grad = g_
@@ -517,6 +521,12 @@ class UNetTrainEngine:
             if acc_p:
                 torch._foreach_add_(acc_p, acc_g)
             self._pending = []
+            if sent_p is not None:
+                out = [None] * len(mask)
+                for i, p_ in enumerate(params):
+                    if p_ is sent_p and mask[i]:
+                        out[i] = grads[i]
+                return out
         return [None] * len(mask)
 
     @staticmethod

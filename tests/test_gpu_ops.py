@@ -258,7 +258,8 @@ def test_groupnorm_stats_apply_concat(cs, H, B, silu):
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("L,heads,hd,B", [(256, 4, 64, 2), (64, 4, 64, 3), (16, 4, 64, 5), (256, 6, 64, 2), (1024, 6, 64, 1),
                                           (256, 2, 64, 1), (16, 4, 64, 3), (64, 4, 64, 1), (128, 2, 64, 3), (32, 1, 64, 7),
-                                          (256, 4, 64, 37), (512, 2, 64, 3), (1024, 6, 64, 2), (2048, 1, 64, 1)])
+                                          (256, 4, 64, 37), (512, 2, 64, 3), (1024, 6, 64, 2), (2048, 1, 64, 1),
+                                          (256, 4, 64, 80), (256, 6, 64, 75), (256, 1, 64, 300)])
 def test_attention(L, heads, hd, B, impl):
     from diffusion_models_collection_b200 import _lib
 

@@ -172,6 +172,66 @@ def test_native_gradient_allreduce_world_2_gloo():
         assert torch.equal(out[0][1], out[1][1])  # parameters were broadcast from rank 0
 
 
+def _ddp_wrap_worker(rank, world, port, out):
+    """the reference trainer's own line, `DDP(model)` (utils/trainer.py:58-61), around the native UNet: DDP is handed every parameter
+    but the sentinel to ignore, the engine averages the rest itself, the sentinel's gradient goes through DDP's reducer"""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rec = _Recorder()
+        _lib.load, _lib.stream_ptr, _lib.check = (lambda: rec), (lambda: 0), (lambda rc, what="": rc)
+        torch.cuda.device = lambda d: contextlib.nullcontext()
+        from torch.nn.parallel import DistributedDataParallel as DDP
+
+        from diffusion_models_collection_b200.models import unet_train
+
+        unet_train.USE_GRAPHS = False
+        net = _net(None).train()
+        net.dropout = 0.0
+        assert not hasattr(net, "_ddp_params_and_buffers_to_ignore")  # nobody but a DDP constructor sees the attribute
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(float(rank))
+        net._run = lambda x, t, y, cfg: net._run_train(x, t, y)  # (the CUDA-only check of forward(); no device here)
+        model = DDP(net)
+        ok = net._grad_allreduce is model.process_group and net._ddp_sentinel == "input_conv.bias"
+        ok = ok and len(model._module_parameters) == 1 and model._module_parameters[0] is net.get_parameter("input_conv.bias")
+        ok = ok and len(model.parameters_to_ignore) == len(list(net.parameters())) - 1 and model.module is net
+        first = next(net.parameters()).detach().clone()
+        x, t = torch.randn(2, 3, 32, 32), torch.randint(0, 1000, (2,))
+        kernel_params = None
+        for it in range(2):  # two steps: DDP's reducer must be satisfied after the first (else the second forward raises)
+            eps = model(x, t, None)
+            eng = next(iter(net._train_engines.values()))
+            for s in eng.segs:
+                eng.flat[s].fill_(float(rank + 1))
+            for _, dc in eng.dcond_parts:
+                dc.zero_()
+            eps.sum().backward()
+            kernel_params = [net.get_parameter(n) for n in eng.gview
+                             if not (n.startswith("output.2") or n == "input_conv.weight" or n.endswith(".shortcut.weight"))]
+            ok = ok and all(torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2)) for p in kernel_params)
+            ok = ok and all(p.grad is not None for p in net.parameters())
+            ok = ok and any(p is net.get_parameter("input_conv.bias") for p in kernel_params)
+            for p in net.parameters():
+                p.grad = None
+        os.environ["DMC_DDP_NATIVE"] = "0"  # stock DDP over every parameter
+        plain = _net(None)
+        ok = ok and len(DDP(plain)._module_parameters) == len(list(plain.parameters())) and plain._grad_allreduce is None
+        out[rank] = (bool(ok), first)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_wrapper_hands_the_gradients_to_the_native_allreduce_world_2_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_ddp_wrap_worker, args=(world, 29657, out), nprocs=world, join=True)
+        assert all(out[r][0] for r in range(world))
+        assert torch.equal(out[0][1], out[1][1])  # rank 0's parameters everywhere, like DDP's own broadcast
+
+
 def test_models_deepcopy_and_pickle_without_their_native_caches():
     """EMA helpers deep-copy the model (torch.optim.swa_utils.AveragedModel does) and torch.save(model) pickles it: plans, engines
     and packed operands hold native handles / device pointers and must not travel; the copy rebuilds them on its first forward"""

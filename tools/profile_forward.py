@@ -29,33 +29,39 @@ def main():
     args = ap.parse_args()
 
     from diffusion_models_collection_b200 import _lib, synth
-    from diffusion_models_collection_b200.models import UNet
+    from diffusion_models_collection_b200.models import DiT, UNet
 
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    net = UNet(**synth.CIFAR_UNET, num_classes=10)
-    net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
+    dit = args.model == "dit"
+    if dit:  # BASELINE configs[3]: unconditional DiT-32, one forward of `batch` images
+        net = DiT(**synth.CIFAR_DIT, num_classes=None)
+        net.load_state_dict(synth.make_dit_state_dict(synth.CIFAR_DIT, None, seed=42))
+    else:
+        net = UNet(**synth.CIFAR_UNET, num_classes=10)
+        net.load_state_dict(synth.make_unet_state_dict(None, 10, seed=42))
     net = net.to(dev).eval()
     B = args.batch
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, 3, 32, 32, generator=g).to(dev)
     y = (torch.randint(0, 10, (B,), generator=g) + 1).to(dev)
     t = torch.full((B,), 500, device=dev)
+    fwd = (lambda: net(x, t, None)) if dit else (lambda: net.forward_cfg(x, t, y))
     with torch.no_grad(), net.uniform_timesteps():
         for _ in range(3):
-            net.forward_cfg(x, t, y)
-        plan = net.plan_info(B, cfg=True, device=dev)
+            fwd()
+        plan = net.plan_info(B, cfg=not dit, device=dev)
         lib = _lib.load()
         n = lib.dmc_plan_num_ops(plan.handle)
         table = [dict(index=i, name=plan.op_names[i], kind=_lib.OP_KINDS[lib.dmc_plan_op_kind(plan.handle, i)],
                       flops=lib.dmc_plan_op_flops(plan.handle, i), bytes=lib.dmc_plan_op_bytes(plan.handle, i))
                  for i in range(n)]
         if args.table_out:
-            json.dump(dict(images=2 * B, ops=table), open(args.table_out, "w"), indent=1)
+            json.dump(dict(images=B if dit else 2 * B, ops=table), open(args.table_out, "w"), indent=1)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         if args.mode == "forward":
-            net.forward_cfg(x, t, y)
+            fwd()
         else:
             want = [s for s in args.ops.split(",") if s]
             for name in want:
