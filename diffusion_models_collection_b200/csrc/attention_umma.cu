@@ -45,10 +45,11 @@ struct AttnParams {
 };
 
 struct AttnPrepared {
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
   AttnParams p;
   int grid;
-  int pp;   // L == 256: the ping-pong kernel (DMC_ATTN_PP=0 keeps the one-warpgroup-per-tile kernel, for A/B runs)
+  int pp;   // L == 256: 2 = P in tensor memory (attention_ts_kernel), 1 = ping-pong kernel with P in shared memory (DMC_ATTN_PP=1),
+            // 0 = the one-warpgroup-per-tile kernel (DMC_ATTN_PP=0); the older forms stay for A/B runs
 };
 
 // MN-major SWIZZLE_128B descriptor (operand rows = K index, 128-byte rows of 64 MN elements): 8-row groups 1024 B apart
@@ -903,6 +904,318 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// L = 256, third form: P NEVER LEAVES TENSOR MEMORY.  What the timing switches of the ping-pong kernel showed (run 16, 2048 images,
+// tools/bench_attention.py): 9 600 clocks per (image, head) item; without the exponentials 9 500; with the softmax warps doing
+// nothing at all 7 700 -- the kernel is not bound by the SFU or the tensor pipe but by its LOADS: 128 FLOP per HBM byte is half the
+// chip's ridge (254), K and V were single-buffered (each load could only be issued ~4 000 clocks before its first use, about the
+// HBM latency under load), and 128 of the 227 KB of shared memory held the two P tiles.  Here
+//   * the softmax warps write P (bf16 pairs) back into the S columns they have just read (tcgen05.st) and O = P V is a
+//     tcgen05.mma with the A operand IN TENSOR MEMORY -- no P in shared memory, no generic-proxy fence, 4 KB less shared-memory
+//     traffic per MMA;
+//   * the 128 KB that frees double-buffer Q, K and V: the producer runs a whole item ahead;
+//   * the output warps stage their 32 x 64 block in shared memory and store it with TMA (full 128-byte rows) instead of 8
+//     row-strided 16-byte stores per thread.
+// TMEM columns of slot s (256 s + ...): S [0, 256) -> P keys 0..127 in [0, 64), O in [64, 128), P keys 128..255 in [128, 192).
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_SMEM_Q = 2 * 2 * AT_Q_BYTES;          // [stage][slot]
+constexpr int TS_SMEM_KV = 2 * AT_KV_BYTES;            // [stage], K and V each
+constexpr int TS_SMEM_O = 4 * 4096;                    // one 32-row x 64-channel staging block per output warp
+constexpr int TS_SMEM_F = 2 * 2 * 2 * AT_M * 4;        // row maxima + partial row sums: [slot][half][row] each
+constexpr int TS_NEED = TS_SMEM_Q + 2 * TS_SMEM_KV + TS_SMEM_O + TS_SMEM_F + 256;
+constexpr size_t TS_SMEM = TS_NEED + 1024;
+
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (128 rows = lanes, 16 bf16 = 8 columns per K step) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attention_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sQ = smem;                          // [stage][slot] 16 KB
+  uint8_t* sK = sQ + TS_SMEM_Q;                // [stage] 32 KB
+  uint8_t* sV = sK + TS_SMEM_KV;               // [stage] 32 KB
+  uint8_t* sO = sV + TS_SMEM_KV;               // [output warp] 4 KB
+  float* s_mx = reinterpret_cast<float*>(sO + TS_SMEM_O);   // [slot][half][row]
+  float* s_sum = s_mx + 2 * 2 * AT_M;                       // [slot][half][row]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 2 * 2 * AT_M);
+  uint64_t* k_full = bars + 0;    // [2 stages]
+  uint64_t* k_empty = bars + 2;   // [2]
+  uint64_t* v_full = bars + 4;    // [2]
+  uint64_t* v_empty = bars + 6;   // [2]
+  uint64_t* q_full = bars + 8;    // [stage][slot]
+  uint64_t* q_empty = bars + 12;  // [stage][slot]
+  uint64_t* s_full = bars + 16;   // [slot]
+  uint64_t* s_empty = bars + 18;  // [slot] 128 arrivals: the output warps have read O
+  uint64_t* p_full = bars + 20;   // [slot] 256 arrivals: P is in tensor memory, the partial row sums in shared memory
+  uint64_t* o_full = bars + 22;   // [slot]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int L = AT_MAXKEYS;
+
+  if (warp == 12) {
+    // ===================== TMA producer: a whole item ahead of the MMAs =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int st = it & 1u;
+        const uint32_t ph = (it >> 1) & 1u;
+        const int h = item % p.heads;
+        const int row0 = (item / p.heads) * L;
+        mbar_wait(&k_empty[st], ph ^ 1u);
+        mbar_expect_tx(&k_full[st], AT_KV_BYTES);
+        tma_load_2d(sK + st * AT_KV_BYTES, &tmKV, &k_full[st], p.C + h * AT_HD, row0);
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&q_empty[st * 2 + s], ph ^ 1u);
+          mbar_expect_tx(&q_full[st * 2 + s], AT_Q_BYTES);
+          tma_load_2d(sQ + (st * 2 + s) * AT_Q_BYTES, &tmQ, &q_full[st * 2 + s], h * AT_HD, row0 + s * AT_M);
+        }
+        mbar_wait(&v_empty[st], ph ^ 1u);
+        mbar_expect_tx(&v_full[st], AT_KV_BYTES);
+        tma_load_2d(sV + st * AT_KV_BYTES, &tmKV, &v_full[st], 2 * p.C + h * AT_HD, row0);
+      }
+    }
+  } else if (warp == 13) {
+    // ===================== MMA issuer:  S_A(0) S_B(0);  per item i:  PV_A(i)  S_A(i+1)  PV_B(i)  S_B(i+1) =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_M, L);
+      const uint32_t idesc_o = umma_idesc_bf16(AT_M, AT_HD, /*b_mn_major=*/1);
+      auto issue_s = [&](int s, uint32_t jt) {  // S[s] = Q[s] K^T of the CTA's jt-th item
+        const int st = jt & 1u;
+        const uint32_t ph = (jt >> 1) & 1u;
+        if (s == 0) mbar_wait(&k_full[st], ph);
+        mbar_wait(&q_full[st * 2 + s], ph);
+        tc_fence_after();
+        const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ + (st * 2 + s) * AT_Q_BYTES));
+        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + st * AT_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k)
+          umma_bf16(tmem_base + s * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&q_empty[st * 2 + s]);
+        umma_commit(&s_full[s]);
+        if (s == 1) umma_commit(&k_empty[st]);
+      };
+      uint32_t it = 0;
+      int item = blockIdx.x;
+      if (item < p.items) {
+        issue_s(0, 0u);
+        issue_s(1, 0u);
+      }
+      for (; item < p.items; item += gridDim.x, ++it) {
+        const int st = it & 1u;
+        const uint32_t ph = it & 1u;            // per-slot barriers complete once per item
+        const uint32_t phs = (it >> 1) & 1u;    // per-stage barriers complete once per two items
+        const bool next = item + static_cast<int>(gridDim.x) < p.items;
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&p_full[s], ph);
+          if (s == 0) mbar_wait(&v_full[st], phs);
+          tc_fence_after();
+          const uint32_t vbase = smem_u32(sV + st * AT_KV_BYTES);
+          const uint32_t tslot = tmem_base + s * 256;
+#pragma unroll 4
+          for (int j = 0; j < L / 16; ++j) {
+            const uint64_t vdesc = umma_desc_mn_sw128(vbase + j * 16 * 128);
+            const uint32_t pa = tslot + (j < 8 ? 8 * j : 128 + 8 * (j - 8));
+            umma_bf16_ts(tslot + 64, pa, vdesc, idesc_o, j != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[s]);
+          if (s == 1) umma_commit(&v_empty[st]);
+          if (next) {
+            mbar_wait(&s_empty[s], ph);   // the output warps have read O(i) of this slot
+            issue_s(s, it + 1);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== softmax: 8 warps on one q-tile; thread = (query row, half of the keys) =====================
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int dbg = p.debug;   // DMC_ATTN_DEBUG timing switches (wrong results): 1 no row max, 2 no P stores, 4 no exponentials,
+                               // 16 no maximum exchange, 32 no output stores
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint32_t la = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256 + half * 128;
+        float* mx = s_mx + slot * 2 * AT_M;
+        mbar_wait(&s_full[slot], ph);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        float m = -INFINITY;
+        if (!(dbg & 1)) {
+        tmem_ld_32x32(la, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 32, rb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 64, ra);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 96, rb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(ra[j]));
+        tmem_ld_wait();
+        tmem_ld_32x32(la, ra);  // chunk 0 again, for pass 2
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rb[j]));
+        } else {
+          m = 30.f;
+          tmem_ld_32x32(la, ra);
+        }
+        if (!(dbg & 16)) {
+        mx[half * AT_M + row] = m;
+        named_bar_sync(1, 256);
+        m = fmaxf(m, mx[(half ^ 1) * AT_M + row]);
+        }
+        const float ms = m * p.scale_log2e;
+        float sum = 0.f;
+        // pass 2: p = 2^(s * scale - max * scale) as bf16 pairs, written over the S columns this thread has already consumed
+        auto emit = [&](const uint32_t (&r)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float e0 = fmaf(__uint_as_float(r[j]), p.scale_log2e, -ms);
+            float e1 = fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -ms);
+            if (!(dbg & 4)) {
+              e0 = ex2_approx(e0);
+              e1 = ex2_approx(e1);
+            }
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          if (!(dbg & 2) || pk[3] == 0x12345678u) tmem_st_16(la + 16 * c, pk);
+        };
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 32, rb);
+        emit(ra, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 64, ra);
+        emit(rb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32(la + 96, rb);
+        emit(ra, 2);
+        tmem_ld_wait();
+        emit(rb, 3);
+        s_sum[(slot * 2 + half) * AT_M + row] = sum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[slot]);
+      }
+    }
+  } else {
+    // ===================== output warps: O * (1 / rowsum) -> bf16 -> shared memory -> TMA store =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint8_t* stg = sO + q * 4096;
+    const uint32_t xr = static_cast<uint32_t>(lane & 7) << 4;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int h = item % p.heads;
+      const int row0 = (item / p.heads) * L;
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint32_t la = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 256 + 64;
+        mbar_wait(&p_full[slot], ph);   // (acquires the softmax warps' partial row sums)
+        mbar_wait(&o_full[slot], ph);
+        tc_fence_after();
+        uint32_t r[32];
+        uint32_t pk[32];
+        tmem_ld_32x32(la, r);
+        const float inv = 1.0f / (s_sum[(slot * 2) * AT_M + row] + s_sum[(slot * 2 + 1) * AT_M + row]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+        tmem_ld_32x32(la + 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[slot]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[16 + j] = pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has left the buffer
+        __syncwarp();
+        uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>(c) << 4) ^ xr)) =
+              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 32)) {
+          tma_store_2d(&tmO, stg, h * AT_HD, row0 + slot * AT_M + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   DMC_REQUIRE(fn != nullptr, "attention: cuTensorMapEncodeTiled unavailable -- call dmc_init()");
@@ -944,7 +1257,11 @@ int attention_prepare(const dmc_attn_desc& d, AttnPrepared** out) {
     return -1;
   }
   const char* e = getenv("DMC_ATTN_PP");
-  P->pp = (d.L == AT_MAXKEYS && !(e && e[0] == '0')) ? 1 : 0;
+  P->pp = d.L == AT_MAXKEYS ? ((e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2) : 0;
+  if (P->pp == 2 && encode2d(&P->tmO, d.out, static_cast<uint64_t>(d.C), rows, 32) != 0) {
+    delete P;
+    return -1;
+  }
   if (P->pp) p.items = p.tiles / 2;   // one item = one (image, head): both q-tiles, shared K / V
   const char* dbg = getenv("DMC_ATTN_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
@@ -967,7 +1284,14 @@ int launch_attention_umma(const AttnPrepared* P, cudaStream_t st) {
                                      static_cast<int>(AT_SMEM)));
     DMC_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(PP_SMEM)));
+    DMC_CUDA_OK(cudaFuncSetAttribute(attention_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(TS_SMEM)));
     attr_set.done(attr_set_dev);
+  }
+  if (P->pp == 2) {
+    attention_ts_kernel<<<P->grid, PP_THREADS, TS_SMEM, st>>>(P->tmQ, P->tmKV, P->tmO, P->p);
+    DMC_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   if (P->pp) {
     attention_pp_kernel<<<P->grid, PP_THREADS, PP_SMEM, st>>>(P->tmQ, P->tmKV, P->p);

@@ -437,10 +437,14 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.residual_lo = reinterpret_cast<const __nv_bfloat16*>(d.residual_lo);
   kp.out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
   // the straight-line box loop of the epilogue: bf16 TMA stores, bias only (+ GELU), residual only as TMA boxes, no conditioning
-  // rows, no GroupNorm partial sums, no split-bf16 low parts (DMC_CONV_EPI_FAST=0: the generic chunk loop, for A/B runs)
+  // rows, no split-bf16 low parts (DMC_CONV_EPI_FAST=0: the generic chunk loop, for A/B runs)
   kp.epi_fast = (env_flag("DMC_CONV_EPI_FAST", 1) && kp.tma_store && !gn && (epi == 0 || epi == 1) && d.cond == nullptr &&
-                 d.stats == nullptr && d.out_lo == nullptr && d.residual_lo == nullptr && d.out_bf16 != nullptr &&
+                 d.out_lo == nullptr && d.residual_lo == nullptr && d.out_bf16 != nullptr &&
                  (d.residual == nullptr || kp.res_tma)) ? 1 : 0;
+  // transformer residual GEMMs (out_proj, fc2): out = res + gate * (acc + bias) in fp32, residual and output as TMA boxes
+  if (env_flag("DMC_CONV_EPI_FAST", 1) && kp.tma_store && epi == 3 && kp.res_tma && d.residual_f32 != nullptr &&
+      d.out_f32_nhwc != nullptr && d.out_bf16 == nullptr)
+    kp.epi_fast = 1;
   if (d.stats) {
     const int ppi_img = Hout * Wout;  // iteration pixels per image
     const int base = ppi_img >= 32 ? ppi_img / 32 : 1;

@@ -970,6 +970,101 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
               ++boxi;
+              if (UNET && p.stats != nullptr) {
+                // GroupNorm partial sums of the output, exactly as the generic loop writes them (same slots, same order)
+                const bool full = ppi >= 32;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  float sv[8];
+#pragma unroll
+                  for (int b = 0; b < 4; ++b) {
+                    float s_ = 0.f, ss_ = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      s_ += v[32 * hf + 8 * b + j];
+                      ss_ = fmaf(v[32 * hf + 8 * b + j], v[32 * hf + 8 * b + j], ss_);
+                    }
+                    sv[b] = valid ? s_ : 0.f;
+                    sv[4 + b] = valid ? ss_ : 0.f;
+                  }
+                  float tot;
+                  int idx;
+                  reduce8(sv, full, lane, tot, idx);
+                  const bool writer = full ? ((lane & 3) == 0) : ((lane & 1) == 0);
+                  if (writer && valid) {
+                    const int wpi = ppi >> 5;
+                    const int slot = p.stats_slot_base + (full ? ((th * p.tiles_w + tw) * wpi + (q % wpi)) : 0);
+                    float* dst = p.stats + ((static_cast<size_t>(n) * p.stats_slots + slot) * (p.Cout >> 3) +
+                                            (((cg + 32 * hf) >> 3) + (idx & 3))) * 2;
+                    dst[idx >> 2] = tot;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if constexpr (TS && EPI == 3) {
+          // ---- the same straight-line loop for the transformer residual GEMMs (out_proj, fc2): out = res + gate * (acc + bias),
+          // fp32 boxes of 32 channels, residual fetched and result stored by TMA ----
+          if (p.epi_fast && n_tile * BN + col0 + COLS <= p.Cout) {
+            fast_done = true;
+            const uint32_t xr = static_cast<uint32_t>(lane & 7) << 4;
+            const float* gate_row = p.gate != nullptr ? p.gate + static_cast<size_t>(min(n, p.B - 1)) * p.gate_stride : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS; c0 += 32) {
+              const int cg = n_tile * BN + col0 + c0;
+              const uint32_t bi = (p.store_bufs == 2) ? (boxi & 1u) : 0u;
+              uint8_t* stg = my_stage + bi * 4096u;
+              uint64_t* rb = &rbar[(warp - 4) * 2 + bi];
+              if (lane == 0) {
+                if (p.store_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_expect_tx(rb, 4096);
+                tma_load_4d(stg, &tmRes, rb, cg, sw0, sh0, sn0);
+              }
+              __syncwarp();
+              uint32_t r[32];
+              tmem_ld_32x32(taddr + c0, r);
+              float v[32];
+              tmem_ld_wait();
+              if (p.bias != nullptr) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(b4 + j);
+                  v[4 * j] = __uint_as_float(r[4 * j]) + b.x;
+                  v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+                  v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+                  v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              }
+              if (gate_row != nullptr) {
+                const float4* g4 = reinterpret_cast<const float4*>(gate_row + cg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 gv = __ldg(g4 + j);
+                  v[4 * j] *= gv.x; v[4 * j + 1] *= gv.y; v[4 * j + 2] *= gv.z; v[4 * j + 3] *= gv.w;
+                }
+              }
+              uint8_t* rowp = stg + lane * 128;
+              mbar_wait(rb, (rphase >> bi) & 1u);
+              rphase ^= 1u << bi;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4* cp = reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(j) << 4) ^ xr));
+                const float4 rv = *cp;
+                *cp = make_float4(v[4 * j] + rv.x, v[4 * j + 1] + rv.y, v[4 * j + 2] + rv.z, v[4 * j + 3] + rv.w);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, stg, cg, sw0, sh0, sn0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++boxi;
             }
           }
         }
