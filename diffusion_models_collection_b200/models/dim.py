@@ -26,6 +26,8 @@ from .unet import _register
 
 
 class DiM(DiT):
+    _train_supported = False
+
     def __init__(self, img_size: Tuple[int, int] = (32, 32), patch_size=2, in_channels=3, hidden_size=768, depth=12,
                  state_size=16, mlp_ratio=4.0, num_classes=None, dropout=0.1):
         self.state_size = state_size

@@ -58,7 +58,7 @@ class DiT(nn.Module):
         """copy.deepcopy(model) / torch.save(model): launch plans and packed operands are caches bound to native handles and
         device pointers -- a copy starts without them and rebuilds them on its first forward"""
         st = self.__dict__.copy()
-        st.update(_plans={}, _packed=None, _packed_version=None, _dmc_graph_token=None)
+        st.update(_plans={}, _packed=None, _packed_version=None, _dmc_graph_token=None, _train_engines={})
         return st
 
     def _init_parameters(self):
@@ -166,12 +166,46 @@ class DiT(nn.Module):
     def max_images_per_launch(self):
         return max(2, self.max_tokens_per_launch // (self.h_tokens * self.w_tokens))
 
+    _train_supported = True  # (DiM carries LayerNorm affines and split adaLN linears: inference only)
+
+    def _run_train(self, x, t, y):
+        """training forward (autograd enabled): the linears and the attention core of every block run -- forward and backward -- on
+        the native kernels as autograd nodes, the memory-bound glue between them is differentiable PyTorch (models/dit_train.py)"""
+        from .dit_train import DiTTrainEngine
+
+        if not self._train_supported:
+            raise NotImplementedError(f"{type(self).__name__}: the native training step covers DiT only; use torch.no_grad() / eval "
+                                      "for sampling")
+        if self.precision != "bf16":
+            raise NotImplementedError("native DiT training runs in the bf16 mode only")
+        _lib.load()
+        device = x.device
+        Hh, Ww = self.img_size
+        if x.dim() != 4 or x.shape[1] != self.in_channels or tuple(x.shape[2:]) != (Hh, Ww):
+            raise ValueError(f"DiT.forward: expected x of shape [B, {self.in_channels}, {Hh}, {Ww}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        if t.shape[0] != B or (y is not None and y.shape[0] != B):
+            raise ValueError("DiT.forward: t / y batch size mismatch")
+        x = x.detach().contiguous().float()
+        t = t.to(device=device, dtype=torch.long).contiguous()
+        if y is not None:
+            y = y.to(device=device, dtype=torch.long).contiguous()
+        engines = self.__dict__.setdefault("_train_engines", {})
+        with torch.cuda.device(device):
+            eng = engines.get((str(device), B))
+            if eng is None:
+                eng = engines[(str(device), B)] = DiTTrainEngine(self, device, B)
+            return eng.forward(x, t, y)
+
     def _run(self, x, t, y, cfg):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise _lib.DmcError("DiT.forward: CUDA tensors only -- the B200 hot path has no CPU / PyTorch fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("the native DiT implements the inference forward only (sampling); "
-                                      "wrap calls in torch.no_grad() / model.eval()")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the native DiT does not differentiate with respect to its image input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if cfg:
+                raise NotImplementedError("forward_cfg is a sampling call: wrap it in torch.no_grad()")
+            return self._run_train(x, t, y)
         _lib.load()
         device = x.device
         self._ensure_packed(device)

@@ -43,8 +43,8 @@ REF = os.environ.get("DMC_REFERENCE_DIR", "/root/reference")
 
 from diffusion_models_collection_b200 import synth  # noqa: E402
 from oracle.sched_oracle import toy_model  # noqa: E402
-from tests.golden_cases import (DIT_CASES, UNET_CASES, SMALL_UNET, TRAIN_CASES, case_inputs, perturbed_state_dict,  # noqa: E402
-                                sample_index, train_inputs)
+from tests.golden_cases import (DIT_CASES, UNET_CASES, SMALL_UNET, TRAIN_CASES, TRAIN_DIT_CASES, case_inputs,  # noqa: E402
+                                perturbed_state_dict, sample_index, train_inputs)
 
 
 def _load(name, rel):
@@ -308,6 +308,34 @@ def gen_train():
         out[name + "/sums"] = np.array(sums)
         print("train", name, "loss", loss.item(), "params", len(names), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
     np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
+
+
+def gen_train_dit():
+    """train_dit_golden.npz: loss and parameter gradients of the reference's own DDPM.p_losses(DiT, ...) + backward() (eval mode)"""
+    out = {}
+    for name, c in TRAIN_DIT_CASES.items():
+        cfg = synth.CIFAR_DIT
+        net = ref_dit.DiT(**cfg, num_classes=c["num_classes"]).eval()
+        net.load_state_dict(synth.make_dit_state_dict(cfg, c["num_classes"], seed=c["wseed"]), strict=True)
+        ddpm = ref_ddpm.DDPM(num_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", device="cpu")
+        x0, t, y, noise = train_inputs(c)
+        loss = ddpm.p_losses(net, x0, t, y, noise=noise, loss_type="l2")
+        loss.backward()
+        out[name + "/loss"] = np.float64(loss.item())
+        names, norms = [], []
+        for k, p in net.named_parameters():
+            g = p.grad
+            names.append(k)
+            norms.append(float(g.double().norm()))
+            flat = g.reshape(-1)
+            if g.dim() == 1 and flat.numel() <= 4096:
+                out[f"{name}/full/{k}"] = flat.numpy().copy()
+            else:
+                out[f"{name}/sample/{k}"] = flat[torch.from_numpy(sample_index(flat.numel()))].numpy().copy()
+        out[name + "/names"] = np.array(names)
+        out[name + "/norms"] = np.array(norms)
+        print("train_dit", name, "loss", loss.item(), "params", len(names), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
+    np.savez_compressed(os.path.join(HERE, "train_dit_golden.npz"), **out)
 
 
 CONFIG1_HORIZONS = [1, 2, 3, 5, 10, 20, 50]  # states after this many free-running DDIM steps

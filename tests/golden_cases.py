@@ -53,6 +53,11 @@ def case_inputs(c):
 TRAIN_CASES = {"cond_b3": dict(num_classes=10, B=3, seed=7), "uncond_b2": dict(num_classes=None, B=2, seed=8)}
 
 
+# DiT training step (reference models/dit.py under DDPM.p_losses + backward, eval mode): CIFAR DiT, all zero-init tensors
+# re-randomised (synth.make_dit_state_dict)
+TRAIN_DIT_CASES = {"dit_cond_b3": dict(num_classes=10, B=3, seed=17, wseed=11), "dit_uncond_b2": dict(num_classes=None, B=2, seed=18, wseed=12)}
+
+
 def train_inputs(c):
     """inputs of one training iteration (utils/trainer.py:221-251): images in [-1, 1], labels already shifted (0 = null), t, noise"""
     g = torch.Generator().manual_seed(c["seed"])

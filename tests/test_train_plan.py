@@ -121,6 +121,38 @@ def test_weight_repack_items_describe_every_gemm_operand(fake_lib):
             assert tns.shape == (extra[1], w.shape[0]) and extra[0] + extra[1] <= w.shape[1]
 
 
+def test_dit_training_engine_hands_a_gradient_to_every_parameter(fake_lib):
+    """host logic of models/dit_train.py with the library replaced by the recorder: every linear has a forward, an input-gradient
+    and a weight-gradient launch, the attention backward runs once per block, every parameter receives a gradient of its shape"""
+    from diffusion_models_collection_b200 import synth
+    from diffusion_models_collection_b200.models.dit import DiT
+
+    cfg = dict(synth.CIFAR_DIT, depth=2)
+    net = DiT(**cfg, num_classes=10).eval()
+    net.load_state_dict(synth.make_dit_state_dict(cfg, 10, seed=1))
+    x, t, y = torch.randn(2, 3, 32, 32), torch.randint(0, 1000, (2,)), torch.tensor([0, 7])
+    eps = net._run_train(x, t, y)
+    assert eps.shape == x.shape
+    eng = next(iter(net._train_engines.values()))
+    for lay in eng.layers.values():  # what the kernels would have written
+        lay.y.zero_(), lay.dw.fill_(1.0), lay.db.fill_(2.0)
+    for buf in list(eng._dx.values()) + list(eng._dy.values()):
+        buf.zero_()
+    eps = net._run_train(x, t, y)
+    eps.sum().backward()
+    for n, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, n
+    calls = [c[0] for c in fake_lib.calls]
+    assert calls.count("dmc_conv_wgrad") == 4 * 2 and calls.count("dmc_attention_backward") == 2
+    assert calls.count("dmc_channel_sum") == 4 * 2
+    assert float(net.get_parameter("blocks.0.mlp.0.weight").grad.mean()) == 1.0
+    assert net.get_parameter("blocks.0.mlp.0.weight").grad.data_ptr() != eng.layers["blocks.0.fc1"].dw.data_ptr()
+    from diffusion_models_collection_b200.models.dim import DiM
+
+    with pytest.raises(NotImplementedError):
+        DiM(hidden_size=512, depth=1)._run_train(x, t, None)
+
+
 def _native_allreduce_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
