@@ -646,7 +646,12 @@ def ncu_traffic(nimg):
     import glob
 
     best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*forward_ncu*.json"))):
+    import re
+
+    def order(path):  # r02_forward_ncu_run20.json after r02_forward_ncu_run8.json: (round, run) as numbers
+        return [int(v) for v in re.findall(r"\d+", os.path.basename(path))]
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*forward_ncu*.json")), key=order):
         try:
             d = json.load(open(f))
         except Exception:
