@@ -96,6 +96,21 @@ class AttnBwdDesc(C.Structure):
                 ("heads", C.c_int32), ("C", C.c_int32)]
 
 
+class DitGlmDesc(C.Structure):
+    _fields_ = [("x_in", vp), ("y", vp), ("gate", vp), ("x_out", vp), ("h", vp), ("shift", vp), ("scale", vp),
+                ("mod_stride", C.c_int32), ("gate_stride", C.c_int32), ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32),
+                ("eps", C.c_float), ("drop_p", C.c_float), ("seed", C.c_uint32)]
+
+
+class DitGlmBwdDesc(C.Structure):
+    _fields_ = [("x", vp), ("dh", vp), ("dx_out", vp), ("y", vp), ("gate", vp), ("scale", vp), ("mod_stride", C.c_int32),
+                ("gate_stride", C.c_int32), ("dx_in", vp), ("dy", vp), ("dgate", vp), ("dshift", vp), ("dscale", vp), ("B", C.c_int32), ("L", C.c_int32),
+                ("C", C.c_int32), ("eps", C.c_float), ("drop_p", C.c_float), ("seed", C.c_uint32), ("scratch", vp)]
+
+
+DIT_GLM_BWD_SLICES = 4  # DMC_DIT_GLM_BWD_SLICES of include/dmc.h
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("x", vp), ("dy", vp), ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin", C.c_int32),
                 ("Cout", C.c_int32), ("stride", C.c_int32), ("taps", C.c_int32), ("splits", C.c_int32), ("partial", vp),
@@ -188,6 +203,10 @@ SYMBOLS = {
     "dmc_attention_backward": (C.c_int, [C.POINTER(AttnBwdDesc), vp]),
     "dmc_channel_sum": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "dmc_dilate2x": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dmc_dit_gate_ln_mod": (C.c_int, [C.POINTER(DitGlmDesc), vp]),
+    "dmc_dit_gate_ln_mod_backward": (C.c_int, [C.POINTER(DitGlmBwdDesc), vp]),
+    "dmc_gelu_forward": (C.c_int, [vp, vp, C.c_int64, C.c_float, C.c_uint32, vp]),
+    "dmc_gelu_backward": (C.c_int, [vp, vp, vp, C.c_int64, C.c_float, C.c_uint32, vp]),
     "dmc_pack_weights": (C.c_int, [vp, C.c_int32, vp]),
     "dmc_opt_grad_norm": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp]),
     "dmc_opt_adamw_step": (C.c_int, [vp, vp, C.c_int32, C.POINTER(AdamWDesc), vp, vp]),

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdmc_b200.so")
 OBJ = os.path.join(PKG, "csrc", "_build")
 
-SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu", "dit_ops.cu", "conv_wgrad.cu", "train_ops.cu", "attention_bwd_mma.cu", "optim.cu",
+SOURCES = ["plan.cu", "sched.cu", "elementwise.cu", "conv_umma.cu", "conv_ref.cu", "attention.cu", "attention_umma.cu", "dit_ops.cu", "conv_wgrad.cu", "train_ops.cu", "attention_bwd_mma.cu", "optim.cu", "dit_train_ops.cu",
            "conv_inst_256_1_2.cu", "conv_inst_128_2_2.cu", "conv_inst_256_1_1.cu", "conv_inst_128_2_1.cu", "conv_inst_128_1_1.cu",
            "conv_inst_64_1_1.cu", "conv_inst_32_1_1.cu"]
 NVCC_FLAGS = [

@@ -55,6 +55,11 @@ bool conv_affine_supported(int B, int H, int W, int Cin, int Cout);
 uint32_t dropout_threshold(float p);
 int launch_gn_backward(const dmc_gn_bwd_desc& d, cudaStream_t st);
 int launch_attention_backward(const dmc_attn_bwd_desc& d, cudaStream_t st);
+// dit_train_ops.cu
+int launch_dit_gate_ln_mod(const dmc_dit_glm_desc& d, cudaStream_t st);
+int launch_dit_gate_ln_mod_backward(const dmc_dit_glm_bwd_desc& d, cudaStream_t st);
+int launch_gelu_forward(const void* u, void* m, int64_t n, float drop_p, uint32_t seed, cudaStream_t st);
+int launch_gelu_backward(const void* u, const void* dm, void* du, int64_t n, float drop_p, uint32_t seed, cudaStream_t st);
 int launch_channel_sum(const void* src, float* out, int B, int HW, int C, int per_image, int accumulate, float* scratch, cudaStream_t st);
 int launch_dilate2x(const void* src, void* dst, int B, int h, int w, int C, cudaStream_t st);
 int launch_attention_backward_mma(const dmc_attn_bwd_desc& d, cudaStream_t st);

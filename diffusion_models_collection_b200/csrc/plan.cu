@@ -178,6 +178,20 @@ int dmc_channel_sum(const void* src, float* out, int32_t B, int32_t HW, int32_t 
                     float* scratch, void* stream) {
   return launch_channel_sum(src, out, B, HW, C, per_image, accumulate, scratch, static_cast<cudaStream_t>(stream));
 }
+int dmc_dit_gate_ln_mod(const dmc_dit_glm_desc* d, void* stream) {
+  DMC_REQUIRE(d != nullptr, "dmc_dit_gate_ln_mod: null descriptor");
+  return launch_dit_gate_ln_mod(*d, static_cast<cudaStream_t>(stream));
+}
+int dmc_dit_gate_ln_mod_backward(const dmc_dit_glm_bwd_desc* d, void* stream) {
+  DMC_REQUIRE(d != nullptr, "dmc_dit_gate_ln_mod_backward: null descriptor");
+  return launch_dit_gate_ln_mod_backward(*d, static_cast<cudaStream_t>(stream));
+}
+int dmc_gelu_forward(const void* u, void* m, int64_t n, float drop_p, uint32_t seed, void* stream) {
+  return launch_gelu_forward(u, m, n, drop_p, seed, static_cast<cudaStream_t>(stream));
+}
+int dmc_gelu_backward(const void* u, const void* dm, void* du, int64_t n, float drop_p, uint32_t seed, void* stream) {
+  return launch_gelu_backward(u, dm, du, n, drop_p, seed, static_cast<cudaStream_t>(stream));
+}
 int dmc_dilate2x(const void* src, void* dst, int32_t B, int32_t h, int32_t w, int32_t C, void* stream) {
   return launch_dilate2x(src, dst, B, h, w, C, static_cast<cudaStream_t>(stream));
 }

@@ -10,19 +10,26 @@ the hand-written sm_100a kernels behind the C ABI:
   linear bias grad     dmc_channel_sum
   attention            tcgen05 forward (P in tensor memory), dmc_attention_backward
 
-The memory-bound glue between them -- LayerNorm + adaLN modulate, GELU, the gated residual adds on the fp32 stream, the
-conditioning MLPs, patch embedding (K = 12) and the 12-column output head (0.7 % of the FLOPs) -- is ordinary differentiable
-PyTorch on the GPU, so autograd supplies its backward; each native op is a ``torch.autograd.Function`` node in that graph.  This is
-the first, correctness-first form of the DiT step: the glue costs extra HBM passes (and one staging copy per GEMM operand, because
-the TMA descriptors of a launch plan are bound to fixed buffers) that fused kernels -- the UNet engine's route, models/unet_train.py
--- would remove.  Dropout: the MLP dropouts of the block (models/dit.py:98,100) are applied in ``.train()`` mode; the dropout on the
-attention probabilities inside nn.MultiheadAttention is not (the attention kernel has none).
+The memory-bound glue between them is fused into three more native kernels (csrc/dit_train_ops.cu), each an autograd node too:
+
+  gated residual + LayerNorm + adaLN modulate   x_out = x_in + gate * y;  h = LN(x_out) * (1 + scale) + shift -> bf16, written straight
+                                                into the next GEMM's operand buffer; its backward also yields the per-image gradients of
+                                                gate / shift / scale (one CTA per image, fixed summation order)
+  GELU forward / backward                       between fc1 and fc2 (erf form)
+
+What stays in PyTorch (differentiable, < 1 % of the FLOPs and of the bytes): patch embedding (K = 12) + pos_embed, the timestep /
+label conditioning MLPs and the adaLN_modulation linears ([B, hidden] matrices), the 12-column output head and unpatchify.  With
+`DMC_DIT_TRAIN_GLUE=torch` the LayerNorm / GELU / residual glue runs in PyTorch as well (the first form of this step: 39.9 ms
+per step at batch 128 against the fused kernels' figure in DESIGN.md section 10; kept as a cross-check).  Dropout: the MLP dropouts
+of the block (models/dit.py:97,100) are applied in ``.train()`` mode inside the GELU and residual kernels (counter-based mask, regenerated
+by the backward kernels); the dropout on the attention probabilities inside nn.MultiheadAttention is not (the attention kernel has none).
 
 There is no CPU fallback: every native op raises when the CUDA library or device is missing."""
 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as F
@@ -82,6 +89,99 @@ class _Attention(torch.autograd.Function):
             raise _lib.DmcError(f"DiT attention backward: {eng.lib.dmc_last_error().decode()}")
         eng.keep.append(dout)
         return None, None, eng.dqkv.view_as(eng.dqkv)
+
+
+def _row_ptr(t):
+    """(pointer, row stride in elements) of a [B, C] fp32 chunk of the adaLN table"""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    return t.data_ptr(), t.stride(0)
+
+
+class _GateLnMod(torch.autograd.Function):
+    """x_out = x_in + gate * y (when y is given);  h = LayerNorm(x_out) * (1 + scale) + shift -> bf16 into `h_buf`.
+    Returns (x_out, h) with y, h alone without."""
+
+    @staticmethod
+    def forward(ctx, eng, slot, h_buf, x_in, shift, scale, y=None, gate=None, drop=0.0):
+        x_in = x_in.contiguous()
+        d = _lib.DitGlmDesc()
+        d.x_in, d.h = x_in.data_ptr(), h_buf.data_ptr()
+        d.shift, ms = _row_ptr(shift)
+        d.scale, ms2 = _row_ptr(scale)
+        assert ms == ms2
+        d.mod_stride, d.B, d.L, d.C, d.eps = ms, eng.B, eng.L, eng.hs, 1e-6
+        x_out = x_in
+        if y is not None:
+            y = y.contiguous()
+            x_out = eng.stream_buf(slot)
+            d.y, d.x_out = y.data_ptr(), x_out.data_ptr()
+            d.gate, d.gate_stride = _row_ptr(gate)
+            d.drop_p, d.seed = drop, eng.op_seed(slot)
+        if eng.lib.dmc_dit_gate_ln_mod(C.byref(d), _lib.stream_ptr()) < 0:
+            raise _lib.DmcError(f"DiT training: {eng.lib.dmc_last_error().decode()}")
+        ctx.eng, ctx.step, ctx.has_y = eng, eng.step_id, y is not None
+        ctx.drop, ctx.seed = (drop, eng.op_seed(slot)) if y is not None else (0.0, 0)
+        ctx.keep = (x_out, y, gate, scale, shift)
+        ctx.set_materialize_grads(False)
+        h = h_buf.view_as(h_buf)
+        return (x_out.view_as(x_out), h) if y is not None else h
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng = ctx.eng
+        eng.check_step(ctx.step)
+        dx_out, dh = grads if ctx.has_y else (None, grads[0])
+        x_out, y, gate, scale, shift = ctx.keep
+        B, hs = eng.B, eng.hs
+        if dh is None:
+            raise RuntimeError("DiT training: the modulated LayerNorm output received no gradient")
+        dh = dh.contiguous()
+        dx_in = dx_out.contiguous() if dx_out is not None else torch.empty_like(x_out)  # (in place on the later layers' gradient)
+        sums = torch.empty((3, B, hs), dtype=torch.float32, device=x_out.device)
+        d = _lib.DitGlmBwdDesc()
+        d.x, d.dh, d.dx_in = x_out.data_ptr(), dh.data_ptr(), dx_in.data_ptr()
+        d.dx_out = dx_out.data_ptr() if dx_out is not None else None
+        d.scale, d.mod_stride = _row_ptr(scale)
+        d.dshift, d.dscale = sums[1].data_ptr(), sums[2].data_ptr()
+        d.B, d.L, d.C, d.eps = B, eng.L, hs, 1e-6
+        d.scratch = eng.glm_scratch.data_ptr()
+        dy = None
+        if ctx.has_y:
+            dyb = eng.dy_buf(hs)
+            d.y, d.dy, d.dgate = y.data_ptr(), dyb.data_ptr(), sums[0].data_ptr()
+            d.gate, d.gate_stride = _row_ptr(gate)
+            d.drop_p, d.seed = ctx.drop, ctx.seed
+            dy = dyb.view_as(dyb)
+        if eng.lib.dmc_dit_gate_ln_mod_backward(C.byref(d), _lib.stream_ptr()) < 0:
+            raise _lib.DmcError(f"DiT training: {eng.lib.dmc_last_error().decode()}")
+        eng.keep.append((dh, dx_in))
+        return None, None, None, dx_in, sums[1], sums[2], dy, (sums[0] if ctx.has_y else None), None
+
+
+class _Gelu(torch.autograd.Function):
+    """m = gelu(u) (erf form) from the fc1 output into the fc2 operand buffer"""
+
+    @staticmethod
+    def forward(ctx, eng, i, u, drop=0.0):
+        m = eng.layers[f"blocks.{i}.fc2"].x
+        u = u.contiguous()
+        seed = eng.op_seed(1000 + i)
+        if eng.lib.dmc_gelu_forward(u.data_ptr(), m.data_ptr(), u.numel(), drop, seed, _lib.stream_ptr()) < 0:
+            raise _lib.DmcError(f"DiT training: {eng.lib.dmc_last_error().decode()}")
+        ctx.eng, ctx.step, ctx.u, ctx.drop, ctx.seed = eng, eng.step_id, u, drop, seed
+        return m.view_as(m)
+
+    @staticmethod
+    def backward(ctx, dm):
+        eng = ctx.eng
+        eng.check_step(ctx.step)
+        dm = dm.contiguous()
+        du = eng.dy_buf(ctx.u.shape[-1])
+        if eng.lib.dmc_gelu_backward(ctx.u.data_ptr(), dm.data_ptr(), du.data_ptr(), dm.numel(), ctx.drop, ctx.seed,
+                                     _lib.stream_ptr()) < 0:
+            raise _lib.DmcError(f"DiT training: {eng.lib.dmc_last_error().decode()}")
+        eng.keep.append(dm)
+        return None, None, du.view_as(du), None
 
 
 class _Layer:
@@ -151,6 +251,19 @@ class DiTTrainEngine:
             lay.wd.partial = self.part.data_ptr()
         self.sum_scratch = torch.empty((B * max(3 * hs, hid),), dtype=f32, device=device)
         self._packed_ver = None
+        self._stream = {}   # fp32 token stream after every gated residual add (kept for the LayerNorm backward)
+        self.h_final = torch.empty((B, L, hs), dtype=bf16, device=device)
+        self.glm_scratch = torch.empty((B * _lib.DIT_GLM_BWD_SLICES * 3 * hs,), dtype=f32, device=device)
+        self.native_glue = os.environ.get("DMC_DIT_TRAIN_GLUE", "native") != "torch"
+
+    def op_seed(self, slot):
+        """dropout seed of one op of the current forward (base drawn once per forward from torch's CPU generator)"""
+        return (self.seed_base + 0x9E3779B1 * (slot + 1)) & 0xFFFFFFFF
+
+    def stream_buf(self, slot):
+        if slot not in self._stream:
+            self._stream[slot] = torch.empty((self.B, self.L, self.hs), dtype=torch.float32, device=self.device)
+        return self._stream[slot]
 
     # ------------------------------------------------------------------------------------------------------------------
     def dy_buf(self, c):
@@ -218,6 +331,7 @@ class DiTTrainEngine:
         self.pack()
         self.step_id += 1
         self.keep = []
+        self.seed_base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if (net.training and net.dropout > 0) else 0
         P = dict(net.named_parameters())
         p = net.patch_size
         # PatchEmbed + pos_embed (models/dit.py:23-27, 271)
@@ -233,6 +347,43 @@ class DiTTrainEngine:
             c = c + F.embedding(torch.clamp(y, 0, net.num_classes), P["y_embedder.embedding_table.weight"], padding_idx=0)
         sc = F.silu(c)
         drop = float(net.dropout) if net.training else 0.0
+        if not self.native_glue:
+            return self._forward_torch_glue(tok, sc, P, drop)
+        x, y_prev, g_prev = tok.contiguous(), None, None
+        for i in range(net.depth):
+            b = f"blocks.{i}"
+            mod = F.linear(sc, P[b + ".adaLN_modulation.1.weight"], P[b + ".adaLN_modulation.1.bias"])
+            sh1, sc1, g1, sh2, sc2, g2 = mod.chunk(6, dim=-1)
+            hbuf = self.layers[b + ".qkv"].x
+            if y_prev is None:
+                h = _GateLnMod.apply(self, 2 * i, hbuf, x, sh1, sc1)
+            else:
+                x, h = _GateLnMod.apply(self, 2 * i, hbuf, x, sh1, sc1, y_prev, g_prev, drop)
+            qkv = _Linear.apply(self, b + ".qkv", h, P[b + ".attn.in_proj_weight"], P[b + ".attn.in_proj_bias"])
+            ao = _Attention.apply(self, i, qkv)
+            y1 = _Linear.apply(self, b + ".out", ao, P[b + ".attn.out_proj.weight"], P[b + ".attn.out_proj.bias"])
+            x, h = _GateLnMod.apply(self, 2 * i + 1, self.layers[b + ".fc1"].x, x, sh2, sc2, y1, g1)
+            u = _Linear.apply(self, b + ".fc1", h, P[b + ".mlp.0.weight"], P[b + ".mlp.0.bias"])
+            m = _Gelu.apply(self, i, u, drop)                 # GELU + Dropout (models/dit.py:96-97)
+            y2 = _Linear.apply(self, b + ".fc2", m, P[b + ".mlp.3.weight"], P[b + ".mlp.3.bias"])
+            y_prev, g_prev = y2, g2                            # (the Dropout after fc2, :100, is applied by the next fused kernel)
+        mod = F.linear(sc, P["final_layer.adaLN_modulation.1.weight"], P["final_layer.adaLN_modulation.1.bias"])
+        shift, scale = mod.chunk(2, dim=-1)
+        x, h = _GateLnMod.apply(self, 2 * net.depth, self.h_final, x, shift, scale, y_prev, g_prev, drop)
+        return self._head(h.float(), P)
+
+    def _head(self, h, P):
+        """final linear (12 columns) + unpatchify (models/dit.py:150, 249-261)"""
+        net, B = self.net, self.B
+        p = net.patch_size
+        o = F.linear(h, P["final_layer.linear.weight"], P["final_layer.linear.bias"])
+        co = net.out_channels
+        o = o.reshape(B, net.h_tokens, net.w_tokens, p, p, co)
+        return torch.einsum("nhwpqc->nchpwq", o).reshape(B, co, net.h_tokens * p, net.w_tokens * p)
+
+    def _forward_torch_glue(self, tok, sc, P, drop):
+        """the first form of this step: LayerNorm / modulate / GELU / gated residual as differentiable PyTorch"""
+        net, hs = self.net, self.hs
         for i in range(net.depth):
             b = f"blocks.{i}"
             mod = F.linear(sc, P[b + ".adaLN_modulation.1.weight"], P[b + ".adaLN_modulation.1.bias"])
@@ -254,10 +405,7 @@ class DiTTrainEngine:
         mod = F.linear(sc, P["final_layer.adaLN_modulation.1.weight"], P["final_layer.adaLN_modulation.1.bias"])
         shift, scale = mod.chunk(2, dim=-1)
         h = F.layer_norm(tok, (hs,), eps=1e-6) * (1 + scale[:, None]) + shift[:, None]
-        o = F.linear(h, P["final_layer.linear.weight"], P["final_layer.linear.bias"])
-        co = net.out_channels
-        o = o.reshape(B, net.h_tokens, net.w_tokens, p, p, co)
-        return torch.einsum("nhwpqc->nchpwq", o).reshape(B, co, net.h_tokens * p, net.w_tokens * p)
+        return self._head(h, P)
 
     def destroy(self):
         if getattr(self, "handle", None) is not None:

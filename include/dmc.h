@@ -175,6 +175,58 @@ typedef struct {
 } dmc_attn_bwd_desc;
 DMC_API int dmc_attention_backward(const dmc_attn_bwd_desc* d, void* stream);
 
+/* ---- DiT training step: the memory-bound glue between the GEMMs (models/dit_train.py; reference models/dit.py:111-132 under
+ * autograd).  Forward:  x_out = x_in + gate[n] * y   (skipped when y == NULL: the first LayerNorm of the model)
+ *                       h     = LayerNorm(x_out, eps) * (1 + scale[n]) + shift[n]  -> bf16 (the next GEMM's operand)
+ * shift / scale: row n at ptr + n * mod_stride, gate: row n at ptr + n * gate_stride (chunks of adaLN_modulation outputs). */
+typedef struct {
+  const float* x_in;   /* fp32 [B, L, C] token stream */
+  const void* y;       /* bf16 [B, L, C] branch output (attention out_proj / mlp fc2), or NULL */
+  const float* gate;   /* per-image gate rows, NULL iff y is NULL */
+  float* x_out;        /* fp32 [B, L, C], NULL iff y is NULL (x_out == x_in then) */
+  void* h;             /* bf16 [B, L, C] */
+  const float* shift;
+  const float* scale;
+  int32_t mod_stride;  /* row stride (floats) of shift / scale */
+  int32_t gate_stride; /* row stride (floats) of gate (it comes from the PREVIOUS adaLN table when this LayerNorm opens a block) */
+  int32_t B, L, C;     /* C % 128 == 0, 128 <= C <= 1024 */
+  float eps;
+  float drop_p;        /* nn.Dropout on y before the gated add (models/dit.py:100, training mode); 0: none */
+  uint32_t seed;       /* counter-based mask: element i is kept when its 16 hash bits of (seed, i) are >= round(p * 65536) */
+} dmc_dit_glm_desc;
+DMC_API int dmc_dit_gate_ln_mod(const dmc_dit_glm_desc* d, void* stream);
+/* Its backward: from dh (gradient of h, the GEMM's input gradient) and dx_out (gradient of the stream from later layers, or NULL):
+ *   dx_in = dx_out + LayerNorm'(dh * (1 + scale)),  dy = dx_in * gate,
+ *   dgate[n] = sum_l dx_in * y,  dshift[n] = sum_l dh,  dscale[n] = sum_l dh * xhat      (fp32 [B, C] each, contiguous)
+ * One CTA per image; the per-image sums are added in a fixed order (deterministic).  dx_in may alias dx_out. */
+typedef struct {
+  const float* x;      /* fp32 [B, L, C]: x_out of the forward call (x_in when it had no y) */
+  const void* dh;      /* bf16 [B, L, C] */
+  const float* dx_out; /* fp32 [B, L, C] or NULL */
+  const void* y;       /* bf16 [B, L, C] or NULL */
+  const float* gate;   /* NULL iff y is NULL */
+  const float* scale;
+  int32_t mod_stride, gate_stride;
+  float* dx_in;        /* fp32 [B, L, C] */
+  void* dy;            /* bf16 [B, L, C], NULL iff y is NULL */
+  float* dgate;        /* fp32 [B, C], NULL iff y is NULL */
+  float* dshift;       /* fp32 [B, C] */
+  float* dscale;       /* fp32 [B, C] */
+  int32_t B, L, C;
+  float eps;
+  float drop_p;        /* the forward call's dropout (same seed: the mask is regenerated) */
+  uint32_t seed;
+  float* scratch;      /* optional fp32 [B, DMC_DIT_GLM_BWD_SLICES, 3, C]: with it every image is cut into row slices over several
+                          CTAs whose partial sums a second launch adds in slice order; NULL: one CTA per image */
+} dmc_dit_glm_bwd_desc;
+#define DMC_DIT_GLM_BWD_SLICES 4
+DMC_API int dmc_dit_gate_ln_mod_backward(const dmc_dit_glm_bwd_desc* d, void* stream);
+/* nn.GELU() (erf form) followed by nn.Dropout(drop_p) on bf16 tensors of n elements (n % 8 == 0): m = drop(gelu(u));
+ * du = drop(dm) * gelu'(u) with the same (seed-generated) mask   (models/dit.py:96-97) */
+DMC_API int dmc_gelu_forward(const void* u_bf16, void* m_bf16, int64_t n, float drop_p, uint32_t seed, void* stream);
+DMC_API int dmc_gelu_backward(const void* u_bf16, const void* dm_bf16, void* du_bf16, int64_t n, float drop_p, uint32_t seed,
+                              void* stream);
+
 /* out[n or 0][c] (+)= sum over pixels (and images unless per_image) of src[n, p, c]: bias and conditioning-row gradients.
  * scratch: fp32 [B, C], needed when per_image == 0 (the images are added in index order by a second kernel) */
 DMC_API int dmc_channel_sum(const void* src_bf16, float* out, int32_t B, int32_t HW, int32_t C, int32_t per_image,

@@ -57,7 +57,7 @@ def test_struct_layouts_match_the_c_compiler():
         "dmc_gn_apply_desc": _lib.GnApplyDesc, "dmc_conv_desc": _lib.ConvDesc, "dmc_attn_desc": _lib.AttnDesc,
         "dmc_upsample_desc": _lib.UpsampleDesc, "dmc_step_desc": _lib.StepDesc, "dmc_dit_cond_desc": _lib.DitCondDesc,
         "dmc_patch_embed_desc": _lib.PatchEmbedDesc, "dmc_ln_mod_desc": _lib.LnModDesc, "dmc_head_desc": _lib.HeadDesc, "dmc_wgrad_desc": _lib.WgradDesc, "dmc_gn_bwd_desc": _lib.GnBwdDesc, "dmc_pack_item": _lib.PackItem, "dmc_opt_item": _lib.OptItem, "dmc_opt_chunk": _lib.OptChunk, "dmc_adamw_desc": _lib.AdamWDesc,
-        "dmc_attn_bwd_desc": _lib.AttnBwdDesc,
+        "dmc_attn_bwd_desc": _lib.AttnBwdDesc, "dmc_dit_glm_desc": _lib.DitGlmDesc, "dmc_dit_glm_bwd_desc": _lib.DitGlmBwdDesc,
     }
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     prog = f'#include <stdio.h>\n#include "dmc.h"\nint main(void){{{body}return 0;}}\n'

@@ -172,6 +172,31 @@ def test_conv_kernel_variants(kind, cins, cout, H, B, variant, monkeypatch):
     assert torch.equal(out, out2) and torch.equal(st, st2)
 
 
+@pytest.mark.parametrize("kind,cin,cout,H,B,k", [("bias", 256, 768, 16, 3, 1), ("bias", 384, 1152, 16, 2, 1), ("res+stats", 256, 256, 16, 5, 1),
+                                                 ("res+stats", 128, 128, 32, 3, 3), ("bias+stats", 256, 256, 8, 4, 1)])
+def test_straight_line_epilogue_is_bit_identical_to_the_generic_loop(kind, cin, cout, H, B, k, monkeypatch):
+    """ConvKParams.epi_fast (one 64-channel TMA box per iteration, no per-chunk decisions) against the generic chunk loop
+    (DMC_CONV_EPI_FAST=0): same arithmetic in the same order -> the same bits, output and GroupNorm partial sums"""
+    monkeypatch.setenv("DMC_CONV_TMA_STORE", "2")
+    x = _q(_rand((B, cin, H, H), 5))
+    w = _q(_rand((cout, cin, k, k), 6, (cin * k * k) ** -0.5))
+    bias = _rand((cout,), 3, 0.1)
+    res = nhwc_bf16(_q(_rand((B, cout, H, H), 8))) if kind.startswith("res") else None
+    args = ([nhwc_bf16(x)], [k * k], pack3(w) if k == 3 else w.reshape(cout, cin), cout)
+    kw = dict(bias=bias, residual=res, stats="stats" in kind)
+    out = {}
+    for fast in ("1", "0"):
+        monkeypatch.setenv("DMC_CONV_EPI_FAST", fast)
+        out[fast] = run_conv(*args, **kw)
+    assert torch.equal(out["1"][0], out["0"][0])
+    if "stats" in kind:
+        assert torch.equal(out["1"][1], out["0"][1])
+    ref = F.conv2d(x, w, bias, padding=k // 2)
+    if res is not None:
+        ref = ref + nchw_f32(res)
+    assert rel_l2(nchw_f32(out["1"][0]), ref) < TOL_BF16
+
+
 @pytest.mark.parametrize("B", [1, 3, 8])
 def test_head_conv_fp32_nchw(B):
     x = _q(_rand((B, 128, 32, 32), 30))
@@ -276,6 +301,29 @@ def test_attention(L, heads, hd, B, impl):
     a = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
     ref = (a @ v).transpose(1, 2).reshape(B, L, C_)
     assert rel_l2(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("heads,B", [(4, 3), (6, 40)])
+def test_attention_kernel_generations_agree(heads, B, monkeypatch):
+    """L = 256: P in tensor memory (default), the ping-pong kernel with P in shared memory (DMC_ATTN_PP=1) and the round-1
+    one-warpgroup-per-tile kernel (DMC_ATTN_PP=0) compute the same softmax(QK^T/8)V; the first two share the summation order of the
+    row sums and differ only in where P lives -> identical bits"""
+    from diffusion_models_collection_b200 import _lib
+
+    C_ = heads * 64
+    qkv = _q(_rand((B, 256, 3 * C_), 81)).to(torch.bfloat16).contiguous()
+    outs = {}
+    for mode in ("2", "1", "0"):
+        monkeypatch.setenv("DMC_ATTN_PP", mode)
+        out = torch.full((B, 256, C_), float("nan"), device="cuda", dtype=torch.bfloat16)
+        d = _lib.AttnDesc()
+        d.qkv, d.out, d.B, d.L, d.heads, d.C, d.impl = qkv.data_ptr(), out.data_ptr(), B, 256, heads, C_, 0
+        p = Plan()
+        p.add("attention", d)
+        p.run()
+        outs[mode] = out
+    assert torch.equal(outs["2"], outs["1"])
+    assert rel_l2(outs["2"].float(), outs["0"].float()) < 2e-3
 
 
 @pytest.mark.parametrize("uniform_t,has_y", [(1, True), (0, True), (0, False), (1, False)])
