@@ -304,9 +304,19 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
   kp.slab = 0;
   kp.slab_bytes = 0;
   P->tmS = P->tmA[0];
-  if (env_flag("DMC_CONV_SLAB", 1) && !kp.bres && (epi == 0 || epi == 2 || epi == 4) && d.src_taps[0] == 9 && d.stride == 1 && d.up_phase < 0 && BNIMG == 1 &&
-      kp.tiles_w == 1 && BW >= 8 && kp.tiles_h % tc.mt == 0) {
-    const int rows = tc.mt * BH + 2;
+  // the 2 x 2 windows of the Upsample phase convolutions (models/unet.py:118-120 as four stride-1 convolutions over the low-resolution
+  // map) take the same route: one box of BH + 1 rows serves both vertical taps (DMC_CONV_SLAB_PHASE=0: regular steps, for A/B runs)
+  const bool phase_slab = d.up_phase >= 0 && d.src_taps[0] == 4 && d.nsrc == 1 && env_flag("DMC_CONV_SLAB_PHASE", 1);
+  kp.slab_nv = kp.slab_nh = 3;
+  kp.slab_dh0 = kp.slab_dw0 = -1;
+  if (phase_slab) {
+    kp.slab_nv = kp.slab_nh = 2;
+    kp.slab_dh0 = kp.dh[0][0];
+    kp.slab_dw0 = kp.dw[0][0];
+  }
+  if (env_flag("DMC_CONV_SLAB", 1) && !kp.bres && (epi == 0 || epi == 2 || epi == 4) && (d.src_taps[0] == 9 ? d.up_phase < 0 : phase_slab) &&
+      d.stride == 1 && BNIMG == 1 && kp.tiles_w == 1 && BW >= 8 && kp.tiles_h % tc.mt == 0) {
+    const int rows = tc.mt * BH + kp.slab_nv - 1;
     const int C = d.src_c[0];
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(d.Win), static_cast<cuuint64_t>(d.Hin),
                           static_cast<cuuint64_t>(d.B)};
@@ -321,7 +331,7 @@ int conv_prepare(const dmc_conv_desc& d, ConvPrepared** out) {
     }
   }
   kp.a_bytes = kp.slab ? std::max(kp.slab_bytes, a_tiles_bytes) : a_tiles_bytes;
-  kp.stage_bytes = kp.a_bytes + (kp.bres ? 0 : (kp.slab ? 3 : 1) * b_tile);
+  kp.stage_bytes = kp.a_bytes + (kp.bres ? 0 : (kp.slab ? kp.slab_nv : 1) * b_tile);
   // (3) TMA-store epilogue: coalesced 32-row x 64-channel boxes instead of per-thread 16-byte stores.  Pays for itself
   //     when the K loop is short (the epilogue is then the bottleneck: measured -10 % .. -22 % up to 18-27 K blocks);
   //     longer K loops lose more from the 32 KB it takes out of the operand ring (+4 % .. +19 % at 36-48 K blocks).

@@ -63,6 +63,8 @@ struct ConvKParams {
   int nst, stage_bytes, a_bytes, b_region_bytes;
   int bres;                   // weights of the whole K extent stay resident (short-K GEMMs: 1x1 convs, transformer linears)
   int slab, slab_bytes;       // 3x3 segment 0 is loaded as row slabs shared by the three vertical taps
+  int slab_nv, slab_nh;       // vertical / horizontal taps of the slab segment: 3 x 3, or 2 x 2 for an Upsample phase convolution
+  int slab_dh0, slab_dw0;     // offset of its first tap (-1 for 3x3; -1 or 0 per axis for a phase)
   // fused GroupNorm(+SiLU) of the output (VAR_GN): see dmc_conv_desc.gn_*
   int gn_nver;                // normalised versions written by the epilogue (1 or 2)
   int gn_P;                   // output pixels per image
@@ -285,8 +287,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   //   slab step (3x3 segment 0 when p.slab): ONE box of (MT*BH + 2) image rows x BW pixels x 64 channels shifted by dw
   //     serves the three vertical taps dh = -1, 0, +1 of MT vertically adjacent sub-tiles (sub-tile mt, tap dh reads rows
   //     [mt*BH + dh + 1, +BH) of the box: a 1024-byte aligned offset) -> the activations cross L2->SM 3x instead of 9x;
+  //     the 2 x 2 windows of the Upsample phase convolutions run the same steps with slab_nv = slab_nh = 2 (2x instead of 4x);
   //   regular step: MT boxes of 128 pixels x 64 channels for one (tap, chunk) K block.
-  const int slab_steps = SLAB ? 3 * p.seg_chunks[0] : 0;
+  const int slab_nv = p.slab_nv, slab_nh = p.slab_nh;
+  const int slab_steps = SLAB ? slab_nh * p.seg_chunks[0] : 0;
   const int reg_kb0 = SLAB ? p.seg_kb_end[0] : 0;            // first K block handled by regular steps
   const int num_steps = slab_steps + (p.num_kb - reg_kb0);
 
@@ -321,15 +325,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint8_t* sb = sa + p.a_bytes;
           const uint32_t lbar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0;
           if (SLAB && step < slab_steps) {
-            const int chunk = step / 3, dwi = step % 3;
+            const int chunk = step / slab_nh, dwi = step % slab_nh;
             // the leader's barrier counts the bytes of BOTH CTAs of a pair (the MMAs it issues read both)
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (p.slab_bytes + (bres ? 0 : 3 * B_TILE)));
-            if (CG == 2) tma_load_4d_cg2(sa, &tmS, lbar, chunk * KB, w0[0] + dwi - 1, h0[0] - 1, n0[0]);
-            else tma_load_4d(sa, &tmS, &full_bar[stage], chunk * KB, w0[0] + dwi - 1, h0[0] - 1, n0[0]);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(CG) * (p.slab_bytes + (bres ? 0 : slab_nv * B_TILE)));
+            if (CG == 2) tma_load_4d_cg2(sa, &tmS, lbar, chunk * KB, w0[0] + dwi + p.slab_dw0, h0[0] + p.slab_dh0, n0[0]);
+            else tma_load_4d(sa, &tmS, &full_bar[stage], chunk * KB, w0[0] + dwi + p.slab_dw0, h0[0] + p.slab_dh0, n0[0]);
             if (!bres) {
 #pragma unroll
               for (int dhi = 0; dhi < 3; ++dhi) {
-                const int kb = (dhi * 3 + dwi) * p.seg_chunks[0] + chunk;
+                if (dhi >= slab_nv) break;
+                const int kb = (dhi * slab_nh + dwi) * p.seg_chunks[0] + chunk;
                 if (CG == 2) tma_load_2d_cg2(sb + dhi * B_TILE, &tmB, lbar, kb * KB, n_tile * BN + rank * (BN / 2));
                 else tma_load_2d(sb + dhi * B_TILE, &tmB, &full_bar[stage], kb * KB, n_tile * BN);
               }
@@ -401,10 +406,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
           const uint32_t sb = sa + p.a_bytes;
           if (SLAB && step < slab_steps) {
-            const int chunk = step / 3, dwi = step % 3;
+            const int chunk = step / slab_nh, dwi = step % slab_nh;
 #pragma unroll
             for (int dhi = 0; dhi < 3; ++dhi) {
-              const int kb = (dhi * 3 + dwi) * p.seg_chunks[0] + chunk;
+              if (dhi >= slab_nv) break;
+              const int kb = (dhi * slab_nh + dwi) * p.seg_chunks[0] + chunk;
               const uint64_t bdesc = umma_desc_k_sw128(bres ? bres_addr + kb * B_TILE : sb + dhi * B_TILE);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {

@@ -208,9 +208,12 @@ def test_head_conv_fp32_nchw(B):
     assert rel_l2(out, ref) < 1e-4
 
 
-@pytest.mark.parametrize("C,H,B", [(256, 4, 3), (256, 8, 2), (128, 16, 2)])
-def test_upsample_phase_convs(C, H, B):
-    """nearest-2x + conv3x3 (models/unet.py:118-120) == four 2x2 phase convolutions on the low-res tensor"""
+@pytest.mark.parametrize("slab", ["1", "0"])
+@pytest.mark.parametrize("C,H,B", [(256, 4, 3), (256, 8, 2), (128, 16, 2), (256, 16, 3), (256, 16, 80)])
+def test_upsample_phase_convs(C, H, B, slab, monkeypatch):
+    """nearest-2x + conv3x3 (models/unet.py:118-120) == four 2x2 phase convolutions on the low-res tensor; with row slabs (one box
+    of BH + 1 rows serves both vertical taps of the 2 x 2 window; 16x16 maps) and with regular steps"""
+    monkeypatch.setenv("DMC_CONV_SLAB_PHASE", slab)
     x = _q(_rand((B, C, H, H), 40))
     w = _rand((C, C, 3, 3), 41, (C * 9) ** -0.5)
     bias = _rand((C,), 42, 0.1)
