@@ -233,47 +233,72 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ out_lo,
                                                           const float* __restrict__ shift, const float* __restrict__ scale,
                                                           int mod_stride, size_t tokens, int L, float eps) {
+  // TWO token rows per warp (all loads of both rows issued before the first reduction: twice the bytes in flight per warp -- one
+  // row per warp ran at 4.3 TB/s, latency-bound on its load -> shuffle -> shuffle -> store chain)
   constexpr int C = 128 * V4;
+  constexpr int R = 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t tok = static_cast<size_t>(blockIdx.x) * 8 + warp;
-  if (tok >= tokens) return;
-  const int n = static_cast<int>(tok / L);
-  const float4* xr = reinterpret_cast<const float4*>(x + tok * C);
-  float4 v[V4];
-  float s = 0.f;
+  const size_t tok0 = (static_cast<size_t>(blockIdx.x) * 8 + warp) * R;
+  if (tok0 >= tokens) return;
+  float4 v[R][V4];
+  float s[R];
 #pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int r = 0; r < R; ++r) {
+    const size_t tok = min(tok0 + r, tokens - 1);  // (an odd tail row is computed twice and stored once)
+    const float4* xr = reinterpret_cast<const float4*>(x + tok * C);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) v[r][i] = xr[lane + 32 * i];
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-  const float mean = s * (1.0f / C);
-  float ss = 0.f;
+  for (int r = 0; r < R; ++r) {
+    s[r] = 0.f;
 #pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-    ss += (a * a + b * b) + (c * c + e * e);
+    for (int i = 0; i < V4; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-  const float rstd = rsqrtf(ss * (1.0f / C) + eps);
-  const float4* sh4 = reinterpret_cast<const float4*>(shift + static_cast<size_t>(n) * mod_stride);
-  const float4* sc4 = reinterpret_cast<const float4*>(scale + static_cast<size_t>(n) * mod_stride);
-  uint2* o2 = reinterpret_cast<uint2*>(out + tok * C);
+  for (int o = 16; o; o >>= 1) {
 #pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    const float4 sh = __ldg(sh4 + lane + 32 * i), sc = __ldg(sc4 + lane + 32 * i);
-    const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + sc.x, sh.x);
-    const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + sc.y, sh.y);
-    const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + sc.z, sh.z);
-    const float y3 = fmaf((v[i].w - mean) * rstd, 1.0f + sc.w, sh.w);
-    const uint2 hi = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-    o2[lane + 32 * i] = hi;
-    if (out_lo != nullptr) {  // split-bf16 mode: the rounding remainder
-      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
-      reinterpret_cast<uint2*>(out_lo + tok * C)[lane + 32 * i] =
-          make_uint2(pack_bf16x2(y0 - h0.x, y1 - h0.y), pack_bf16x2(y2 - h1.x, y3 - h1.y));
+    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xFFFFFFFFu, s[r], o);
+  }
+  float mean[R], ss[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mean[r] = s[r] * (1.0f / C);
+    ss[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], e = v[r][i].w - mean[r];
+      ss[r] += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) ss[r] += __shfl_xor_sync(0xFFFFFFFFu, ss[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const size_t tok = tok0 + r;
+    if (tok >= tokens) break;
+    const int n = static_cast<int>(tok / L);
+    const float rstd = rsqrtf(ss[r] * (1.0f / C) + eps);
+    const float4* sh4 = reinterpret_cast<const float4*>(shift + static_cast<size_t>(n) * mod_stride);
+    const float4* sc4 = reinterpret_cast<const float4*>(scale + static_cast<size_t>(n) * mod_stride);
+    uint2* o2 = reinterpret_cast<uint2*>(out + tok * C);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float4 sh = __ldg(sh4 + lane + 32 * i), sc = __ldg(sc4 + lane + 32 * i);
+      const float y0 = fmaf((v[r][i].x - mean[r]) * rstd, 1.0f + sc.x, sh.x);
+      const float y1 = fmaf((v[r][i].y - mean[r]) * rstd, 1.0f + sc.y, sh.y);
+      const float y2 = fmaf((v[r][i].z - mean[r]) * rstd, 1.0f + sc.z, sh.z);
+      const float y3 = fmaf((v[r][i].w - mean[r]) * rstd, 1.0f + sc.w, sh.w);
+      const uint2 hi = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      o2[lane + 32 * i] = hi;
+      if (out_lo != nullptr) {  // split-bf16 mode: the rounding remainder
+        const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+        reinterpret_cast<uint2*>(out_lo + tok * C)[lane + 32 * i] =
+            make_uint2(pack_bf16x2(y0 - h0.x, y1 - h0.y), pack_bf16x2(y2 - h1.x, y3 - h1.y));
+      }
     }
   }
 }
@@ -283,7 +308,7 @@ int launch_ln_modulate(const dmc_ln_mod_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.B > 0 && d.L > 0 && d.C % 128 == 0 && d.C >= 128 && d.C <= 1024 && d.mod_stride % 4 == 0,
               "ln_modulate: C=%d must be a multiple of 128 in [128, 1024]", d.C);
   const size_t tokens = static_cast<size_t>(d.B) * d.L;
-  const int blocks = static_cast<int>((tokens + 7) / 8);
+  const int blocks = static_cast<int>((tokens + 15) / 16);  // 8 warps x 2 rows
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
   __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
 #define LNM(V) ln_modulate_kernel<V><<<blocks, 256, 0, st>>>(d.x, out, out_lo, d.shift, d.scale, d.mod_stride, tokens, d.L, d.eps)
