@@ -1,5 +1,7 @@
 // Memory-bound kernels of the UNet forward: conditioning table, input convolution (fp32 NCHW -> bf16 NHWC),
 // GroupNorm statistics / apply(+SiLU, + channel concat), nearest 2x upsample.  All 128-bit vectorised.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -138,16 +140,19 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                                                    int Cout) {
   constexpr int K = CIN * 9;
   extern __shared__ float sw[];  // [K][Cout] transposed weights, then bias[Cout]
+  // coalesced reads of the [Cout][K] parameter, transposed on the way into shared memory (the strided form -- one cache line per
+  // lane -- cost a third of a block's life); the grid is persistent so that the 14 KB are staged once per SM, not once per 512 pixels
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-    int k = i / Cout, c = i % Cout;
-    sw[i] = w[static_cast<size_t>(c) * K + k];
+    const int c = i / K, k = i % K;
+    sw[k * Cout + c] = __ldg(w + i);
   }
   float* sb = sw + K * Cout;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t total = static_cast<size_t>(B) * H * W;
-  const size_t base = (static_cast<size_t>(blockIdx.x) * 8 + warp) * 64;
+  for (size_t blk = blockIdx.x; blk * 512 < total; blk += gridDim.x) {
+  const size_t base = (blk * 8 + warp) * 64;
   float xv[2][K];
   size_t pix[2];
 #pragma unroll
@@ -212,13 +217,14 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
       }
     }
   }
+  }
 }
 
 int launch_stem(const dmc_stem_desc& d, cudaStream_t st) {
   DMC_REQUIRE(d.x && d.weight && d.bias && d.out, "stem: null pointer argument");
   DMC_REQUIRE(d.Cin >= 1 && d.Cin <= 4 && d.Cout % 16 == 0 && d.x_batch > 0 && d.B > 0, "stem: unsupported shape");
   const size_t total = static_cast<size_t>(d.B) * d.H * d.W;
-  const int blocks = static_cast<int>((total + 511) / 512);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 511) / 512, static_cast<size_t>(num_sms()) * 2));
   const size_t smem = (static_cast<size_t>(d.Cin) * 9 * d.Cout + d.Cout) * sizeof(float);
   DMC_REQUIRE(smem <= 48 * 1024, "stem: Cout=%d too large", d.Cout);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
@@ -309,6 +315,7 @@ struct GnApplyArgs {
   uint4* out_lo;
   int HW, C0_8, C1_8, groups;
   int slots0, slots1;
+  int slab;               // pixels per CTA
   float eps;
   int silu;
   float drop_scale;       // training: 1 / (1 - p) for kept elements
@@ -394,8 +401,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
                    : a.lo1 + static_cast<size_t>(n) * a.HW * a.C1_8 + (cb - a.C0_8);
     dst_lo = a.out_lo + static_cast<size_t>(n) * a.HW * C8 + cb;
   }
-  const int p0 = blockIdx.x * GN_SLAB;
-  const int p1 = min(p0 + GN_SLAB, a.HW);
+  const int p0 = blockIdx.x * a.slab;
+  const int p1 = min(p0 + a.slab, a.HW);
   for (int pb = p0 + r0; pb < p1; pb += 4 * rpi) {
     uint4 in[4], inl[4];
 #pragma unroll
@@ -673,7 +680,16 @@ int launch_gn_apply(const dmc_gn_apply_desc& d, cudaStream_t st) {
   a.lo0 = reinterpret_cast<const uint4*>(d.src_lo[0]);
   a.lo1 = reinterpret_cast<const uint4*>(d.nsrc == 2 ? d.src_lo[1] : d.src_lo[0]);
   a.out_lo = reinterpret_cast<uint4*>(d.out_lo);
-  dim3 grid((d.HW + GN_SLAB - 1) / GN_SLAB, d.B);
+  // pixels per CTA: every CTA first reduces the partial sums to mean / rstd (a prologue of a few microseconds); more pixels per CTA
+  // shrink its share: 4.14 (128 everywhere) -> 3.97 (256) -> 3.93 ms (512) per 2048-image forward, run 34 (DMC_GN_APPLY_SLAB
+  // overrides, for A/B runs)
+  static const int slab_env = [] {
+    const char* e = getenv("DMC_GN_APPLY_SLAB");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 32 && v <= 4096) ? v : 0;
+  }();
+  a.slab = slab_env ? slab_env : (d.HW >= 1024 ? 512 : (d.HW >= 256 ? 256 : GN_SLAB));
+  dim3 grid((d.HW + a.slab - 1) / a.slab, d.B);
   if (lo) gn_apply_kernel<true><<<grid, 256, 0, st>>>(a);
   else gn_apply_kernel<false><<<grid, 256, 0, st>>>(a);
   DMC_CUDA_OK(cudaGetLastError());
