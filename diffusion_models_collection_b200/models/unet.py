@@ -577,7 +577,7 @@ class UNet(nn.Module):
         native handles and device pointers -- a copy starts without them and rebuilds them on its first forward"""
         st = self.__dict__.copy()
         st.update(_plans={}, _train_engines={}, _plist=None, _packed=None, _packed_version=None, _packed_ids=None,
-                  _grad_allreduce=None, _dmc_graph_token=None)
+                  _grad_allreduce=None, _ddp_sentinel=None, _dmc_graph_token=None)
         return st
 
     def parameters(self, recurse: bool = True):
