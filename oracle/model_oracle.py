@@ -130,7 +130,8 @@ def dit_forward(sd, cfg, x, t, y=None, num_classes=None):
     c = F.linear(_dit_time_embedding(t), sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])
     c = F.linear(F.silu(c), sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"])
     if num_classes is not None and y is not None:
-        c = c + F.embedding(torch.clamp(y, 0, num_classes), sd["y_embedder.embedding_table.weight"])
+        # padding_idx = 0 (models/dit.py:62): same forward, and under autograd the null row receives no gradient
+        c = c + F.embedding(torch.clamp(y, 0, num_classes), sd["y_embedder.embedding_table.weight"], padding_idx=0)
     sc = F.silu(c)
     hd = hs // nh
     for i in range(cfg["depth"]):
@@ -178,7 +179,7 @@ def dim_forward(sd, cfg, x, t, y=None, num_classes=None):
     c = F.linear(_dit_time_embedding(t), sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])
     c = F.linear(F.silu(c), sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"])
     if num_classes is not None and y is not None:
-        c = c + F.embedding(torch.clamp(y, 0, num_classes), sd["y_embedder.embedding_table.weight"])
+        c = c + F.embedding(torch.clamp(y, 0, num_classes), sd["y_embedder.embedding_table.weight"], padding_idx=0)
     sc = F.silu(c)
     for i in range(cfg["depth"]):
         m, f = f"blocks.{i}.mamba_block", f"blocks.{i}.ff_block"

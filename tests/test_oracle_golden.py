@@ -202,6 +202,39 @@ def test_oracle_training_gradients_match_the_reference(golden, name):
         assert float(grads[names.index("label_embed.weight")][0].abs().max()) == 0.0 and row0 is not None
 
 
+@pytest.mark.parametrize("name", ["dit_cond_b3", "dit_uncond_b2"])
+def test_oracle_dit_training_gradients_match_the_reference(golden, name):
+    """the DiT training fixture (train_dit_golden.npz, the reference's own DDPM.p_losses(DiT, ...).backward(), eval mode) against
+    autograd through the oracle's restatement of models/dit.py:263-295: pins the oracle's DiT backward as well"""
+    from tests.golden_cases import TRAIN_DIT_CASES, sample_index, train_inputs
+
+    c, g = TRAIN_DIT_CASES[name], golden["train_dit"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.make_dit_state_dict(synth.CIFAR_DIT, c["num_classes"], seed=c["wseed"]).items()}
+    x0, t, y, noise = train_inputs(c)
+    tb = so.make_tables()
+    fwd = getattr(model_oracle.dit_forward, "__wrapped__", model_oracle.dit_forward)
+    eps = fwd(sd, synth.CIFAR_DIT, so.q_sample(tb, x0, t, noise), t, y, c["num_classes"])
+    loss = torch.nn.functional.mse_loss(noise, eps)
+    assert abs(loss.item() - float(g[name + "/loss"])) < 5e-6
+    names = [str(n) for n in g[name + "/names"]]
+    assert names == list(sd)
+    grads = torch.autograd.grad(loss, [sd[n] for n in names])
+    norms = g[name + "/norms"]
+    total = float(np.sqrt((norms ** 2).sum()))
+    for i, (n, gr) in enumerate(zip(names, grads)):
+        assert abs(float(gr.double().norm()) - norms[i]) <= 5e-5 * norms[i] + 1e-7 * total, n
+        flat = gr.reshape(-1)
+        key = f"{name}/full/{n}"
+        if key in g.files:
+            assert rel_l2(flat, g[key]) < 5e-5 or norms[i] < 1e-6 * total, n
+        else:
+            want = g[f"{name}/sample/{n}"]
+            got = flat[torch.from_numpy(sample_index(flat.numel()))]
+            assert float((got - torch.from_numpy(want)).abs().max()) <= 5e-5 * float(np.abs(want).max()) + 1e-6 * norms[i] / gr.numel() ** 0.5, n
+    if c["num_classes"]:
+        assert float(grads[names.index("y_embedder.embedding_table.weight")][0].abs().max()) == 0.0  # padding row
+
+
 def test_config1_b16_oracle_matches_reference_golden():
     """BASELINE configs[0] at its own batch size: the restatement's eps for the 16 images of the reference's first DDIM step (synth
     weights seed 42, checksums stored next to the golden)"""
