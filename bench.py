@@ -687,6 +687,12 @@ def roofline_leg(net, dev, nb, pk, ops_out, cfg=True, step_ms=None, chunks=1):
         if f["flops"] > 0 and k in ("conv", "attention", "gemm"):
             e["tflops"] = round(f["flops"] / (f["ms"] / 1e3) / 1e12, 2)
             e["frac_tensor"] = round(e["tflops"] / peak, 4)
+            if k == "attention" and f["bytes"] > 0:
+                # head dim 64: 128 FLOP per HBM byte at L = 256, half the chip's ridge -> the attention core is HBM-bound and
+                # its roofline fraction is the bandwidth one ("Attention")
+                e["gbs"] = round(f["bytes"] / (f["ms"] / 1e3) / 1e9, 1)
+                e["frac_hbm"] = round(e["gbs"] / pk["hbm_gbs"], 4)
+                e["bound"] = "hbm"
         else:
             e["gbs"] = round(f["bytes"] / (f["ms"] / 1e3) / 1e9, 1)
             e["frac_hbm"] = round(e["gbs"] / pk["hbm_gbs"], 4)
